@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LJ force + neighbour-list hot path on B200.
+
+Contract (one JSON line on stdout, rank 0):
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Workload (BASELINE.json configs[2]): synthetic jittered FCC lattice, rho = 1.0, 63 cells per
+side -> N = 1,000,188 atoms, cutoff 3.0 sigma, search 3.3 sigma, FP64, full (directed) Verlet
+list rebuilt ON THE GPU every 20 steps.  A "step" is one force/momentum-update pass over the
+whole list; every 20th step also pays one list rebuild.  metric = directed pair interactions
+per second = (list entries consumed per step) * steps / time.
+
+  value      inputs resident in HBM, CUDA-event timed on the launching stream.
+  e2e        the same metric through the reference-facing call lj_measure() (the reference's
+             measure(): upload q,p from pinned HOST buffers -> list build -> K steps ->
+             download p), wall clock of the call, copies inside the timed region.
+  roofline   force kernel alone: algorithmic bytes B = 4*P + N*(S_q + 2*S_p + 8|12) per launch
+              / mean launch duration measured live with CUDA events; peak from
+             MEASURED_PEAKS.json.
+  cpu_baseline  the REAL reference (cpu_ref/force_soa.cpp via oracle/_ref) on this box's host,
+             1 core (the reference is serial), on a bounded sample (rho=1.0, L=50).
+
+With N > 1 (torchrun) the lattice is split into z-slabs, one per rank; ghost positions are
+exchanged every step over NVLink (see lj_gpu_b200/decomp.py) and value aggregates all ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REBUILD_EVERY = 20
+METRIC = "pair_interactions_per_s"
+UNIT = "pairs/s"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(pn, pairs, s_vec=32, ptr_bytes=4):
+    """list read once, q read once, p read+written once, nop+pointer read once."""
+    return 4 * pairs + pn * (s_vec + 2 * s_vec + 4 + ptr_bytes)
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_reference_sample(steps_force=20, L=50.0):
+    """The real reference on the host: one makepair()+sortpair() and `steps_force` x
+    force_sorted() at rho=1.0, L=50 (N=119,164): one rebuild period of the bench cadence."""
+    from oracle import ljoracle as lo
+    if lo.have_ref(1.0):
+        ref = lo.Ref(1.0, L)
+        t0 = time.perf_counter()
+        nop, ptr, lst = ref.makepair()
+        t_list = time.perf_counter() - t0
+        ref.zero_p()
+        t0 = time.perf_counter()
+        ref.force("sorted", steps_force)
+        t_force = time.perf_counter() - t0
+        return dict(kind="reference", pn=ref.pn, pairs_half=len(lst), t_list=t_list, t_force=t_force,
+                    steps=steps_force, cores=1,
+                    what="cpu_ref/force_soa.cpp makepair()+sortpair() once + %d x force_sorted(), "
+                         "rho=1.0 L=50 N=%d, 1 thread (the reference is serial)" % (steps_force, ref.pn))
+    # prebuilt reference missing: fall back to the C restatement of the same loops
+    import numpy as np
+    o = lo.Oracle()
+    q = o.init_fcc(1.0, L)
+    o.set_num_threads(1)
+    t0 = time.perf_counter()
+    nop, ptr, lst = o.makepair(q, full=False, brute=True)
+    t_list = time.perf_counter() - t0
+    p = np.zeros_like(q)
+    t0 = time.perf_counter()
+    o.force_sorted(q, p, nop, ptr, lst, steps=steps_force)
+    t_force = time.perf_counter() - t0
+    return dict(kind="port", pn=len(q), pairs_half=len(lst), t_list=t_list, t_force=t_force,
+                steps=steps_force, cores=1,
+                what="oracle/lj_oracle.c brute-force makepair once + %d x force_sorted, rho=1.0 L=50 "
+                     "N=%d, 1 thread" % (steps_force, len(q)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # K steps of the bench cadence on the sample: K force steps + ceil(K/20) list builds.  The
+    # reference's O(N^2) makepair takes ~15 s on the sample, so it is timed ONCE and charged per
+    # scheduled rebuild; the force loop is timed on min(K, 40) steps and scaled.
+    k_force = max(1, min(args.steps, 40))
+    r = cpu_reference_sample(k_force)
+    per_step = r["t_force"] / r["steps"]
+    builds = (args.steps + REBUILD_EVERY - 1) // REBUILD_EVERY
+    total = per_step * args.steps + builds * r["t_list"]
+    pairs_directed = 2 * r["pairs_half"]
+    value = pairs_directed * args.steps / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": "FCC rho=1.0 cutoff=3.0 search=3.3 full-list-equivalent pairs, "
+                               "list rebuild every 20 steps; CPU sample L=50 N=%d" % r["pn"],
+                   "rebuild_every": REBUILD_EVERY},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["what"] + "; force loop timed on %d steps (%.3f s), makepair timed "
+                                   "once (%.2f s) and charged %d times" % (r["steps"], r["t_force"], r["t_list"], builds),
+                         "force_only_pairs_per_s": pairs_directed / per_step,
+                         "ms_per_force_step": 1e3 * per_step, "s_per_list_build": r["t_list"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from lj_gpu_b200 import LJContext, init_fcc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from lj_gpu_b200 import decomp
+        return decomp.bench_decomposed(args, METRIC, UNIT, REBUILD_EVERY, ClockSampler, measured_peak_gbs,
+                                       algorithmic_bytes)
+    torch.cuda.set_device(local)
+    ctx = LJContext(local)
+    stream = torch.cuda.current_stream()
+    K, W = args.steps, max(args.warmup, 3)
+
+    q = init_fcc(args.density, args.L)
+    pn = q.shape[0]
+    q4 = np.zeros((pn, 4)); q4[:, :3] = q
+    qd = torch.from_numpy(q4).cuda()
+    pd = torch.zeros_like(qd)
+    pl = ctx.makepair(qd, pointer64=False)
+    P = pl.number_of_pairs
+    fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
+               threads_per_block=args.threads_per_block)
+
+    def step_block(n0, n):
+        """steps n0 .. n0+n-1 of the cadence: rebuild at multiples of REBUILD_EVERY"""
+        s = n0
+        while s < n0 + n:
+            if s % REBUILD_EVERY == 0:
+                ctx.rebuild(qd, pl)
+            m = min(REBUILD_EVERY - s % REBUILD_EVERY, n0 + n - s)
+            ctx.force_loop(qd, pd, pl, loop=m, **fkw)
+            s += m
+
+    # ---- warm-up, then the timed region: EXACTLY K steps between two events
+    step_block(0, W)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.3)
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    step_block(0, K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    launches = ctx.launches - l0
+    ms = e0.elapsed_time(e1)
+
+    # ---- roofline leg: the force kernel alone, live CUDA events, list (564 MB) >> L2
+    nf = max(20, min(K, 200))
+    ctx.force_loop(qd, pd, pl, loop=3, **fkw)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    ctx.force_loop(qd, pd, pl, loop=nf, **fkw)
+    f1.record(stream)
+    torch.cuda.synchronize()
+    ms_force = f0.elapsed_time(f1) / nf
+    # ---- one list rebuild alone
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for _ in range(5):
+        ctx.rebuild(qd, pl)
+    b1.record(stream)
+    torch.cuda.synchronize()
+    ms_build = b0.elapsed_time(b1) / 5
+    clocks = sampler.finish()
+
+    # ---- e2e: the plugin call on pinned HOST buffers (the reference's measure())
+    qh = torch.from_numpy(q4).pin_memory()
+    ph = torch.zeros_like(qh).pin_memory()
+    ctx.measure(qh.numpy(), ph.numpy(), layout="aos4", loop=min(K, REBUILD_EVERY), rebuild_every=REBUILD_EVERY, **fkw)
+    ph.zero_()
+    m = ctx.measure(qh.numpy(), ph.numpy(), layout="aos4", loop=K, rebuild_every=REBUILD_EVERY, **fkw)
+    e2e_value = P * K / m.seconds_total
+    checksum = float(ph.numpy()[:, :3].sum())
+
+    peak, peak_src = measured_peak_gbs()
+    bytes_force = algorithmic_bytes(pn, P)
+    achieved = bytes_force / (ms_force * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    out = {
+        "metric": METRIC, "value": P * K / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if args.prec == "fp64" else "f32-mixed",
+        "data": "synthetic",
+        "config": {"workload": "synthetic FCC lattice N=%d rho=%.1f cutoff=3.0 search=3.3, full list %d "
+                               "directed pairs, on-GPU list rebuild every %d steps" % (pn, args.density, P, REBUILD_EVERY),
+                   "layout": "aos_double4", "variant": args.variant, "group": args.group,
+                   "l2": "inputs larger than L2 (list %.0f MB per step vs 126 MB L2)" % (4 * P / 1e6),
+                   "rebuild_every": REBUILD_EVERY},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m.h2d_bytes / K,
+                "d2h_bytes_per_step": m.d2h_bytes / K, "seconds_total": m.seconds_total,
+                "seconds_kernel": m.seconds_kernel, "list_builds": m.list_builds,
+                "call": "lj_measure(): pinned host q,p -> H2D -> GPU list build -> K steps (rebuild "
+                        "every 20) -> D2H p", "p_checksum": checksum},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "force step (lj_gather_*)", "algorithmic_bytes_per_launch": bytes_force,
+                     "ms_per_launch": ms_force, "pairs_per_s_force_only": P / (ms_force * 1e-3),
+                     "list_build_ms": ms_build,
+                     "amortised_step_ms": ms_force + ms_build / REBUILD_EVERY},
+    }
+    if not args.no_cpu:
+        r = cpu_reference_sample(20)
+        t = r["t_force"] + r["t_list"]
+        out["cpu_baseline"] = {
+            "value": 2 * r["pairs_half"] * r["steps"] / t, "unit": UNIT, "cores": r["cores"],
+            "kind": r["kind"], "sample": r["what"],
+            "force_only_pairs_per_s": 2 * r["pairs_half"] * r["steps"] / r["t_force"],
+            "ms_per_force_step": 1e3 * r["t_force"] / r["steps"], "s_per_list_build": r["t_list"]}
+    print(json.dumps(out), flush=True)
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--density", type=float, default=1.0)
+    ap.add_argument("--L", type=float, default=100.1, help="box edge; 100.1 -> 63 cells/side -> N=1,000,188")
+    ap.add_argument("--variant", default="auto")
+    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--prec", default="fp64", choices=["fp64", "mixed"])
+    ap.add_argument("--threads-per-block", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

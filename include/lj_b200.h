@@ -1,0 +1,268 @@
+/*
+ * lj_b200.h -- C ABI of the B200-native Lennard-Jones force + neighbour-list path.
+ *
+ * This is the drop-in boundary for the ONE hot path of kohnakagawa/lj_gpu: the kernel launch
+ * inside measure() (cuda/force_cuda.cu:334) and the neighbour-list build that feeds it
+ * (cuda/force_cuda.cu:122-163).  Every entry point names the reference interface it replaces.
+ * Plain pointers and sizes only; all device work is asynchronous on the caller's stream
+ * (a cudaStream_t passed as void*, NULL = the context's own stream).  No function exits the
+ * process: each returns an lj_status and leaves a message in lj_last_error_string().
+ *
+ * Ownership: the caller owns every array it passes (as the reference driver owns its
+ * cuda_ptr globals, cuda/force_cuda.cu:24-30).  The library owns its context, streams,
+ * memory pool and scratch (cell tables, staging ring).  It keeps no hidden copy of p.
+ */
+#ifndef LJ_B200_H
+#define LJ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LJ_API __attribute__((visibility("default")))
+
+typedef struct lj_ctx lj_ctx;
+
+/* reference: checkCudaErrors -> message + exit(EXIT_FAILURE) (cuda/cuda_ptr.cuh:39-73);
+ * here: a status code, the driver decides whether to exit. */
+typedef enum lj_status {
+  LJ_OK = 0,
+  LJ_ERR_CUDA = 1,         /* a CUDA runtime call or kernel launch failed            */
+  LJ_ERR_BAD_ARG = 2,      /* null pointer, negative size, unknown enum, misalignment */
+  LJ_ERR_CAPACITY = 3,     /* sorted_list / ELL capacity too small (nothing written OOB) */
+  LJ_ERR_OVERFLOW32 = 4,   /* list offsets do not fit the int32 pointer[] requested   */
+  LJ_ERR_NO_DEVICE = 5,    /* no CUDA device: there is NO CPU fallback                */
+  LJ_ERR_INVALID_LIST = 6  /* lj_validate_list found an out-of-range entry            */
+} lj_status;
+
+/* Particle-vector layout of q and p.  Reference: template parameter Vec of every kernel
+ * (cuda/kernel.cuh:5), instantiated for double3 and double4 (cuda/force_cuda.cu:355-375);
+ * SoA is the cpu_ref / OpenACC layout (cpu_ref/force_soa.cpp:15-18,
+ * openacc/force_oacc_soa.cpp:17-22); float4 buffers exist but are never timed
+ * (cuda/force_cuda.cu:24-25). */
+typedef enum lj_layout {
+  LJ_AOS_D3 = 0, /* packed {x,y,z} doubles, 24 B stride                                   */
+  LJ_AOS_D4 = 1, /* {x,y,z,w} doubles, 32 B stride, 32 B aligned; .w ignored on read and
+                    preserved on the write of p                                          */
+  LJ_SOA_D = 2,  /* planes x[], y[], z[] of doubles: base + c*plane_stride + i            */
+  LJ_AOS_F4 = 3  /* {x,y,z,w} floats, 16 B stride (FP32 kernels only)                     */
+} lj_layout;
+
+/* Neighbour-list storage.  CSR = sorted_list + number_of_partners + pointer (no sentinel,
+ * cuda/force_cuda.cu:146-162); ELL = column-major transposed_list[i + k*pn], zero padded
+ * (cuda/force_cuda.cu:229-240), pointer unused (the reference passes nullptr, :430-436). */
+typedef enum lj_list_layout { LJ_LIST_CSR = 0, LJ_LIST_ELL = 1 } lj_list_layout;
+
+/* Thread mapping.  Replaces the choice among the 20 kernels of cuda/kernel.cuh. */
+typedef enum lj_variant {
+  LJ_VARIANT_AUTO = 0,      /* library picks per layout/list/precision                      */
+  LJ_VARIANT_SUBWARP = 1,   /* `group` lanes per i-particle (1,2,4,8,16,32); 32 = warp-per-i
+                               (kernel.cuh:821-904), 1 = thread-per-i (kernel.cuh:67-236)     */
+  LJ_VARIANT_TILE_TMA = 2,  /* CTA tile of rows, j-indices staged in shared memory by a TMA
+                               bulk copy, `group` lanes per i (CSR only)                     */
+  LJ_VARIANT_NEWTON3 = 3    /* half list, reaction scattered with FP64 atomics
+                               (the *_with_aar kernels, kernel.cuh:238-469)                  */
+} lj_variant;
+
+typedef enum lj_precision {
+  LJ_PREC_FP64 = 0,  /* all arithmetic FP64 (the reference's Dtype = double)                */
+  LJ_PREC_MIXED = 1  /* FP32 pair arithmetic on origin-shifted coordinates, FP64 accumulation */
+} lj_precision;
+
+/* ---------------------------------------------------------------- context ------------- */
+/* Creates a context on `device` (a CUDA ordinal).  LJ_ERR_NO_DEVICE when CUDA is absent. */
+LJ_API int lj_ctx_create(lj_ctx** out, int device);
+LJ_API int lj_ctx_destroy(lj_ctx* ctx);
+/* replaces cudaDeviceSynchronize() in measure() (cuda/force_cuda.cu:336); stream NULL =
+ * every stream the context owns */
+LJ_API int lj_sync(lj_ctx* ctx, void* stream);
+LJ_API const char* lj_last_error_string(lj_ctx* ctx);
+LJ_API const char* lj_status_string(int status);
+/* number of kernels this library has launched through `ctx` since creation */
+LJ_API int64_t lj_launch_count(lj_ctx* ctx);
+/* the context's own non-blocking stream (a cudaStream_t) */
+LJ_API void* lj_ctx_stream(lj_ctx* ctx);
+LJ_API int lj_device_sm_count(lj_ctx* ctx);
+
+/* ---------------------------------------------------------------- memory layer -------- */
+/* Replaces cuda_ptr<T> (cuda/cuda_ptr.cuh:10-104): a device allocation paired with a
+ * pinned host mirror.  Device memory comes from a stream-ordered pool (cudaMallocAsync)
+ * sized by the request, not by a static maximum. */
+typedef struct lj_buf {
+  void* host;   /* pinned (cuda_ptr::host_ptr, operator[])  */
+  void* dev;    /* device (cuda_ptr::dev_ptr, operator T*)  */
+  size_t bytes;
+} lj_buf;
+
+LJ_API int lj_buf_allocate(lj_ctx* ctx, size_t bytes, lj_buf* out, void* stream);   /* allocate()   */
+LJ_API int lj_buf_deallocate(lj_ctx* ctx, lj_buf* buf, void* stream);               /* deallocate() */
+/* host2dev(beg,count) / host2dev_async: byte range [beg, beg+count) */
+LJ_API int lj_buf_host2dev(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, void* stream);
+LJ_API int lj_buf_dev2host(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, void* stream);
+/* set_val(beg,count,val) for 4-byte elements: fills host mirror and device range */
+LJ_API int lj_buf_set_val32(lj_ctx* ctx, const lj_buf* buf, size_t beg_elems, size_t count_elems,
+                     uint32_t value, void* stream);
+/* raw stream-ordered device allocation for callers that keep their own host arrays */
+LJ_API int lj_dev_alloc(lj_ctx* ctx, size_t bytes, void** out, void* stream);
+LJ_API int lj_dev_free(lj_ctx* ctx, void* ptr, void* stream);
+/* pageable host memory <-> device through the context's pinned double-buffered staging ring
+ * (chunked, copy of chunk k+1 into the ring overlaps the DMA of chunk k) */
+LJ_API int lj_upload(lj_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes, void* stream);
+LJ_API int lj_download(lj_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, void* stream);
+
+/* ---------------------------------------------------------------- force step ---------- */
+/* Replaces the launch
+ *   kernel<<<block_num, THREAD_BLOCK>>>(q, p, particle_number, dt, CL2, list,
+ *                                       number_of_partners, partner_pointer)
+ * (cuda/force_cuda.cu:334; kernel signature cuda/kernel.cuh:5-13).  In place:
+ *   p[i] += dt * sum_k f(r_ik) * (q[j_k] - q[i]),  f = (24 r^6 - 48)/r^14, masked to 0
+ *   where r^2 > cl2.
+ * q is read-only.  Rows may be in any order (the reference shuffles them,
+ * cuda/force_cuda.cu:255-263).  All pointers are DEVICE pointers. */
+typedef struct lj_force_args {
+  const void* q;
+  void* p;
+  int64_t pn;                        /* particle_number                                    */
+  double dt;
+  double cl2;                        /* CL2 = cutoff^2                                     */
+  const int32_t* list;               /* sorted_list (CSR) or transposed_list (ELL)         */
+  const int32_t* number_of_partners;
+  const void* pointer;               /* int32[pn] or int64[pn] (pointer64); NULL for ELL   */
+  int32_t layout;                    /* lj_layout of q and p                               */
+  int32_t list_layout;               /* lj_list_layout                                     */
+  int32_t variant;                   /* lj_variant                                         */
+  int32_t group;                     /* lanes per i-particle, 0 = default for the variant  */
+  int32_t precision;                 /* lj_precision                                       */
+  int32_t pointer64;                 /* 0: pointer is int32[], 1: int64[]                  */
+  int32_t threads_per_block;         /* THREAD_BLOCK (CLI argv[1], 64..1024); 0 = default  */
+  int32_t reserved;
+  int64_t plane_stride;              /* LJ_SOA_D: doubles between planes (>= pn)           */
+  int64_t row_begin, row_end;        /* update only rows [row_begin,row_end); 0,0 = all    */
+  int64_t list_entries;              /* optional: entries allocated in `list` (number_of_pairs);
+                                        0 = unknown.  Lets LJ_VARIANT_TILE_TMA round its bulk
+                                        copies up to 16 bytes without reading past the array */
+} lj_force_args;
+
+LJ_API int lj_force_step(lj_ctx* ctx, const lj_force_args* args, void* stream);
+/* `loop` back-to-back steps, the body of measure() (cuda/force_cuda.cu:333-335).  With
+ * use_graph != 0 the steps are captured once into a CUDA graph and replayed. */
+LJ_API int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int use_graph, void* stream);
+
+/* ---------------------------------------------------------------- list build ---------- */
+/* Replaces makepair() + register_pair() (cuda/force_cuda.cu:102-163) with an O(N) on-GPU
+ * build: cell binning (counting sort) -> 27-cell stencil search -> prefix scan -> fill.
+ * Semantics of the reference: open boundaries, listed iff r2 < search_len^2 (strict) with
+ * r2 = fma(dz,dz,fma(dy,dy,dx*dx)) in FP64; full: every ordered pair i != j; half: i < j.
+ * Output in the caller's numbering: number_of_partners[i], pointer = exclusive scan (pn
+ * entries, no sentinel), sorted_list rows in a deterministic but unspecified order (or
+ * ascending j with LJ_LIST_SORT_ROWS, which is what makepair() produces). */
+enum { LJ_LIST_SORT_ROWS = 1 };
+
+typedef struct lj_list_args {
+  const void* q;                /* device, layout below (FP64 layouts only)               */
+  int64_t pn;
+  int32_t layout;
+  int32_t half;                 /* 0 full list, 1 half list (EN_ACTION_REACTION build)    */
+  int64_t plane_stride;
+  double search_len;            /* SEARCH_LENGTH (3.3)                                    */
+  int32_t* number_of_partners;  /* out, device int32[pn]                                  */
+  void* pointer;                /* out, device int32[pn] or int64[pn]                     */
+  int32_t* sorted_list;         /* out, device int32[capacity]                            */
+  int64_t capacity;             /* entries available in sorted_list                       */
+  int32_t pointer64;
+  int32_t flags;
+  int64_t row_begin, row_end;   /* build rows only for i in [row_begin,row_end); 0,0=all;
+                                   all pn particles are neighbour candidates (ghosts)     */
+} lj_list_args;
+
+/* number_of_pairs_out (host, may be NULL): total entries; when non-NULL the call
+ * synchronises the stream and returns LJ_ERR_CAPACITY (with the needed total stored) or
+ * LJ_ERR_OVERFLOW32 instead of writing out of bounds (the reference silently overruns,
+ * cuda/force_cuda.cu:102-120).  With NULL the call stays asynchronous; query later with
+ * lj_list_result(). */
+LJ_API int lj_build_list(lj_ctx* ctx, const lj_list_args* args, int64_t* number_of_pairs_out,
+                  void* stream);
+/* status + totals of the most recent lj_build_list on this context (synchronises `stream`) */
+LJ_API int lj_list_result(lj_ctx* ctx, int64_t* number_of_pairs_out, int32_t* max_partners_out,
+                   void* stream);
+
+/* Replaces make_transposed_pairlist() (cuda/force_cuda.cu:229-240): CSR -> column-major
+ * ELL with stride pn, zero padding up to max_partners rows.  capacity_entries must be
+ * >= max_partners*pn (LJ_ERR_CAPACITY otherwise; max_partners_out tells how many). */
+LJ_API int lj_build_ell(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* number_of_partners,
+                 const void* pointer, int32_t pointer64, int64_t pn, int32_t* transposed_list,
+                 int64_t capacity_entries, int32_t* max_partners_out, void* stream);
+
+/* Replaces random_shfl() (cuda/force_cuda.cu:255-263) in spirit: a deterministic per-row
+ * permutation on the device (NOT the same permutation as std::shuffle), to prove kernels do
+ * not depend on row order. */
+LJ_API int lj_shuffle_rows(lj_ctx* ctx, int32_t* sorted_list, const int32_t* number_of_partners,
+                    const void* pointer, int32_t pointer64, int64_t pn, uint32_t seed,
+                    void* stream);
+
+/* Replaces check_loadedpair() (cuda/force_cuda.cu:183-201) on the device: 0 <= np < pn,
+ * 0 <= pointer[i] <= number_of_pairs, 0 <= sorted_list[k] < pn.  Synchronises. */
+LJ_API int lj_validate_list(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* number_of_partners,
+                     const void* pointer, int32_t pointer64, int64_t pn, int64_t number_of_pairs,
+                     void* stream);
+
+/* ---------------------------------------------------------------- host helpers -------- */
+/* Replaces init() + add_particle() (cuda/force_cuda.cu:47-94): jittered FCC lattice, one
+ * std::mt19937(2) stream, U(0,0.1) per coordinate, iz->iy->ix->basis order.  HOST function:
+ * writes packed xyz doubles.  Returns the particle count, or -(needed) if cap is too small. */
+LJ_API int64_t lj_init_fcc(double density, double L, double* q_xyz_host, int64_t cap_particles,
+                    int32_t* cells_per_side_out);
+/* same lattice generated on the device for sizes where a host loop is too slow is NOT
+ * offered: the generator is sequential by definition (one RNG stream). */
+
+/* The reference's whole measure() (cuda/force_cuda.cu:319-342) as one call on HOST arrays:
+ * upload q and p, build the neighbour list on the GPU (or upload the caller's), run `loop`
+ * force steps rebuilding the list every `rebuild_every` steps (0 = never), download p.
+ * This is the call bench.py times for its end-to-end number. */
+typedef struct lj_measure_args {
+  const void* q_host;
+  void* p_host;                 /* in/out                                                 */
+  int64_t pn;
+  int32_t layout;
+  int32_t half;                 /* 1: Newton-3 path on a half list                        */
+  int64_t plane_stride;
+  double dt, cl2, search_len;
+  int32_t loop;                 /* LOOP (100)                                             */
+  int32_t rebuild_every;        /* list rebuild cadence in steps; 0 = build once          */
+  int32_t variant, group, precision, threads_per_block;
+  int32_t use_graph;
+  int32_t list_flags;
+  /* optional caller-provided CSR list on the host (the reference uploads its host-built
+   * list in copy_to_gpu, cuda/force_cuda.cu:302-312); NULL = build on the GPU */
+  const int32_t* list_host;
+  const int32_t* number_of_partners_host;
+  const int32_t* pointer_host;
+  int64_t number_of_pairs_in;
+  /* outputs */
+  int64_t number_of_pairs;      /* entries of the list the kernels consumed               */
+  int32_t max_partners;
+  int32_t list_builds;          /* how many GPU list builds ran                           */
+  double seconds_total;         /* wall clock incl. H<->D (first stderr line of measure()) */
+  double seconds_kernel;        /* "without Host<->Device" (second stderr line)           */
+  int64_t h2d_bytes, d2h_bytes;
+} lj_measure_args;
+
+LJ_API int lj_measure(lj_ctx* ctx, lj_measure_args* args);
+
+/* ---------------------------------------------------------------- multi-GPU helpers --- */
+/* z-slab decomposition support (no reference counterpart: the reference is single-GPU).
+ * Peer access by CUDA IPC: export a handle for a device allocation, open a peer's. */
+LJ_API int lj_ipc_export(lj_ctx* ctx, void* dev_ptr, uint8_t handle_out[64]);
+LJ_API int lj_ipc_open(lj_ctx* ctx, const uint8_t handle[64], void** peer_ptr_out);
+LJ_API int lj_ipc_close(lj_ctx* ctx, void* peer_ptr);
+/* Halo pull: copy `bytes` (multiple of 16) from a peer-mapped pointer into local memory
+ * with a grid of 16-byte P2P loads over NVLink. */
+LJ_API int lj_halo_pull(lj_ctx* ctx, void* local_dst, const void* peer_src, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LJ_B200_H */

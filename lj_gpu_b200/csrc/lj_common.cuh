@@ -1,0 +1,215 @@
+// lj_common.cuh -- context, error plumbing and device helpers shared by the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/lj_b200.h"
+
+// ------------------------------------------------------------------------------------
+// Context.  One per host thread / GPU; no global state (SURVEY 8b "Threading").
+// ------------------------------------------------------------------------------------
+struct lj_list_totals {      // written by the list-build kernels, read back on demand
+  unsigned long long total;  // entries of the list
+  int max_np;                // longest row
+  int overflow;              // bit0: capacity, bit1: int32 pointer overflow
+};
+
+struct lj_grid_params {  // cell grid derived ON THE DEVICE from the bounding box
+  double ox, oy, oz;     // origin (min corner)
+  double inv_cell;       // 1 / cell edge
+  int nx, ny, nz;
+  int ncell;
+};
+
+struct lj_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;       // the context's own stream
+  cudaStream_t copy_stream = nullptr;  // staging-ring DMA
+  cudaMemPool_t pool = nullptr;
+  int64_t launches = 0;
+  std::string err;
+
+  // pinned staging ring for pageable host memory (lj_upload / lj_download)
+  void* ring[2] = {nullptr, nullptr};
+  cudaEvent_t ring_ev[2] = {nullptr, nullptr};
+  size_t ring_bytes = 0;
+
+  // list-build scratch, grow-only
+  int64_t scratch_pn = 0;
+  int64_t scratch_cells = 0;
+  double* bbox = nullptr;            // 6 ordered-encoded doubles (as uint64)
+  lj_grid_params* grid = nullptr;    // device
+  int32_t* cell_of = nullptr;        // [pn] cell id of each particle
+  int32_t* cell_slot = nullptr;      // [pn] arrival slot inside its cell
+  uint32_t* cell_count = nullptr;    // [cells+1]
+  uint32_t* cell_start = nullptr;    // [cells+1]
+  double4* sorted_pos = nullptr;     // [pn] positions in cell order, .w = original index bits
+  int32_t* sorted_tmp = nullptr;     // [pn] particle ids in arrival order
+  unsigned long long* scan_tmp = nullptr;  // block sums for the scans
+  int64_t scan_tmp_len = 0;
+  lj_list_totals* totals = nullptr;  // device
+  lj_list_totals* totals_host = nullptr;  // pinned
+  int64_t last_capacity = 0;
+
+  // mixed-precision scratch: origin-shifted float4 positions
+  float4* q32 = nullptr;
+  int64_t q32_len = 0;
+
+  // cached CUDA graph for lj_force_loop
+  cudaGraphExec_t graph_exec = nullptr;
+  lj_force_args graph_args{};
+  int graph_loop = 0;
+  int64_t graph_step_launches = 0;
+};
+
+int lj_set_error(lj_ctx* ctx, int status, const char* what, const char* detail);
+
+#define LJ_CUDA(ctx, call)                                                            \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) return lj_set_error((ctx), LJ_ERR_CUDA, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define LJ_REQUIRE(ctx, cond, msg)                                         \
+  do {                                                                     \
+    if (!(cond)) return lj_set_error((ctx), LJ_ERR_BAD_ARG, msg, #cond);   \
+  } while (0)
+
+// every kernel launch goes through this so gpu_launches can be reported truthfully
+#define LJ_LAUNCHED(ctx)                                                                  \
+  do {                                                                                    \
+    (ctx)->launches++;                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) return lj_set_error((ctx), LJ_ERR_CUDA, "kernel launch", cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline cudaStream_t lj_stream(lj_ctx* ctx, void* s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+// internal entry points shared between translation units
+int lj_scratch_reserve(lj_ctx* ctx, int64_t pn, cudaStream_t st);
+int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st);
+int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t plane,
+                   lj_list_totals* reset_totals, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------
+// Device helpers
+// ------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// order-preserving double <-> uint64 encoding (atomicMin/Max on doubles)
+__device__ __forceinline__ unsigned long long enc_ordered(double v) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_ordered(unsigned long long u) {
+  u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+  return __longlong_as_double((long long)u);
+}
+
+// 256-bit read-only load of one double4 (one 32 B sector): LDG.E.256 on sm_100a.
+__device__ __forceinline__ double4 ld_nc_d4(const double4* ptr) {
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ double4 ld_d4(const double4* ptr) {
+  double4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(ptr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_d4(double4* ptr, double4 v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(v.x), "d"(v.y), "d"(v.z),
+               "d"(v.w)
+               : "memory");
+}
+
+// Position fetch for the three FP64 layouts.
+template <int LAYOUT>
+__device__ __forceinline__ void load_pos(const void* __restrict__ q, int64_t i, int64_t plane,
+                                         double& x, double& y, double& z) {
+  if (LAYOUT == LJ_AOS_D4) {
+    const double4 v = ld_nc_d4(reinterpret_cast<const double4*>(q) + i);
+    x = v.x; y = v.y; z = v.z;
+  } else if (LAYOUT == LJ_AOS_D3) {
+    const double* b = reinterpret_cast<const double*>(q) + 3 * i;
+    x = __ldg(b); y = __ldg(b + 1); z = __ldg(b + 2);
+  } else {
+    const double* b = reinterpret_cast<const double*>(q) + i;
+    x = __ldg(b); y = __ldg(b + plane); z = __ldg(b + 2 * plane);
+  }
+}
+
+// p[i] += (fx,fy,fz); double4 keeps .w (read-modify-write of the whole 32 B vector, which
+// is what the reference's `p[tid] = pf` does, cuda/kernel.cuh:118,133).
+template <int LAYOUT>
+__device__ __forceinline__ void add_mom(void* __restrict__ p, int64_t i, int64_t plane, double fx,
+                                        double fy, double fz) {
+  if (LAYOUT == LJ_AOS_D4) {
+    double4* b = reinterpret_cast<double4*>(p) + i;
+    double4 v = ld_d4(b);
+    v.x += fx; v.y += fy; v.z += fz;
+    st_d4(b, v);
+  } else if (LAYOUT == LJ_AOS_D3) {
+    double* b = reinterpret_cast<double*>(p) + 3 * i;
+    b[0] += fx; b[1] += fy; b[2] += fz;
+  } else {
+    double* b = reinterpret_cast<double*>(p) + i;
+    b[0] += fx; b[plane] += fy; b[2 * plane] += fz;
+  }
+}
+
+// 1/a to ~1 ulp for normal positive a without the IEEE-division slow path:
+// MUFU.RCP64H seed (rel. err < 2^-20) + one cubically convergent correction (3 DFMA).
+__device__ __forceinline__ double fast_rcp(double a) {
+  double x0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
+  const double e = fma(-a, x0, 1.0);
+  const double e2 = fma(e, e, e);
+  return fma(x0, e2, x0);
+}
+
+// The FP64 pair body.  c24 = 24*dt, c48 = 48*dt (dt folded into the constants as
+// cpu_ref/force_soa.cpp:202-203 does).  df = (24 r^6 - 48) / r^14 * dt = x^4 (24dt - 48dt x^3)
+// with x = 1/r^2.  The cutoff test compares the bit patterns (positive doubles order like
+// integers), which keeps it off the FP64 pipe; pairs with r2 > cl2 contribute nothing,
+// r2 == cl2 contributes (cuda/kernel.cuh:30).
+__device__ __forceinline__ void lj_pair(double dx, double dy, double dz, double c24, double c48,
+                                        long long cl2_bits, double& fx, double& fy,
+                                        double& fz) {
+  const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+  const double x = fast_rcp(r2);
+  const double x3 = x * x * x;
+  const double t = fma(-c48, x3, c24);
+  // Mask the scalar, not the three products: ptxas turns a guarded accumulation into six
+  // FSELs per pair, masking df costs two (the reference's "ifless" form, kernel.cuh:59).
+  const double df = (__double_as_longlong(r2) <= cl2_bits) ? (x * x3) * t : 0.0;
+  fx = fma(df, dx, fx);
+  fy = fma(df, dy, fy);
+  fz = fma(df, dz, fz);
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+template <bool PTR64>
+__device__ __forceinline__ int64_t row_offset(const void* __restrict__ pointer, int64_t i) {
+  if (PTR64) return __ldg(reinterpret_cast<const long long*>(pointer) + i);
+  // int32 pointer[] of the reference; offsets above 2^31-1 cannot be represented there
+  return (int64_t)(uint32_t)__ldg(reinterpret_cast<const int*>(pointer) + i);
+}
+
+#endif  // __CUDACC__

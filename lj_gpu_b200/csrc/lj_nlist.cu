@@ -1,0 +1,696 @@
+// lj_nlist.cu -- on-GPU Verlet neighbour-list build (cell binning + stencil search + scan).
+//
+// Replaces makepair()/register_pair() (cuda/force_cuda.cu:102-163), an O(N^2) host loop that
+// materialises (i,j) pair arrays, with an O(N) device pipeline that never leaves the GPU:
+//
+//   bbox -> grid setup (device) -> cell id + arrival slot (atomics) -> scan(cell counts)
+//        -> scatter -> deterministic in-cell ordering -> COUNT pass (27-cell stencil)
+//        -> scan(number_of_partners) = pointer[] (64-bit inside) -> FILL pass
+//
+// Output contract = the reference's: number_of_partners[i], pointer[] (exclusive scan, pn
+// entries), sorted_list in the caller's numbering.  Membership is decided by the exact FP64
+// expression r2 = fma(dz,dz,fma(dy,dy,dx*dx)) < search^2 (same chain as oracle/lj_oracle.c);
+// an FP32 test on origin-shifted coordinates only pre-classifies candidates that are farther
+// than a rigorous error margin from the threshold.
+#include "lj_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ small utilities ---
+__global__ void k_bbox_init(unsigned long long* bb, lj_list_totals* tot) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = ~0ull;      // mins
+  else if (threadIdx.x < 6) bb[threadIdx.x] = 0ull;  // maxs
+  if (threadIdx.x == 0 && tot) { tot->total = 0; tot->max_np = 0; tot->overflow = 0; }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+k_bbox(const void* __restrict__ q, int64_t pn, int64_t plane, unsigned long long* bb) {
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pn;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double v[3];
+    load_pos<LAYOUT>(q, i, plane, v[0], v[1], v[2]);
+#pragma unroll
+    for (int d = 0; d < 3; d++) { lo[d] = fmin(lo[d], v[d]); hi[d] = fmax(hi[d], v[d]); }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+    for (int m = 16; m >= 1; m >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], m));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], m));
+    }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      atomicMin(bb + d, enc_ordered(lo[d]));
+      atomicMax(bb + 3 + d, enc_ordered(hi[d]));
+    }
+  }
+}
+
+struct grid_ext {  // lj_grid_params + the FP32 pre-filter margin, lives right behind it
+  lj_grid_params g;
+  float margin;    // |r2_f32 - r2_f64| bound for candidates within two cells
+  float sl2f;
+};
+
+__global__ void k_grid_setup(const unsigned long long* bb, double search_len, int64_t cap_cells,
+                             grid_ext* out) {
+  double lo[3], hi[3];
+  for (int d = 0; d < 3; d++) { lo[d] = dec_ordered(bb[d]); hi[d] = dec_ordered(bb[3 + d]); }
+  double edge = search_len * (1.0 + 1e-9);  // strictly larger: no neighbour two cells away
+  int n[3];
+  for (;;) {
+    double cells = 1.0;
+    for (int d = 0; d < 3; d++) {
+      double c = floor((hi[d] - lo[d]) / edge) + 1.0;
+      if (c > 2.0e9) c = 2.0e9;
+      n[d] = (int)c;
+      cells *= c;
+    }
+    if (cells <= (double)cap_cells) break;
+    edge *= 1.26;  // sparse cloud: coarser cells stay correct for a 27-cell stencil
+  }
+  out->g.ox = lo[0]; out->g.oy = lo[1]; out->g.oz = lo[2];
+  out->g.inv_cell = 1.0 / edge;
+  out->g.nx = n[0]; out->g.ny = n[1]; out->g.nz = n[2];
+  out->g.ncell = n[0] * n[1] * n[2];
+  // FP32 pre-filter error budget.  E = largest extent; a shifted coordinate rounds to float
+  // with error <= 2^-24 E, a float difference of two of them adds <= 2^-24 |d|, |d| <= 2 edge
+  // for stencil candidates.  r2 error <= sum_c (2|d| delta + delta^2) + rounding of the
+  // three multiply-adds.  Doubled for safety.
+  double E = fmax(hi[0] - lo[0], fmax(hi[1] - lo[1], hi[2] - lo[2]));
+  const double u = 5.9604644775390625e-8;  // 2^-24
+  double delta = 2.0 * u * E + u * 2.0 * edge;
+  double m = 3.0 * (4.0 * edge * delta + delta * delta) + 4.0 * u * 12.0 * edge * edge;
+  out->margin = (float)(2.0 * m);
+  out->sl2f = (float)(search_len * search_len);
+}
+
+__device__ __forceinline__ int cell_coord(double v, double o, double inv, int n) {
+  int c = (int)floor((v - o) * inv);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+k_cell_assign(const void* __restrict__ q, int64_t pn, int64_t plane, const grid_ext* __restrict__ ge,
+              int32_t* __restrict__ cell_of, int32_t* __restrict__ cell_slot,
+              uint32_t* __restrict__ cell_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  const lj_grid_params g = ge->g;
+  double x, y, z;
+  load_pos<LAYOUT>(q, i, plane, x, y, z);
+  const int cx = cell_coord(x, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(y, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(z, g.oz, g.inv_cell, g.nz);
+  const int c = (cz * g.ny + cy) * g.nx + cx;
+  cell_of[i] = c;
+  cell_slot[i] = (int32_t)atomicAdd(cell_count + c, 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_cell_scatter(int64_t pn, const int32_t* __restrict__ cell_of, const int32_t* __restrict__ cell_slot,
+               const uint32_t* __restrict__ cell_start, int32_t* __restrict__ sorted_tmp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  sorted_tmp[cell_start[cell_of[i]] + (uint32_t)cell_slot[i]] = (int32_t)i;
+}
+
+// Arrival order inside a cell depends on atomic timing; re-rank by original index so the
+// whole build is deterministic: rank = #members of my cell with a smaller index.
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+k_cell_order(const void* __restrict__ q, int64_t pn, int64_t plane, const grid_ext* __restrict__ ge,
+             const int32_t* __restrict__ cell_of, const uint32_t* __restrict__ cell_start,
+             const uint32_t* __restrict__ cell_count, const int32_t* __restrict__ sorted_tmp,
+             double4* __restrict__ sorted_pos, float4* __restrict__ sorted_pos32) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  const int c = cell_of[i];
+  const uint32_t b = cell_start[c], n = cell_count[c];
+  uint32_t rank = 0;
+  for (uint32_t m = 0; m < n; m++) rank += (sorted_tmp[b + m] < (int32_t)i) ? 1u : 0u;
+  double x, y, z;
+  load_pos<LAYOUT>(q, i, plane, x, y, z);
+  sorted_pos[b + rank] = make_double4(x, y, z, __longlong_as_double((long long)i));
+  const lj_grid_params g = ge->g;
+  sorted_pos32[b + rank] = make_float4((float)(x - g.ox), (float)(y - g.oy), (float)(z - g.oz),
+                                       __int_as_float((int)i));
+}
+
+// ------------------------------------------------------------------ prefix scans ------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v,
+                                                                   unsigned long long* total) {
+  __shared__ unsigned long long warp_sums[kScanThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, m);
+    if (lane >= m) inc += t;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long s = lane < kScanThreads / 32 ? warp_sums[lane] : 0ull;
+#pragma unroll
+    for (int m = 1; m < kScanThreads / 32; m <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, s, m);
+      if (lane >= m) s += t;
+    }
+    if (lane < kScanThreads / 32) warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const unsigned long long base = w ? warp_sums[w - 1] : 0ull;
+  *total = warp_sums[kScanThreads / 32 - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+
+// n_dev (optional) overrides n with a device-side length (the cell count is only known there)
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, const int* __restrict__ n_dev,
+              unsigned long long* __restrict__ tile_sums) {
+  if (n_dev) n = *n_dev;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  unsigned long long s = 0;
+  if (base < n) {
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      const int64_t idx = base + (int64_t)k * kScanThreads + threadIdx.x;
+      if (idx < n) s += in[idx];
+    }
+  }
+  unsigned long long tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_spine(unsigned long long* __restrict__ tile_sums, int64_t ntiles,
+             unsigned long long* __restrict__ total_out) {
+  unsigned long long carry = 0;
+  for (int64_t b = 0; b < ntiles; b += kScanThreads) {
+    const int64_t idx = b + threadIdx.x;
+    const unsigned long long v = idx < ntiles ? tile_sums[idx] : 0ull;
+    unsigned long long tot;
+    const unsigned long long ex = block_exclusive_scan(v, &tot);
+    if (idx < ntiles) tile_sums[idx] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+// OUT = uint32_t (cell starts / int32 pointer[]) or long long (int64 pointer[])
+template <typename OUT>
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_down(const uint32_t* __restrict__ in, int64_t n, const int* __restrict__ n_dev,
+            const unsigned long long* __restrict__ tile_sums, OUT* __restrict__ out) {
+  if (n_dev) n = *n_dev;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  if (base >= n) return;
+  // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems)
+  uint32_t v[kScanItems];
+  unsigned long long s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    const int64_t idx = base + (int64_t)threadIdx.x * kScanItems + k;
+    v[k] = idx < n ? in[idx] : 0u;
+    s += v[k];
+  }
+  unsigned long long tot;
+  unsigned long long run = tile_sums[blockIdx.x] + block_exclusive_scan(s, &tot);
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    const int64_t idx = base + (int64_t)threadIdx.x * kScanItems + k;
+    if (idx < n) out[idx] = (OUT)run;
+    run += v[k];
+  }
+}
+
+// ------------------------------------------------------------------ stencil search ----
+// One warp per particle (in cell order).  For each of the 9 (dz,dy) rows of the 27-cell
+// stencil the three x-adjacent cells are one contiguous range of sorted_pos32, which the
+// warp streams with coalesced 16 B loads.  FILL=false counts, FILL=true writes the row.
+template <bool FILL, bool PTR64>
+__global__ void __launch_bounds__(256)
+k_search(int64_t pn, const grid_ext* __restrict__ ge, const int32_t* __restrict__ cell_of,
+         const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+         const double4* __restrict__ sorted_pos, const float4* __restrict__ sorted_pos32,
+         double sl2, int half, int64_t row_begin, int64_t row_end,
+         int32_t* __restrict__ nop, const void* __restrict__ pointer, int32_t* __restrict__ list,
+         int64_t capacity, lj_list_totals* __restrict__ tot) {
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // slot in cell order
+  const int lane = threadIdx.x & 31;
+  if (s >= pn) return;
+  const float4 me32 = sorted_pos32[s];
+  const int i = __float_as_int(me32.w);
+  if (i < row_begin || i >= row_end) return;
+  const lj_grid_params g = ge->g;
+  const float margin = ge->margin, sl2f = ge->sl2f;
+  const float lo_f = sl2f - margin, hi_f = sl2f + margin;
+  const int c = cell_of[i];
+  const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+
+  int64_t base = 0;
+  bool fits = true;
+  if (FILL) {
+    base = row_offset<PTR64>(pointer, i);
+    fits = base + nop[i] <= capacity;
+    if (!fits) {
+      if (lane == 0) atomicOr(&tot->overflow, 1);
+      return;
+    }
+  }
+  int count = 0;
+  double4 me = make_double4(0, 0, 0, 0);
+  bool have_me = false;
+
+  for (int dz = -1; dz <= 1; dz++) {
+    const int z = cz + dz;
+    if (z < 0 || z >= g.nz) continue;
+    for (int dy = -1; dy <= 1; dy++) {
+      const int y = cy + dy;
+      if (y < 0 || y >= g.ny) continue;
+      const int rowc = (z * g.ny + y) * g.nx;
+      const uint32_t mb = cell_start[rowc + x0];
+      const uint32_t me_ = cell_start[rowc + x1] + cell_count[rowc + x1];
+      for (uint32_t m0 = mb; m0 < me_; m0 += 32) {
+        const uint32_t m = m0 + lane;
+        bool hit = false;
+        int j = -1;
+        if (m < me_) {
+          const float4 c32 = sorted_pos32[m];
+          j = __float_as_int(c32.w);
+          const float dx = me32.x - c32.x, dy_ = me32.y - c32.y, dz_ = me32.z - c32.z;
+          const float r2f = fmaf(dz_, dz_, fmaf(dy_, dy_, dx * dx));
+          const bool wanted = (j != i) && (!half || j > i);
+          if (wanted && r2f < hi_f) {
+            if (r2f < lo_f) {
+              hit = true;
+            } else {  // within the error margin of the threshold: decide in FP64, exactly
+              if (!have_me) { me = sorted_pos[s]; have_me = true; }
+              const double4 cj = sorted_pos[m];
+              const double ddx = me.x - cj.x, ddy = me.y - cj.y, ddz = me.z - cj.z;
+              hit = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2;
+            }
+          }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) list[base + count + __popc(ballot & ((1u << lane) - 1u))] = j;
+        count += __popc(ballot);
+      }
+    }
+  }
+  if (!FILL && lane == 0) {
+    nop[i] = count;
+    atomicMax(&tot->max_np, count);
+  }
+}
+
+__global__ void k_zero_u32(uint32_t* p, int64_t n, const int* n_dev) {
+  if (n_dev) n = *n_dev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = 0u;
+}
+
+__global__ void k_zero_i32_rows(int32_t* p, int64_t pn) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pn;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = 0;
+}
+
+__global__ void k_finish_totals(lj_list_totals* tot, int64_t capacity, int pointer64) {
+  if (tot->total > (unsigned long long)capacity) tot->overflow |= 1;
+  if (!pointer64 && tot->total > 0xffffffffull) tot->overflow |= 2;
+}
+
+// ------------------------------------------------------------------ ELL / shuffle / check
+template <bool PTR64>
+__global__ void __launch_bounds__(256)
+k_csr_to_ell(const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
+             const void* __restrict__ pointer, int64_t pn, int max_np, int32_t* __restrict__ tl) {
+  // thread per (row, k) with rows fastest: coalesced writes of the column-major table
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pn * (int64_t)max_np) return;
+  const int64_t i = t % pn;
+  const int k = (int)(t / pn);
+  int v = 0;  // padding value 0, as thrust::fill(…, 0) in the reference (force_cuda.cu:230)
+  if (k < nop[i]) v = list[row_offset<PTR64>(pointer, i) + k];
+  tl[t] = v;
+}
+
+__global__ void k_max_np(const int32_t* __restrict__ nop, int64_t pn, int* out) {
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pn;
+       i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, nop[i]);
+  for (int s = 16; s >= 1; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+// Fisher-Yates per row with a counter-based hash, one thread per row.
+template <bool PTR64>
+__global__ void __launch_bounds__(256)
+k_shuffle_rows(int32_t* __restrict__ list, const int32_t* __restrict__ nop,
+               const void* __restrict__ pointer, int64_t pn, uint32_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  int32_t* row = list + row_offset<PTR64>(pointer, i);
+  const int n = nop[i];
+  uint32_t state = mix32(seed ^ (uint32_t)i * 0x9e3779b9u);
+  for (int k = n - 1; k > 0; k--) {
+    state = mix32(state + 0x9e3779b9u);
+    const int r = (int)(((uint64_t)state * (uint64_t)(k + 1)) >> 32);
+    const int32_t t = row[k]; row[k] = row[r]; row[r] = t;
+  }
+}
+
+template <bool PTR64>
+__global__ void __launch_bounds__(256)
+k_validate(const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
+           const void* __restrict__ pointer, int64_t pn, int64_t npairs, int* bad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < pn) {
+    const int n = nop[t];
+    const int64_t o = row_offset<PTR64>(pointer, t);
+    if (n < 0 || n >= pn || o < 0 || o > npairs || o + n > npairs) atomicOr(bad, 1);
+  }
+  if (t < npairs) {
+    const int j = list[t];
+    if (j < 0 || j >= pn) atomicOr(bad, 2);
+  }
+}
+
+int64_t blocks_for(int64_t n, int tb) { return (n + tb - 1) / tb; }
+
+}  // namespace
+
+// --------------------------------------------------------------------------- scratch ---
+int lj_scratch_reserve(lj_ctx* ctx, int64_t pn, cudaStream_t st) {
+  if (!ctx->totals) {
+    LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->bbox, 8 * sizeof(double), ctx->pool, st));
+    LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->grid, 256, ctx->pool, st));
+    LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->totals, sizeof(lj_list_totals) + 16, ctx->pool, st));
+    LJ_CUDA(ctx, cudaHostAlloc((void**)&ctx->totals_host, sizeof(lj_list_totals) + 16, cudaHostAllocDefault));
+  }
+  if (pn <= ctx->scratch_pn) return LJ_OK;
+  void* olds[] = {ctx->cell_of, ctx->cell_slot, ctx->cell_count, ctx->cell_start,
+                  ctx->sorted_pos, ctx->sorted_tmp, ctx->scan_tmp, ctx->q32};
+  for (void* o : olds)
+    if (o) LJ_CUDA(ctx, cudaFreeAsync(o, st));
+  ctx->q32 = nullptr; ctx->q32_len = 0;
+  const int64_t cells = pn < 32768 ? 32768 : pn;
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cell_of, sizeof(int32_t) * pn, ctx->pool, st));
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cell_slot, sizeof(int32_t) * pn, ctx->pool, st));
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cell_count, sizeof(uint32_t) * (cells + 1), ctx->pool, st));
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cell_start, sizeof(uint32_t) * (cells + 1), ctx->pool, st));
+  // sorted_pos (double4) followed by sorted_pos32 (float4)
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->sorted_pos, (sizeof(double4) + sizeof(float4)) * pn, ctx->pool, st));
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->sorted_tmp, sizeof(int32_t) * pn, ctx->pool, st));
+  ctx->scan_tmp_len = blocks_for(cells > pn ? cells : pn, kScanTile) + 1;
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->scan_tmp, sizeof(unsigned long long) * ctx->scan_tmp_len, ctx->pool, st));
+  ctx->scratch_pn = pn;
+  ctx->scratch_cells = cells;
+  return LJ_OK;
+}
+
+// bounding box of q into ctx->bbox (6 ordered-encoded doubles); shared with the mixed kernels
+int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t plane,
+                   lj_list_totals* reset_totals, cudaStream_t st) {
+  unsigned long long* bb = reinterpret_cast<unsigned long long*>(ctx->bbox);
+  const int nb = (int)(blocks_for(pn, 256) < 4 * ctx->sm_count ? blocks_for(pn, 256) : 4 * ctx->sm_count);
+  k_bbox_init<<<1, 32, 0, st>>>(bb, reset_totals);
+  LJ_LAUNCHED(ctx);
+  switch (layout) {
+    case LJ_AOS_D3: k_bbox<LJ_AOS_D3><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
+    case LJ_AOS_D4: k_bbox<LJ_AOS_D4><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
+    default: k_bbox<LJ_SOA_D><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
+  }
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+// --------------------------------------------------------------------------- build -----
+template <int LAYOUT>
+static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) {
+  const int64_t pn = a->pn;
+  int rc = lj_scratch_reserve(ctx, pn, st);
+  if (rc) return rc;
+  unsigned long long* bb = reinterpret_cast<unsigned long long*>(ctx->bbox);
+  grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
+  float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
+  const int* ncell_dev = &ge->g.ncell;
+  const int64_t cells = ctx->scratch_cells;
+  int64_t r0 = a->row_begin, r1 = a->row_end;
+  if (r0 == 0 && r1 == 0) r1 = pn;
+
+  rc = lj_bbox_launch(ctx, a->q, LAYOUT, pn, a->plane_stride, ctx->totals, st);
+  if (rc) return rc;
+  k_grid_setup<<<1, 1, 0, st>>>(bb, a->search_len, cells, ge);
+  LJ_LAUNCHED(ctx);
+  k_zero_u32<<<4 * ctx->sm_count, 256, 0, st>>>(ctx->cell_count, cells + 1, ncell_dev);
+  LJ_LAUNCHED(ctx);
+  k_cell_assign<LAYOUT><<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(
+      a->q, pn, a->plane_stride, ge, ctx->cell_of, ctx->cell_slot, ctx->cell_count);
+  LJ_LAUNCHED(ctx);
+  // exclusive scan of the cell histogram (length known only on the device)
+  const unsigned cell_tiles = (unsigned)blocks_for(cells, kScanTile);
+  k_scan_reduce<<<cell_tiles, kScanThreads, 0, st>>>(ctx->cell_count, cells, ncell_dev, ctx->scan_tmp);
+  LJ_LAUNCHED(ctx);
+  k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, cell_tiles, nullptr);
+  LJ_LAUNCHED(ctx);
+  k_scan_down<uint32_t><<<cell_tiles, kScanThreads, 0, st>>>(ctx->cell_count, cells, ncell_dev,
+                                                              ctx->scan_tmp, ctx->cell_start);
+  LJ_LAUNCHED(ctx);
+  k_cell_scatter<<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(pn, ctx->cell_of, ctx->cell_slot,
+                                                                 ctx->cell_start, ctx->sorted_tmp);
+  LJ_LAUNCHED(ctx);
+  k_cell_order<LAYOUT><<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(
+      a->q, pn, a->plane_stride, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_tmp,
+      ctx->sorted_pos, sorted_pos32);
+  LJ_LAUNCHED(ctx);
+
+  const double sl2 = a->search_len * a->search_len;
+  const unsigned search_blocks = (unsigned)blocks_for(pn * 32, 256);
+  if (r0 > 0 || r1 < pn) {  // rows outside the range stay empty
+    k_zero_i32_rows<<<4 * ctx->sm_count, 256, 0, st>>>(a->number_of_partners, pn);
+    LJ_LAUNCHED(ctx);
+  }
+  k_search<false, false><<<search_blocks, 256, 0, st>>>(
+      pn, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_pos, sorted_pos32, sl2,
+      a->half, r0, r1, a->number_of_partners, nullptr, nullptr, 0, ctx->totals);
+  LJ_LAUNCHED(ctx);
+  // pointer[] = exclusive scan of number_of_partners, carried in 64 bits
+  const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
+  const uint32_t* nop_u = reinterpret_cast<const uint32_t*>(a->number_of_partners);
+  k_scan_reduce<<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp);
+  LJ_LAUNCHED(ctx);
+  k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, row_tiles, &ctx->totals->total);
+  LJ_LAUNCHED(ctx);
+  if (a->pointer64)
+    k_scan_down<long long><<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp,
+                                                                reinterpret_cast<long long*>(a->pointer));
+  else
+    k_scan_down<uint32_t><<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp,
+                                                               reinterpret_cast<uint32_t*>(a->pointer));
+  LJ_LAUNCHED(ctx);
+  k_finish_totals<<<1, 1, 0, st>>>(ctx->totals, a->capacity, a->pointer64);
+  LJ_LAUNCHED(ctx);
+  if (a->pointer64)
+    k_search<true, true><<<search_blocks, 256, 0, st>>>(
+        pn, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_pos, sorted_pos32, sl2,
+        a->half, r0, r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity, ctx->totals);
+  else
+    k_search<true, false><<<search_blocks, 256, 0, st>>>(
+        pn, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_pos, sorted_pos32, sl2,
+        a->half, r0, r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity, ctx->totals);
+  LJ_LAUNCHED(ctx);
+  ctx->last_capacity = a->capacity;
+  return LJ_OK;
+}
+
+int lj_sort_rows_launch(lj_ctx* ctx, int32_t* list, const int32_t* nop, const void* pointer,
+                        int pointer64, int64_t pn, int64_t capacity, cudaStream_t st);
+
+extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number_of_pairs_out,
+                             void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, a != nullptr, "lj_build_list: null args");
+  LJ_REQUIRE(ctx, a->pn >= 0 && a->pn < 2147483647LL, "lj_build_list: particle_number out of range");
+  LJ_REQUIRE(ctx, a->search_len > 0.0, "lj_build_list: search length must be positive");
+  LJ_REQUIRE(ctx, a->capacity >= 0, "lj_build_list: negative capacity");
+  cudaStream_t st = lj_stream(ctx, stream);
+  if (a->pn == 0) {
+    if (number_of_pairs_out) *number_of_pairs_out = 0;
+    return LJ_OK;
+  }
+  LJ_REQUIRE(ctx, a->q && a->number_of_partners && a->pointer && (a->sorted_list || a->capacity == 0),
+             "lj_build_list: null array");
+  if (a->layout == LJ_SOA_D)
+    LJ_REQUIRE(ctx, a->plane_stride >= a->pn, "lj_build_list: SoA plane_stride < particle_number");
+  int rc;
+  switch (a->layout) {
+    case LJ_AOS_D3: rc = build_list_impl<LJ_AOS_D3>(ctx, a, st); break;
+    case LJ_AOS_D4:
+      LJ_REQUIRE(ctx, (uintptr_t)a->q % 32 == 0, "lj_build_list: double4 array must be 32-byte aligned");
+      rc = build_list_impl<LJ_AOS_D4>(ctx, a, st);
+      break;
+    case LJ_SOA_D: rc = build_list_impl<LJ_SOA_D>(ctx, a, st); break;
+    default: return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_build_list", "layout must be AOS_D3, AOS_D4 or SOA_D");
+  }
+  if (rc) return rc;
+  if (a->flags & LJ_LIST_SORT_ROWS) {
+    rc = lj_sort_rows_launch(ctx, a->sorted_list, a->number_of_partners, a->pointer, a->pointer64,
+                             a->pn, a->capacity, st);
+    if (rc) return rc;
+  }
+  if (number_of_pairs_out) return lj_list_result(ctx, number_of_pairs_out, nullptr, stream);
+  return LJ_OK;
+}
+
+extern "C" int lj_list_result(lj_ctx* ctx, int64_t* number_of_pairs_out, int32_t* max_partners_out,
+                              void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, ctx->totals != nullptr, "lj_list_result: no list has been built on this context");
+  cudaStream_t st = lj_stream(ctx, stream);
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals),
+                               cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (number_of_pairs_out) *number_of_pairs_out = (int64_t)ctx->totals_host->total;
+  if (max_partners_out) *max_partners_out = ctx->totals_host->max_np;
+  if (ctx->totals_host->overflow & 2)
+    return lj_set_error(ctx, LJ_ERR_OVERFLOW32, "lj_build_list", "list offsets exceed 32 bits: pass pointer64=1");
+  if (ctx->totals_host->overflow & 1)
+    return lj_set_error(ctx, LJ_ERR_CAPACITY, "lj_build_list", "sorted_list capacity too small (needed total returned)");
+  return LJ_OK;
+}
+
+extern "C" int lj_build_ell(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* nop,
+                            const void* pointer, int32_t pointer64, int64_t pn, int32_t* tl,
+                            int64_t capacity_entries, int32_t* max_partners_out, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, pn >= 0, "lj_build_ell: negative particle_number");
+  cudaStream_t st = lj_stream(ctx, stream);
+  if (pn == 0) { if (max_partners_out) *max_partners_out = 0; return LJ_OK; }
+  LJ_REQUIRE(ctx, sorted_list && nop && pointer && tl, "lj_build_ell: null array");
+  int rc = lj_scratch_reserve(ctx, 1, st);
+  if (rc) return rc;
+  int* mx = &ctx->totals->max_np;
+  LJ_CUDA(ctx, cudaMemsetAsync(mx, 0, sizeof(int), st));
+  k_max_np<<<4 * ctx->sm_count, 256, 0, st>>>(nop, pn, mx);
+  LJ_LAUNCHED(ctx);
+  LJ_CUDA(ctx, cudaMemcpyAsync(&ctx->totals_host->max_np, mx, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  const int max_np = ctx->totals_host->max_np;
+  if (max_partners_out) *max_partners_out = max_np;
+  if ((int64_t)max_np * pn > capacity_entries)
+    return lj_set_error(ctx, LJ_ERR_CAPACITY, "lj_build_ell", "transposed_list capacity < max_partners*pn");
+  if (max_np == 0) return LJ_OK;
+  const unsigned blocks = (unsigned)blocks_for((int64_t)max_np * pn, 256);
+  if (pointer64) k_csr_to_ell<true><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, max_np, tl);
+  else k_csr_to_ell<false><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, max_np, tl);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+extern "C" int lj_shuffle_rows(lj_ctx* ctx, int32_t* sorted_list, const int32_t* nop,
+                               const void* pointer, int32_t pointer64, int64_t pn, uint32_t seed,
+                               void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (pn <= 0) return LJ_OK;
+  LJ_REQUIRE(ctx, sorted_list && nop && pointer, "lj_shuffle_rows: null array");
+  cudaStream_t st = lj_stream(ctx, stream);
+  const unsigned blocks = (unsigned)blocks_for(pn, 256);
+  if (pointer64) k_shuffle_rows<true><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, seed);
+  else k_shuffle_rows<false><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, seed);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+extern "C" int lj_validate_list(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* nop,
+                                const void* pointer, int32_t pointer64, int64_t pn,
+                                int64_t number_of_pairs, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (pn <= 0) return LJ_OK;
+  LJ_REQUIRE(ctx, sorted_list && nop && pointer, "lj_validate_list: null array");
+  cudaStream_t st = lj_stream(ctx, stream);
+  int rc = lj_scratch_reserve(ctx, 1, st);
+  if (rc) return rc;
+  int* bad = &ctx->totals->overflow;
+  LJ_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), st));
+  const int64_t n = pn > number_of_pairs ? pn : number_of_pairs;
+  const unsigned blocks = (unsigned)blocks_for(n, 256);
+  if (pointer64) k_validate<true><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, number_of_pairs, bad);
+  else k_validate<false><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, number_of_pairs, bad);
+  LJ_LAUNCHED(ctx);
+  LJ_CUDA(ctx, cudaMemcpyAsync(&ctx->totals_host->overflow, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->totals_host->overflow)
+    return lj_set_error(ctx, LJ_ERR_INVALID_LIST, "lj_validate_list",
+                        (ctx->totals_host->overflow & 1) ? "number_of_partners/pointer out of range"
+                                                         : "sorted_list entry out of range");
+  return LJ_OK;
+}
+
+// ------------------------------------------------------------------ optional row sort --
+// LJ_LIST_SORT_ROWS: rows ascending in j, the order makepair() itself produces
+// (cuda/force_cuda.cu:138-162).  One warp per row, rank sort out of shared memory (entries
+// of a row are distinct, so ranks are a permutation).
+namespace {
+constexpr int kSortCap = 1024;  // entries per row held in shared memory
+
+template <bool PTR64>
+__global__ void __launch_bounds__(256)
+k_sort_rows(int32_t* __restrict__ list, const int32_t* __restrict__ nop,
+            const void* __restrict__ pointer, int64_t pn, int64_t capacity) {
+  __shared__ int32_t buf[8][kSortCap];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + w;
+  if (i >= pn) return;
+  const int n = nop[i];
+  const int64_t base = row_offset<PTR64>(pointer, i);
+  if (n < 2 || base + n > capacity) return;
+  int32_t* row = list + base;
+  if (n <= kSortCap) {
+    for (int k = lane; k < n; k += 32) buf[w][k] = row[k];
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+      const int32_t v = buf[w][k];
+      int rank = 0;
+      for (int m = 0; m < n; m++) rank += buf[w][m] < v;
+      row[rank] = v;
+    }
+  } else if (lane == 0) {  // pathological row length: in-place insertion sort by one lane
+    for (int k = 1; k < n; k++) {
+      const int32_t v = row[k];
+      int m = k - 1;
+      while (m >= 0 && row[m] > v) { row[m + 1] = row[m]; m--; }
+      row[m + 1] = v;
+    }
+  }
+}
+}  // namespace
+
+int lj_sort_rows_launch(lj_ctx* ctx, int32_t* list, const int32_t* nop, const void* pointer,
+                        int pointer64, int64_t pn, int64_t capacity, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((pn + 7) / 8);
+  if (pointer64) k_sort_rows<true><<<blocks, 256, 0, st>>>(list, nop, pointer, pn, capacity);
+  else k_sort_rows<false><<<blocks, 256, 0, st>>>(list, nop, pointer, pn, capacity);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}

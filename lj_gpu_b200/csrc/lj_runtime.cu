@@ -1,0 +1,477 @@
+// lj_runtime.cu -- context, Blackwell memory layer and the measure() call of the C ABI.
+//
+// Replaces cuda/cuda_ptr.cuh (paired cudaMalloc + cudaMallocHost sized by a static maximum,
+// blocking cudaMemcpy, thrust::fill) with: a per-context stream-ordered pool
+// (cudaMallocAsync, release threshold = keep everything), pinned host mirrors, async copies
+// on the caller's stream, and a double-buffered pinned staging ring for pageable memory.
+#include <chrono>
+#include <cstring>
+
+#include "lj_common.cuh"
+
+int lj_set_error(lj_ctx* ctx, int status, const char* what, const char* detail) {
+  if (ctx) {
+    ctx->err = std::string(what ? what : "") + ": " + (detail ? detail : "");
+  }
+  return status;
+}
+
+namespace {
+constexpr size_t kRingBytes = 32u << 20;  // 2 x 32 MiB pinned staging
+
+__global__ void k_fill32(uint32_t* p, size_t n, uint32_t v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// 16-byte grid-stride copy; used on peer-mapped sources (P2P loads over NVLink)
+__global__ void __launch_bounds__(256) k_copy16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+extern "C" {
+
+const char* lj_status_string(int s) {
+  switch (s) {
+    case LJ_OK: return "ok";
+    case LJ_ERR_CUDA: return "CUDA error";
+    case LJ_ERR_BAD_ARG: return "bad argument";
+    case LJ_ERR_CAPACITY: return "capacity overflow";
+    case LJ_ERR_OVERFLOW32: return "32-bit offset overflow";
+    case LJ_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case LJ_ERR_INVALID_LIST: return "invalid neighbour list";
+  }
+  return "unknown status";
+}
+
+int lj_ctx_create(lj_ctx** out, int device) {
+  if (!out) return LJ_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return LJ_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) return LJ_ERR_BAD_ARG;
+  lj_ctx* ctx = new lj_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LJ_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  // private pool: never hand memory back to the OS between steps (180 GB HBM, one tenant)
+  cudaMemPoolProps pp{};
+  pp.allocType = cudaMemAllocationTypePinned;
+  pp.handleTypes = cudaMemHandleTypeNone;
+  pp.location.type = cudaMemLocationTypeDevice;
+  pp.location.id = device;
+  if (cudaMemPoolCreate(&ctx->pool, &pp) != cudaSuccess) {
+    cudaGetLastError();
+    cudaDeviceGetDefaultMemPool(&ctx->pool, device);
+  }
+  uint64_t keep = ~0ull;
+  cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&ctx->ring_ev[k], cudaEventDisableTiming);
+  if (cudaGetLastError() != cudaSuccess) { /* non-fatal: reported on first use */ }
+  *out = ctx;
+  return LJ_OK;
+}
+
+int lj_ctx_destroy(lj_ctx* ctx) {
+  if (!ctx) return LJ_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  void* frees[] = {ctx->bbox, ctx->grid, ctx->totals, ctx->cell_of, ctx->cell_slot, ctx->cell_count,
+                   ctx->cell_start, ctx->sorted_pos, ctx->sorted_tmp, ctx->scan_tmp, ctx->q32};
+  for (void* f : frees)
+    if (f) cudaFreeAsync(f, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->totals_host) cudaFreeHost(ctx->totals_host);
+  for (int k = 0; k < 2; k++) {
+    if (ctx->ring[k]) cudaFreeHost(ctx->ring[k]);
+    if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
+  }
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  cudaMemPool_t def = nullptr;
+  cudaDeviceGetDefaultMemPool(&def, ctx->device);
+  if (ctx->pool && ctx->pool != def) cudaMemPoolDestroy(ctx->pool);
+  delete ctx;
+  return LJ_OK;
+}
+
+int lj_sync(lj_ctx* ctx, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (stream) {
+    LJ_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+  } else {
+    LJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    LJ_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  }
+  return LJ_OK;
+}
+
+const char* lj_last_error_string(lj_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t lj_launch_count(lj_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* lj_ctx_stream(lj_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int lj_device_sm_count(lj_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ------------------------------------------------------------------ memory layer ------
+int lj_dev_alloc(lj_ctx* ctx, size_t bytes, void** out, void* stream) {
+  if (!ctx || !out) return LJ_ERR_BAD_ARG;
+  *out = nullptr;
+  if (bytes == 0) return LJ_OK;
+  LJ_CUDA(ctx, cudaMallocAsync(out, bytes, ctx->pool, lj_stream(ctx, stream)));
+  return LJ_OK;
+}
+
+int lj_dev_free(lj_ctx* ctx, void* ptr, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (ptr) LJ_CUDA(ctx, cudaFreeAsync(ptr, lj_stream(ctx, stream)));
+  return LJ_OK;
+}
+
+int lj_buf_allocate(lj_ctx* ctx, size_t bytes, lj_buf* out, void* stream) {
+  if (!ctx || !out) return LJ_ERR_BAD_ARG;
+  out->host = out->dev = nullptr;
+  out->bytes = bytes;
+  if (bytes == 0) return LJ_OK;
+  LJ_CUDA(ctx, cudaMallocAsync(&out->dev, bytes, ctx->pool, lj_stream(ctx, stream)));
+  cudaError_t e = cudaHostAlloc(&out->host, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(out->dev, lj_stream(ctx, stream));
+    out->dev = nullptr;
+    return lj_set_error(ctx, LJ_ERR_CUDA, "cudaHostAlloc", cudaGetErrorString(e));
+  }
+  return LJ_OK;
+}
+
+int lj_buf_deallocate(lj_ctx* ctx, lj_buf* buf, void* stream) {
+  if (!ctx || !buf) return LJ_ERR_BAD_ARG;
+  if (buf->dev) LJ_CUDA(ctx, cudaFreeAsync(buf->dev, lj_stream(ctx, stream)));
+  if (buf->host) {
+    // the host mirror may still be the target of an in-flight copy on this stream
+    LJ_CUDA(ctx, cudaStreamSynchronize(lj_stream(ctx, stream)));
+    LJ_CUDA(ctx, cudaFreeHost(buf->host));
+  }
+  buf->host = buf->dev = nullptr;
+  buf->bytes = 0;
+  return LJ_OK;
+}
+
+int lj_buf_host2dev(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, void* stream) {
+  if (!ctx || !buf) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, beg + count <= buf->bytes, "lj_buf_host2dev: range exceeds the buffer");
+  if (count == 0) return LJ_OK;
+  LJ_CUDA(ctx, cudaMemcpyAsync((char*)buf->dev + beg, (const char*)buf->host + beg, count,
+                               cudaMemcpyHostToDevice, lj_stream(ctx, stream)));
+  return LJ_OK;
+}
+
+int lj_buf_dev2host(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, void* stream) {
+  if (!ctx || !buf) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, beg + count <= buf->bytes, "lj_buf_dev2host: range exceeds the buffer");
+  if (count == 0) return LJ_OK;
+  LJ_CUDA(ctx, cudaMemcpyAsync((char*)buf->host + beg, (const char*)buf->dev + beg, count,
+                               cudaMemcpyDeviceToHost, lj_stream(ctx, stream)));
+  return LJ_OK;
+}
+
+int lj_buf_set_val32(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, uint32_t value,
+                     void* stream) {
+  if (!ctx || !buf) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, (beg + count) * 4 <= buf->bytes, "lj_buf_set_val32: range exceeds the buffer");
+  if (count == 0) return LJ_OK;
+  uint32_t* h = (uint32_t*)buf->host + beg;
+  for (size_t i = 0; i < count; i++) h[i] = value;
+  size_t blocks = (count + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 8) blocks = (size_t)ctx->sm_count * 8;
+  k_fill32<<<(unsigned)blocks, 256, 0, lj_stream(ctx, stream)>>>((uint32_t*)buf->dev + beg, count, value);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+static int ring_init(lj_ctx* ctx) {
+  if (ctx->ring[0]) return LJ_OK;
+  for (int k = 0; k < 2; k++) LJ_CUDA(ctx, cudaHostAlloc(&ctx->ring[k], kRingBytes, cudaHostAllocDefault));
+  ctx->ring_bytes = kRingBytes;
+  return LJ_OK;
+}
+
+int lj_upload(lj_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (bytes == 0) return LJ_OK;
+  LJ_REQUIRE(ctx, dev_dst && host_src, "lj_upload: null pointer");
+  cudaStream_t st = lj_stream(ctx, stream);
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, host_src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+    LJ_CUDA(ctx, cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, st));  // already pinned
+    return LJ_OK;
+  }
+  cudaGetLastError();
+  int rc = ring_init(ctx);
+  if (rc) return rc;
+  size_t off = 0;
+  int k = 0;
+  while (off < bytes) {
+    const size_t n = bytes - off < ctx->ring_bytes ? bytes - off : ctx->ring_bytes;
+    LJ_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[k]));  // previous DMA out of this half done
+    memcpy(ctx->ring[k], (const char*)host_src + off, n);  // overlaps the other half's DMA
+    LJ_CUDA(ctx, cudaMemcpyAsync((char*)dev_dst + off, ctx->ring[k], n, cudaMemcpyHostToDevice, st));
+    LJ_CUDA(ctx, cudaEventRecord(ctx->ring_ev[k], st));
+    off += n;
+    k ^= 1;
+  }
+  return LJ_OK;
+}
+
+int lj_download(lj_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (bytes == 0) return LJ_OK;
+  LJ_REQUIRE(ctx, host_dst && dev_src, "lj_download: null pointer");
+  cudaStream_t st = lj_stream(ctx, stream);
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, host_dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+    LJ_CUDA(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+    return LJ_OK;
+  }
+  cudaGetLastError();
+  int rc = ring_init(ctx);
+  if (rc) return rc;
+  // chunk k is copied out of the ring while chunk k+1 is in flight
+  size_t off = 0, prev_off = 0, prev_n = 0;
+  int k = 0;
+  while (off < bytes) {
+    const size_t n = bytes - off < ctx->ring_bytes ? bytes - off : ctx->ring_bytes;
+    LJ_CUDA(ctx, cudaMemcpyAsync(ctx->ring[k], (const char*)dev_src + off, n, cudaMemcpyDeviceToHost, st));
+    LJ_CUDA(ctx, cudaEventRecord(ctx->ring_ev[k], st));
+    if (prev_n) {
+      LJ_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[k ^ 1]));
+      memcpy((char*)host_dst + prev_off, ctx->ring[k ^ 1], prev_n);
+    }
+    prev_off = off; prev_n = n;
+    off += n;
+    k ^= 1;
+  }
+  LJ_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[k ^ 1]));
+  memcpy((char*)host_dst + prev_off, ctx->ring[k ^ 1], prev_n);
+  return LJ_OK;
+}
+
+// ------------------------------------------------------------------ force entry points -
+int lj_force_step(lj_ctx* ctx, const lj_force_args* args, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  return lj_force_launch(ctx, args, lj_stream(ctx, stream));
+}
+
+int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int use_graph, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, args != nullptr && loop >= 0, "lj_force_loop: bad arguments");
+  cudaStream_t st = lj_stream(ctx, stream);
+  if (!use_graph || loop < 2) {
+    for (int s = 0; s < loop; s++) {
+      int rc = lj_force_launch(ctx, args, st);
+      if (rc) return rc;
+    }
+    return LJ_OK;
+  }
+  // capture once, replay: the 100-launch loop of measure() becomes one graph launch
+  const bool same = ctx->graph_exec && ctx->graph_loop == loop &&
+                    memcmp(&ctx->graph_args, args, sizeof(*args)) == 0;
+  if (!same) {
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    // Validate the arguments and force the kernel's module to load OUTSIDE the capture with
+    // a numerically neutral launch: a few rows, dt = 0 (p += 0).
+    lj_force_args warm = *args;
+    warm.dt = 0.0;
+    warm.row_begin = 0;
+    warm.row_end = args->pn < 32 ? args->pn : 32;
+    if (args->row_begin || args->row_end) {
+      warm.row_begin = args->row_begin;
+      warm.row_end = args->row_begin + 32 < args->row_end ? args->row_begin + 32 : args->row_end;
+    }
+    int rc = lj_force_launch(ctx, &warm, st);
+    if (rc) return rc;
+    LJ_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t before = ctx->launches;
+    cudaStream_t cap = ctx->copy_stream;  // never the stream the caller is working on
+    LJ_CUDA(ctx, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    for (int s = 0; s < loop && rc == LJ_OK; s++) rc = lj_force_launch(ctx, args, cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    ctx->graph_step_launches = loop > 0 ? (ctx->launches - before) / loop : 0;
+    ctx->launches = before;  // captured, not executed yet
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return lj_set_error(ctx, LJ_ERR_CUDA, "cudaStreamEndCapture", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      ctx->graph_exec = nullptr;
+      return lj_set_error(ctx, LJ_ERR_CUDA, "cudaGraphInstantiate", cudaGetErrorString(e));
+    }
+    ctx->graph_args = *args;
+    ctx->graph_loop = loop;
+  }
+  LJ_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+  ctx->launches += ctx->graph_step_launches * loop;  // kernels the replay executes
+  return LJ_OK;
+}
+
+// ------------------------------------------------------------------ measure() ---------
+static size_t vec_bytes(int layout) {
+  return layout == LJ_AOS_D4 ? 32 : layout == LJ_AOS_D3 ? 24 : layout == LJ_AOS_F4 ? 16 : 8;
+}
+
+int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, m && m->q_host && m->p_host && m->pn > 0 && m->loop >= 0, "lj_measure: bad arguments");
+  LJ_REQUIRE(ctx, m->layout == LJ_AOS_D3 || m->layout == LJ_AOS_D4 || m->layout == LJ_SOA_D,
+             "lj_measure: layout must be AOS_D3, AOS_D4 or SOA_D");
+  cudaStream_t st = ctx->stream;
+  const int64_t pn = m->pn;
+  const size_t qbytes = m->layout == LJ_SOA_D ? (size_t)m->plane_stride * 3 * 8 : (size_t)pn * vec_bytes(m->layout);
+  if (m->layout == LJ_SOA_D) LJ_REQUIRE(ctx, m->plane_stride >= pn, "lj_measure: plane_stride < pn");
+  const bool own_list = m->list_host == nullptr;
+  const double t_all0 = now_s();
+  m->h2d_bytes = m->d2h_bytes = 0;
+  m->list_builds = 0;
+
+  void *q = nullptr, *p = nullptr;
+  int32_t *list = nullptr, *nop = nullptr;
+  void* ptr = nullptr;
+  int rc = LJ_OK;
+  int64_t capacity = 0, npairs = 0;
+  int32_t max_np = 0;
+  int ptr64 = own_list ? 1 : 0;  // int64 offsets whenever the library builds the list itself
+#define M_TRY(x) do { rc = (x); if (rc) goto done; } while (0)
+  M_TRY(lj_dev_alloc(ctx, qbytes, &q, st));
+  M_TRY(lj_dev_alloc(ctx, qbytes, &p, st));
+  M_TRY(lj_dev_alloc(ctx, sizeof(int32_t) * pn, (void**)&nop, st));
+  M_TRY(lj_dev_alloc(ctx, (ptr64 ? 8 : 4) * (size_t)pn, &ptr, st));
+  M_TRY(lj_upload(ctx, q, m->q_host, qbytes, st));
+  M_TRY(lj_upload(ctx, p, m->p_host, qbytes, st));
+  m->h2d_bytes += 2 * (int64_t)qbytes;
+
+  {
+    lj_list_args la{};
+    la.q = q; la.pn = pn; la.layout = m->layout; la.half = m->half; la.plane_stride = m->plane_stride;
+    la.search_len = m->search_len; la.number_of_partners = nop; la.pointer = ptr; la.pointer64 = ptr64;
+    la.flags = m->list_flags;
+    if (own_list) {
+      // first build sizes the list: count pass only needs capacity 0 to learn the total
+      la.sorted_list = nullptr; la.capacity = 0;
+      rc = lj_build_list(ctx, &la, &npairs, st);
+      if (rc != LJ_OK && rc != LJ_ERR_CAPACITY) goto done;
+      capacity = npairs + npairs / 64 + 1024;  // headroom for later rebuilds
+      M_TRY(lj_dev_alloc(ctx, sizeof(int32_t) * (size_t)capacity, (void**)&list, st));
+      la.sorted_list = list; la.capacity = capacity;
+      M_TRY(lj_build_list(ctx, &la, &npairs, st));
+      M_TRY(lj_list_result(ctx, &npairs, &max_np, st));
+      m->list_builds = 1;
+    } else {
+      LJ_REQUIRE(ctx, m->number_of_partners_host && m->pointer_host && m->number_of_pairs_in >= 0,
+                 "lj_measure: incomplete host list");
+      npairs = m->number_of_pairs_in;
+      capacity = npairs;
+      M_TRY(lj_dev_alloc(ctx, sizeof(int32_t) * (size_t)(capacity ? capacity : 1), (void**)&list, st));
+      M_TRY(lj_upload(ctx, list, m->list_host, sizeof(int32_t) * (size_t)npairs, st));
+      M_TRY(lj_upload(ctx, nop, m->number_of_partners_host, sizeof(int32_t) * (size_t)pn, st));
+      M_TRY(lj_upload(ctx, ptr, m->pointer_host, sizeof(int32_t) * (size_t)pn, st));
+      m->h2d_bytes += 4 * (npairs + 2 * pn);
+      M_TRY(lj_validate_list(ctx, list, nop, ptr, 0, pn, npairs, st));
+    }
+
+    lj_force_args fa{};
+    fa.q = q; fa.p = p; fa.pn = pn; fa.dt = m->dt; fa.cl2 = m->cl2; fa.list = list;
+    fa.number_of_partners = nop; fa.pointer = ptr; fa.layout = m->layout; fa.list_layout = LJ_LIST_CSR;
+    fa.variant = m->half ? LJ_VARIANT_NEWTON3 : m->variant; fa.group = m->group;
+    fa.precision = m->precision; fa.pointer64 = ptr64; fa.threads_per_block = m->threads_per_block;
+    fa.plane_stride = m->plane_stride;
+
+    M_TRY(lj_sync(ctx, st));
+    const double t_k0 = now_s();
+    int done_steps = 0;
+    while (done_steps < m->loop) {
+      int chunk = m->loop - done_steps;
+      if (own_list && m->rebuild_every > 0) {
+        if (done_steps > 0) {  // the list for steps [0, rebuild_every) was built above
+          M_TRY(lj_build_list(ctx, &la, nullptr, st));
+          m->list_builds++;
+        }
+        if (chunk > m->rebuild_every) chunk = m->rebuild_every;
+      }
+      M_TRY(lj_force_loop(ctx, &fa, chunk, m->use_graph, st));
+      done_steps += chunk;
+    }
+    M_TRY(lj_sync(ctx, st));
+    m->seconds_kernel = now_s() - t_k0;
+    if (own_list && m->list_builds > 1) M_TRY(lj_list_result(ctx, &npairs, &max_np, st));
+  }
+  M_TRY(lj_download(ctx, m->p_host, p, qbytes, st));
+  M_TRY(lj_sync(ctx, st));
+  m->d2h_bytes += (int64_t)qbytes;
+  m->number_of_pairs = npairs;
+  m->max_partners = max_np;
+done:
+  lj_dev_free(ctx, q, st);
+  lj_dev_free(ctx, p, st);
+  lj_dev_free(ctx, list, st);
+  lj_dev_free(ctx, nop, st);
+  lj_dev_free(ctx, ptr, st);
+  cudaStreamSynchronize(st);
+  m->seconds_total = now_s() - t_all0;
+#undef M_TRY
+  return rc;
+}
+
+// ------------------------------------------------------------------ multi-GPU helpers --
+int lj_ipc_export(lj_ctx* ctx, void* dev_ptr, uint8_t handle_out[64]) {
+  if (!ctx || !dev_ptr || !handle_out) return LJ_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  LJ_CUDA(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle_out, &h, 64);
+  return LJ_OK;
+}
+
+int lj_ipc_open(lj_ctx* ctx, const uint8_t handle[64], void** peer_ptr_out) {
+  if (!ctx || !handle || !peer_ptr_out) return LJ_ERR_BAD_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  LJ_CUDA(ctx, cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return LJ_OK;
+}
+
+int lj_ipc_close(lj_ctx* ctx, void* peer_ptr) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (peer_ptr) LJ_CUDA(ctx, cudaIpcCloseMemHandle(peer_ptr));
+  return LJ_OK;
+}
+
+int lj_halo_pull(lj_ctx* ctx, void* local_dst, const void* peer_src, size_t bytes, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (bytes == 0) return LJ_OK;
+  LJ_REQUIRE(ctx, local_dst && peer_src, "lj_halo_pull: null pointer");
+  LJ_REQUIRE(ctx, bytes % 16 == 0 && (uintptr_t)local_dst % 16 == 0 && (uintptr_t)peer_src % 16 == 0,
+             "lj_halo_pull: pointers and size must be multiples of 16 bytes");
+  const size_t n16 = bytes / 16;
+  size_t blocks = (n16 + 255) / 256;
+  // a few CTAs per SM are enough to saturate one NVLink direction and leave the SMs to the
+  // interior force kernel running concurrently
+  if (blocks > (size_t)ctx->sm_count) blocks = (size_t)ctx->sm_count;
+  k_copy16<<<(unsigned)blocks, 256, 0, lj_stream(ctx, stream)>>>((int4*)local_dst, (const int4*)peer_src, n16);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// force_b200.cpp -- C++ host driver: the reference's benchmark program on the new library.
+//
+// Keeps the observable behaviour of cuda/force_cuda.cu main()/measure() (:319-444):
+//   * same input (jittered FCC lattice from one mt19937(2) stream), same constants
+//     (density 0.5, L 50, dt 0.001, cutoff 3.0, search 3.3, LOOP 100),
+//   * `./force_b200 [THREAD_BLOCK]` stays valid (first positional argument, 64..1024),
+//   * stderr carries the two timing lines of measure() verbatim,
+//     "N=%d, %s %f [sec]" and "N=%d, %s %f [sec] (without Host<->Device)",
+//   * with --test (the EN_TEST_GPU build) stdout is print_results(): p[0..4], p[pn-5..pn-1]
+//     in "%.10f %.10f %.10f", comparable with ref_data/density*.dat.
+// What changed underneath: makepair() is lj_build_list on the GPU (no pair cache needed),
+// the kernels are the sm_100a ones behind lj_force_step, memory comes from the library.
+//
+// Extra flags (the reference has compile-time constants instead, SURVEY 5 "Config"):
+//   --density R  --L X  --layout aos3|aos4|soa  --variant auto|warp|thread|subwarp|tile|n3
+//   --group G  --prec fp64|mixed  --steps K  --rebuild-every M  --graph  --test  --all
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lj_b200.h"
+
+namespace {
+
+struct Options {
+  int thread_block = 128;
+  double density = 0.5, L = 50.0;
+  std::string layout = "aos4", variant = "auto", prec = "fp64";
+  int group = 0, steps = 100, rebuild_every = 0;
+  bool graph = false, test = false, all = false;
+};
+
+[[noreturn]] void die(lj_ctx* ctx, int rc, const char* where) {
+  std::fprintf(stderr, "%s: %s: %s\n", where, lj_status_string(rc), ctx ? lj_last_error_string(ctx) : "");
+  std::exit(EXIT_FAILURE);  // the driver, not the library, decides to exit
+}
+
+int layout_id(const std::string& s) {
+  if (s == "aos3") return LJ_AOS_D3;
+  if (s == "aos4") return LJ_AOS_D4;
+  if (s == "soa") return LJ_SOA_D;
+  std::fprintf(stderr, "unknown layout %s\n", s.c_str());
+  std::exit(1);
+}
+
+// q (packed xyz) -> the requested layout; p zero-initialised like init() does
+void pack(const std::vector<double>& xyz, int64_t pn, int layout, std::vector<double>& q,
+          std::vector<double>& p) {
+  const int w = layout == LJ_AOS_D4 ? 4 : 3;
+  q.assign((size_t)pn * w, 0.0);
+  p.assign((size_t)pn * w, 0.0);
+  for (int64_t i = 0; i < pn; i++)
+    for (int c = 0; c < 3; c++) {
+      if (layout == LJ_SOA_D) q[(size_t)c * pn + i] = xyz[3 * i + c];
+      else q[(size_t)i * w + c] = xyz[3 * i + c];
+    }
+}
+
+void print_results(const std::vector<double>& p, int64_t pn, int layout) {
+  const int w = layout == LJ_AOS_D4 ? 4 : 3;
+  auto at = [&](int64_t i, int c) { return layout == LJ_SOA_D ? p[(size_t)c * pn + i] : p[(size_t)i * w + c]; };
+  for (int64_t i = 0; i < 5; i++) std::fprintf(stdout, "%.10f %.10f %.10f\n", at(i, 0), at(i, 1), at(i, 2));
+  for (int64_t i = pn - 5; i < pn; i++) std::fprintf(stdout, "%.10f %.10f %.10f\n", at(i, 0), at(i, 1), at(i, 2));
+}
+
+void measure(lj_ctx* ctx, const Options& o, const std::vector<double>& xyz, int64_t pn,
+             const std::string& layout, const std::string& variant, int group, const char* name,
+             bool print) {
+  const int lay = layout_id(layout);
+  std::vector<double> q, p;
+  pack(xyz, pn, lay, q, p);
+  lj_measure_args m{};
+  m.q_host = q.data(); m.p_host = p.data(); m.pn = pn; m.layout = lay;
+  m.plane_stride = lay == LJ_SOA_D ? pn : 0;
+  m.dt = 0.001; m.cl2 = 3.0 * 3.0; m.search_len = 3.3;
+  m.loop = o.steps; m.rebuild_every = o.rebuild_every;
+  m.half = variant == "n3";
+  m.variant = variant == "tile" ? LJ_VARIANT_TILE_TMA : variant == "n3" ? LJ_VARIANT_NEWTON3
+              : variant == "auto" ? LJ_VARIANT_AUTO : LJ_VARIANT_SUBWARP;
+  m.group = group ? group : (variant == "warp" ? 32 : variant == "thread" ? 1 : 0);
+  m.precision = o.prec == "mixed" ? LJ_PREC_MIXED : LJ_PREC_FP64;
+  m.threads_per_block = o.thread_block; m.use_graph = o.graph;
+  const int rc = lj_measure(ctx, &m);
+  if (rc) die(ctx, rc, "lj_measure");
+  std::fprintf(stderr, "N=%d, %s %f [sec]\n", (int)pn, name, m.seconds_total);
+  std::fprintf(stderr, "N=%d, %s %f [sec] (without Host<->Device)\n", (int)pn, name, m.seconds_kernel);
+  std::fprintf(stderr, "  pairs=%lld max_partners=%d list_builds=%d  %.4g pair-interactions/s\n",
+               (long long)m.number_of_pairs, m.max_partners, m.list_builds,
+               (double)m.number_of_pairs * (m.half ? 2.0 : 1.0) * o.steps / m.seconds_kernel);
+  if (print) print_results(p, pn, lay);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Options o;
+  for (int a = 1; a < argc; a++) {
+    std::string s = argv[a];
+    auto next = [&]() -> const char* {
+      if (a + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", s.c_str()); std::exit(1); }
+      return argv[++a];
+    };
+    if (s == "--density") o.density = std::atof(next());
+    else if (s == "--L") o.L = std::atof(next());
+    else if (s == "--layout") o.layout = next();
+    else if (s == "--variant") o.variant = next();
+    else if (s == "--group") o.group = std::atoi(next());
+    else if (s == "--prec") o.prec = next();
+    else if (s == "--steps") o.steps = std::atoi(next());
+    else if (s == "--rebuild-every") o.rebuild_every = std::atoi(next());
+    else if (s == "--graph") o.graph = true;
+    else if (s == "--test") o.test = true;
+    else if (s == "--all") o.all = true;
+    else if (s[0] != '-') o.thread_block = std::atoi(s.c_str());
+    else { std::fprintf(stderr, "unknown option %s\n", s.c_str()); return 1; }
+  }
+  if (o.thread_block < 64 || o.thread_block > 1024) {  // cuda/force_cuda.cu:380-383
+    std::fprintf(stderr, "THREAD_BLOCK size is too large or small.\n");
+    return 1;
+  }
+
+  int cells = 0;
+  const int64_t need = -lj_init_fcc(o.density, o.L, nullptr, 0, &cells);
+  std::vector<double> xyz((size_t)need * 3);
+  const int64_t pn = lj_init_fcc(o.density, o.L, xyz.data(), need, &cells);
+  if (pn <= 0) { std::fprintf(stderr, "empty system\n"); return 1; }
+
+  lj_ctx* ctx = nullptr;
+  int rc = lj_ctx_create(&ctx, 0);
+  if (rc) die(nullptr, rc, "lj_ctx_create");
+
+  if (o.test) {
+    // the EN_TEST_GPU build: one kernel for double3 then double4, then print p_d3.  Unlike the
+    // reference (which re-uploads the accumulated p, force_cuda.cu:331,338) each measure()
+    // here starts from p = 0, so the printed values are those of ONE 100-step run.
+    measure(ctx, o, xyz, pn, "aos4", "warp", 0, "force_kernel_warp_unroll2_double4", false);
+    measure(ctx, o, xyz, pn, "aos3", "warp", 0, "force_kernel_warp_unroll2_double3", true);
+  } else if (o.all) {
+    for (const char* lay : {"aos3", "aos4", "soa"}) {
+      for (int g : {1, 4, 8, 16, 32}) {
+        const std::string name = std::string("force_gather_g") + std::to_string(g) + "_" + lay;
+        measure(ctx, o, xyz, pn, lay, "subwarp", g, name.c_str(), false);
+      }
+      measure(ctx, o, xyz, pn, lay, "tile", 8, (std::string("force_tile_tma_g8_") + lay).c_str(), false);
+      measure(ctx, o, xyz, pn, lay, "n3", 8, (std::string("force_newton3_g8_") + lay).c_str(), false);
+    }
+  } else {
+    const std::string name = "force_" + o.variant + "_" + o.layout;
+    measure(ctx, o, xyz, pn, o.layout, o.variant, o.group, name.c_str(), false);
+  }
+  lj_ctx_destroy(ctx);
+  return 0;
+}

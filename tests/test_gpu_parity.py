@@ -1,0 +1,513 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (lj_gpu_b200._capi), against the
+CPU oracle on the same seeded inputs, and against the committed goldens of the reference.
+
+Bars (BASELINE.json north_star): neighbour lists bit-exact after per-row sorting; momenta
+within 1e-12 (FP64) / 1e-5 (mixed), norm-wise relative |dp|_max / |p|_max, after the
+reference's LOOP = 100 steps.
+"""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_rows
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP64 = 1e-12
+TOL_MIXED = 1e-5
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(torch):
+    from lj_gpu_b200 import LJContext
+    c = LJContext(0)
+    yield c
+    c.close()
+
+
+class System:
+    """One reference configuration with its oracle results (computed once per module)."""
+
+    def __init__(self, oracle, rho, L=50.0, steps=100):
+        from oracle import ljoracle as lo
+        self.rho, self.L, self.steps = rho, L, steps
+        self.q = oracle.init_fcc(rho, L)
+        self.pn = self.q.shape[0]
+        self.full = oracle.makepair(self.q, full=True)
+        self.half = oracle.makepair(self.q, full=False)
+        self.p = np.zeros_like(self.q)
+        oracle.force_gather(self.q, self.p, *self.full, steps=steps)
+        self.scale = np.abs(self.p).max()
+        self.lo = lo
+
+    def device_arrays(self, torch, layout):
+        q, pn = self.q, self.pn
+        if layout == "aos3":
+            qh = q.copy()
+        elif layout == "aos4":
+            qh = np.zeros((pn, 4)); qh[:, :3] = q; qh[:, 3] = -123.25  # .w is ignored
+        else:
+            stride = pn + 24
+            qh = np.zeros((3, stride)); qh[:, :pn] = q.T
+        qd = torch.from_numpy(qh).cuda()
+        pd = torch.zeros_like(qd)
+        if layout == "aos4":
+            pd[:, 3] = 77.5  # .w of p must survive
+        return qd, pd
+
+    def p_host(self, pd, layout):
+        a = pd.cpu().numpy()
+        return a[:, :3] if layout != "soa" else a[:, :self.pn].T
+
+    def err(self, pd, layout):
+        return np.abs(self.p_host(pd, layout) - self.p).max() / self.scale
+
+
+@pytest.fixture(scope="module")
+def sysA(oracle):
+    return System(oracle, 0.5)
+
+
+@pytest.fixture(scope="module")
+def sysB(oracle):
+    return System(oracle, 1.0)
+
+
+@pytest.fixture(scope="module")
+def sysS(oracle):
+    return System(oracle, 0.7, L=14.0, steps=7)
+
+
+def list_to_host(pl):
+    nop = pl.number_of_partners.cpu().numpy()
+    ptr = pl.pointer.cpu().numpy().astype(np.int64)
+    lst = pl.sorted_list.cpu().numpy()[:pl.number_of_pairs]
+    return nop, ptr, lst
+
+
+# ------------------------------------------------------------------------ generator
+def test_init_fcc_bit_exact(oracle, golden):
+    from lj_gpu_b200 import init_fcc
+    for rho in (0.5, 1.0):
+        q = init_fcc(rho, 50.0)
+        assert sha(q) == str(golden(rho)["q_sha256"])
+    assert np.array_equal(init_fcc(1.0, 20.3), oracle.init_fcc(1.0, 20.3))
+
+
+# ------------------------------------------------------------------------ neighbour list
+@pytest.mark.parametrize("which", ["A", "B"])
+@pytest.mark.parametrize("half", [False, True])
+def test_list_bit_exact(ctx, torch, sysA, sysB, golden, which, half):
+    s = sysA if which == "A" else sysB
+    qd, _ = s.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd, half=half)
+    nop, ptr, lst = list_to_host(pl)
+    nop_o, ptr_o, lst_o = s.half if half else s.full
+    assert pl.number_of_pairs == len(lst_o)
+    assert np.array_equal(nop, nop_o)
+    assert np.array_equal(ptr, ptr_o)
+    rows = s.lo.sort_rows(nop, ptr, lst)
+    assert np.array_equal(rows, lst_o)
+    assert pl.max_partners == nop_o.max()
+    if half:  # straight against the real reference's half list (hash in the golden file)
+        g = golden(s.rho)
+        assert sha(nop) == str(g["nop_half_sha256"]) and sha(rows) == str(g["list_half_sha256"])
+    ctx.check_loadedpair(pl)
+
+
+@pytest.mark.parametrize("layout", ["aos3", "soa"])
+def test_list_layouts_pointer64_sorted_rows(ctx, torch, sysS, layout):
+    s = sysS
+    qd, _ = s.device_arrays(torch, layout)
+    pl = ctx.makepair(qd, layout=layout, pointer64=True, sort_rows=True,
+                      pn=s.pn if layout == "soa" else None)
+    nop, ptr, lst = list_to_host(pl)
+    assert pl.pointer.dtype == torch.int64
+    assert np.array_equal(nop, s.full[0]) and np.array_equal(ptr, s.full[1])
+    assert np.array_equal(lst, s.full[2])  # LJ_LIST_SORT_ROWS: already ascending, like makepair()
+
+
+def test_list_deterministic_and_rebuild(ctx, torch, sysA):
+    qd, _ = sysA.device_arrays(torch, "aos4")
+    a = ctx.makepair(qd)
+    la = list_to_host(a)
+    b = ctx.makepair(qd)
+    lb = list_to_host(b)
+    for x, y in zip(la, lb):
+        assert np.array_equal(x, y)  # same row ORDER too: the build has no timing dependence
+    b.sorted_list.zero_(); b.number_of_partners.zero_()
+    ctx.rebuild(qd, b)  # asynchronous in-place rebuild
+    assert ctx.list_result() == (a.number_of_pairs, a.max_partners)
+    for x, y in zip(la, list_to_host(b)):
+        assert np.array_equal(x, y)
+
+
+def test_list_capacity_overflow_is_reported_not_written(ctx, torch, sysS):
+    from lj_gpu_b200 import LJError, PairList, _capi
+    qd, _ = sysS.device_arrays(torch, "aos4")
+    need = len(sysS.full[2])
+    cap, guard = need // 2, 4096
+    buf = torch.full((cap + guard,), -7, dtype=torch.int32, device="cuda")
+    small = PairList(torch.empty(sysS.pn, dtype=torch.int32, device="cuda"),
+                     torch.empty(sysS.pn, dtype=torch.int32, device="cuda"), buf[:cap], 0, 0)
+    with pytest.raises(LJError) as e:
+        ctx.makepair(qd, out=small)
+    assert e.value.status == _capi.LJ_ERR_CAPACITY
+    total = ctx.lib.lj_launch_count(ctx.h)  # context still usable after the error
+    assert total > 0
+    assert torch.all(buf[cap:] == -7)  # nothing past the capacity was touched
+    # the needed size is reported so the caller can re-allocate (makepair() does exactly that)
+    assert ctx.makepair(qd).number_of_pairs == need
+
+
+def test_list_threshold_semantics(ctx, torch, oracle):
+    # listed iff r2 < SL2 (strict), decided in FP64 even where the FP32 pre-filter cannot tell
+    sl = 3.3
+    pts = np.array([[0, 0, 0, 0], [sl, 0, 0, 0],                          # r2 == SL2: not listed
+                    [0, 50, 0, 0], [np.nextafter(sl, 0), 50, 0, 0],       # one ulp inside
+                    [0, 0, 50, 0], [np.nextafter(sl, 10), 0, 50, 0],      # one ulp outside
+                    [100, 100, 100, 0], [100 + 1e-9, 100, 100, 0],        # nearly coincident
+                    [30, 30, 30, 0], [30 + 1.9052558883257651, 30 + 1.9052558883257651, 30 + 1.9052558883257651, 0]],
+                   np.float64)
+    qd = torch.from_numpy(pts).cuda()
+    pl = ctx.makepair(qd)
+    nop, ptr, lst = list_to_host(pl)
+    nop_o, ptr_o, lst_o = oracle.makepair(pts[:, :3].copy(), full=True, brute=True)
+    assert nop_o[0] == 0 and nop_o[2] == 1 and nop_o[4] == 0 and nop_o[6] == 1
+    assert np.array_equal(nop, nop_o)
+    from oracle import ljoracle as lo
+    assert np.array_equal(lo.sort_rows(nop, ptr, lst), lst_o)
+
+
+def test_list_edge_sizes(ctx, torch, oracle):
+    for pts in (np.zeros((1, 4)), np.array([[0.0, 0, 0, 0], [1.2, 0, 0, 0]]),
+                np.array([[0.0, 0, 0, 0], [10.0, 0, 0, 0]])):
+        qd = torch.from_numpy(pts).cuda()
+        pl = ctx.makepair(qd)
+        nop_o, ptr_o, lst_o = oracle.makepair(pts[:, :3], full=True)
+        assert pl.number_of_pairs == len(lst_o)
+        assert np.array_equal(pl.number_of_partners.cpu().numpy()[:len(pts)], nop_o)
+    # sparse, non-cubic cloud with a different search length
+    rng = np.random.RandomState(3)
+    q = oracle.init_fcc(1.0, 12.0)
+    q = q[rng.rand(len(q)) < 0.5] * np.array([1.0, 0.4, 2.5]) + np.array([-7.0, 3.0, 0.125])
+    q4 = np.zeros((len(q), 4)); q4[:, :3] = q
+    pl = ctx.makepair(torch.from_numpy(q4).cuda(), search_len=2.1)
+    nop_o, ptr_o, lst_o = oracle.makepair(q, search_len=2.1, full=True)
+    nop, ptr, lst = list_to_host(pl)
+    from oracle import ljoracle as lo
+    assert np.array_equal(nop, nop_o) and np.array_equal(lo.sort_rows(nop, ptr, lst), lst_o)
+
+
+def test_row_range_build_for_ghosts(ctx, torch, sysS):
+    # rows only for "owned" particles [r0,r1); all particles remain candidates
+    s = sysS
+    qd, _ = s.device_arrays(torch, "aos4")
+    r0, r1 = s.pn // 5, s.pn // 2
+    pl = ctx.makepair(qd, rows=(r0, r1))
+    nop, ptr, lst = list_to_host(pl)
+    nop_o, ptr_o, lst_o = s.full
+    assert np.all(nop[:r0] == 0) and np.all(nop[r1:] == 0)
+    assert np.array_equal(nop[r0:r1], nop_o[r0:r1])
+    for i in (r0, (r0 + r1) // 2, r1 - 1):
+        assert sorted(lst[ptr[i]:ptr[i] + nop[i]]) == lst_o[ptr_o[i]:ptr_o[i] + nop_o[i]].tolist()
+
+
+# ------------------------------------------------------------------------ force, FP64
+FORCE_CASES = [("aos4", "subwarp", 8), ("aos4", "warp", 32), ("aos4", "thread", 1),
+               ("aos4", "subwarp", 4), ("aos4", "subwarp", 16), ("aos4", "subwarp", 2),
+               ("aos4", "tile", 8), ("aos4", "tile", 32), ("aos4", "tile", 4),
+               ("aos3", "subwarp", 8), ("aos3", "warp", 32), ("aos3", "tile", 16),
+               ("soa", "subwarp", 8), ("soa", "thread", 1), ("soa", "tile", 8)]
+
+
+@pytest.mark.parametrize("layout,variant,group", FORCE_CASES)
+def test_force_fp64_config_A(ctx, torch, sysA, golden, layout, variant, group):
+    s = sysA
+    qd, pd = s.device_arrays(torch, layout)
+    pn = s.pn if layout == "soa" else None
+    pl = ctx.makepair(qd, layout=layout, pn=pn)
+    ctx.force_loop(qd, pd, pl, loop=100, layout=layout, variant=variant, group=group, pn=pn)
+    ctx.sync()
+    assert s.err(pd, layout) < TOL_FP64
+    ph = s.p_host(pd, layout)
+    g = golden(0.5)  # full-precision sample dumped from the REAL reference (force_sorted x100)
+    assert np.abs(ph[g["sample_idx"]] - g["p_sorted_sample"]).max() / float(g["p_sorted_absmax"]) < TOL_FP64
+    rows = np.array(golden_rows(0.5))  # the published ref_data/density0.5.dat
+    assert np.abs(np.vstack([ph[:5], ph[-5:]]) - rows).max() < 1e-10
+    if layout == "aos4":
+        assert torch.all(pd[:, 3] == 77.5)  # .w preserved
+
+
+@pytest.mark.parametrize("layout,variant,group", [("aos4", "subwarp", 8), ("aos4", "tile", 8),
+                                                   ("aos3", "warp", 32), ("soa", "subwarp", 16)])
+def test_force_fp64_config_B(ctx, torch, sysB, golden, layout, variant, group):
+    s = sysB
+    qd, pd = s.device_arrays(torch, layout)
+    pn = s.pn if layout == "soa" else None
+    pl = ctx.makepair(qd, layout=layout, pn=pn)
+    ctx.force_loop(qd, pd, pl, loop=100, layout=layout, variant=variant, group=group, pn=pn,
+                   use_graph=True)
+    ctx.sync()
+    assert s.err(pd, layout) < TOL_FP64
+    ph = s.p_host(pd, layout)
+    g = golden(1.0)
+    assert np.abs(ph[g["sample_idx"]] - g["p_sorted_sample"]).max() / float(g["p_sorted_absmax"]) < TOL_FP64
+    from lj_gpu_b200 import print_results
+    with open(os.path.join(GOLDEN, "density1.dat")) as f:
+        assert print_results(ph) == f.read()  # byte-identical to ref_data/density1.dat
+
+
+def test_force_pointer64_and_thread_block(ctx, torch, sysS):
+    s = sysS
+    qd, _ = s.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd, pointer64=True)
+    for tb in (64, 256, 1024):
+        for variant, group in (("subwarp", 8), ("tile", 8), ("warp", 32)):
+            pd = torch.zeros_like(qd)
+            ctx.force_loop(qd, pd, pl, loop=s.steps, variant=variant, group=group, threads_per_block=tb)
+            assert s.err(pd, "aos4") < TOL_FP64, (tb, variant)
+
+
+def test_force_ell(ctx, torch, sysA, oracle):
+    s = sysA
+    qd, pd = s.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd, sort_rows=True)
+    tl = ctx.make_transposed_pairlist(pl)
+    tl_o, max_np = oracle.transpose_list(s.full[2], s.full[0], s.full[1])
+    assert pl.max_partners == max_np
+    assert np.array_equal(tl.cpu().numpy()[:max_np * s.pn], tl_o[:max_np * s.pn])  # zero padded too
+    ctx.force_loop(qd, pd, pl, loop=100, ell=True)
+    assert s.err(pd, "aos4") < TOL_FP64
+    q3, p3 = s.device_arrays(torch, "aos3")
+    ctx.force_loop(q3, p3, pl, loop=100, ell=True, layout="aos3")
+    assert s.err(p3, "aos3") < TOL_FP64
+
+
+@pytest.mark.parametrize("layout,group", [("aos4", 8), ("aos4", 32), ("aos3", 1), ("soa", 8)])
+def test_force_newton3_half_list(ctx, torch, sysA, layout, group):
+    s = sysA
+    qd, pd = s.device_arrays(torch, layout)
+    pn = s.pn if layout == "soa" else None
+    pl = ctx.makepair(qd, half=True, layout=layout, pn=pn)
+    assert pl.number_of_pairs == 2268138  # P_half of config A
+    ctx.force_loop(qd, pd, pl, loop=100, layout=layout, variant="n3", group=group, pn=pn)
+    assert s.err(pd, layout) < TOL_FP64
+
+
+@pytest.mark.parametrize("which", ["A", "B"])
+@pytest.mark.parametrize("layout,group", [("aos4", 8), ("aos4", 32), ("aos3", 4), ("soa", 8)])
+def test_force_mixed(ctx, torch, sysA, sysB, which, layout, group):
+    s = sysA if which == "A" else sysB
+    qd, pd = s.device_arrays(torch, layout)
+    pn = s.pn if layout == "soa" else None
+    pl = ctx.makepair(qd, layout=layout, pn=pn)
+    ctx.force_loop(qd, pd, pl, loop=100, layout=layout, group=group, precision="mixed", pn=pn)
+    e = s.err(pd, layout)
+    assert e < TOL_MIXED, e
+    assert e > 1e-14  # it really is the FP32 path
+
+
+def test_row_order_is_irrelevant_and_gather_is_reproducible(ctx, torch, sysA):
+    s = sysA
+    qd, _ = s.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd)
+    ref = torch.zeros_like(qd)
+    ctx.force_loop(qd, ref, pl, loop=5, group=8)
+    again = torch.zeros_like(qd)
+    ctx.force_loop(qd, again, pl, loop=5, group=8)
+    assert torch.equal(ref, again)  # no atomics in the gather path: bit-reproducible
+    before = s.lo.sort_rows(*list_to_host(pl))
+    ctx.random_shfl(pl, seed=10)
+    nop, ptr, lst = list_to_host(pl)
+    assert not np.array_equal(lst, s.full[2])
+    assert np.array_equal(s.lo.sort_rows(nop, ptr, lst), before)  # a permutation within rows
+    for variant, group in (("subwarp", 8), ("tile", 8), ("warp", 32)):
+        pd = torch.zeros_like(qd)
+        ctx.force_loop(qd, pd, pl, loop=5, variant=variant, group=group)
+        assert (pd - ref)[:, :3].abs().max().item() / ref[:, :3].abs().max().item() < 1e-13
+
+
+def test_force_cutoff_semantics(ctx, torch, oracle):
+    # r2 == CL2 contributes, r2 just above does not (cuda/kernel.cuh:30 `if (r2 > CL2) df = 0`)
+    pts = np.array([[0, 0, 0, 0], [3.0, 0, 0, 0], [0, 40, 0, 0], [np.nextafter(3.0, 4), 40, 0, 0]], np.float64)
+    qd = torch.from_numpy(pts).cuda()
+    pl = ctx.makepair(qd)
+    nop, ptr, lst = oracle.makepair(pts[:, :3], full=True)
+    po = np.zeros((4, 3))
+    oracle.force_gather(pts[:, :3].copy(), po, nop, ptr, lst)
+    assert po[0, 0] != 0 and po[2, 0] == 0
+    for variant, group, prec in (("subwarp", 8, "fp64"), ("tile", 8, "fp64"), ("thread", 1, "fp64"),
+                                 ("subwarp", 8, "mixed")):
+        pd = torch.zeros_like(qd)
+        ctx.force_step(qd, pd, pl, variant=variant, group=group, precision=prec)
+        ph = pd.cpu().numpy()[:, :3]
+        assert ph[2, 0] == 0 and ph[3, 0] == 0
+        assert abs(ph[0, 0] - po[0, 0]) <= (1e-14 if prec == "fp64" else 1e-6) * abs(po[0, 0])
+        assert ph[1, 0] == -ph[0, 0]
+
+
+def test_force_row_range(ctx, torch, sysS):
+    s = sysS
+    qd, pd = s.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd)
+    r0, r1 = 100, s.pn - 333
+    for variant in ("subwarp", "tile"):
+        pd.zero_()
+        ctx.force_loop(qd, pd, pl, loop=s.steps, variant=variant, group=8, rows=(r0, r1))
+        ph = pd.cpu().numpy()[:, :3]
+        assert np.all(ph[:r0] == 0) and np.all(ph[r1:] == 0)
+        assert np.abs(ph[r0:r1] - s.p[r0:r1]).max() / s.scale < TOL_FP64
+
+
+def test_bad_arguments_are_rejected(ctx, torch, sysS):
+    from lj_gpu_b200 import LJError
+    from lj_gpu_b200 import _capi
+    qd, pd = sysS.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd)
+    with pytest.raises(LJError) as e:
+        ctx.force_step(qd, pd, pl, threads_per_block=48)  # reference CLI range is 64..1024
+    assert e.value.status == _capi.LJ_ERR_BAD_ARG
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl, group=3)
+    mis = torch.zeros(sysS.pn * 4 + 1, dtype=torch.float64, device="cuda")[1:].view(sysS.pn, 4)
+    with pytest.raises(LJError):
+        ctx.force_step(mis, pd, pl)  # double4 must be 32-byte aligned
+    with pytest.raises(LJError):
+        ctx.makepair(qd, search_len=-1.0)
+    bad = ctx.makepair(qd)
+    bad.sorted_list[5] = sysS.pn + 3
+    with pytest.raises(LJError) as e:
+        ctx.check_loadedpair(bad)
+    assert e.value.status == _capi.LJ_ERR_INVALID_LIST
+
+
+# ------------------------------------------------------------------------ measure() / memory layer
+def test_measure_host_buffers_reproduce_goldens(ctx, torch, sysA):
+    from lj_gpu_b200 import print_results
+    s = sysA
+    for layout, kw in (("aos3", dict(variant="warp")), ("aos4", dict(variant="tile", group=8, rebuild_every=20)),
+                       ("aos4", dict(variant="auto", use_graph=True, rebuild_every=20))):
+        w = 3 if layout == "aos3" else 4
+        qh = np.zeros((s.pn, w)); qh[:, :3] = s.q
+        ph = np.zeros((s.pn, w))
+        m = ctx.measure(qh, ph, layout=layout, loop=100, **kw)
+        assert m.number_of_pairs == 4536276 and m.max_partners == 78
+        assert m.list_builds == (5 if kw.get("rebuild_every") else 1)
+        with open(os.path.join(GOLDEN, "density0.5.dat")) as f:
+            assert print_results(ph) == f.read()
+        assert np.abs(ph[:, :3] - s.p).max() / s.scale < TOL_FP64
+        assert m.h2d_bytes == 2 * qh.nbytes and m.d2h_bytes == ph.nbytes
+    # the reference's own flow: host-built list uploaded by copy_to_gpu; half list -> Newton-3
+    nop, ptr, lst = s.half
+    qh = np.zeros((s.pn, 4)); qh[:, :3] = s.q
+    ph = np.zeros((s.pn, 4))
+    m = ctx.measure(qh, ph, layout="aos4", loop=100, half=True, host_list=(nop, ptr.astype(np.int32), lst))
+    assert m.list_builds == 0 and m.number_of_pairs == len(lst)
+    assert np.abs(ph[:, :3] - s.p).max() / s.scale < TOL_FP64
+
+
+def test_cuda_ptr_semantics(ctx, torch):
+    # the reference's disabled unit test (cuda/cuda_ptr.cuh:106-147): copy round trip, set_val ranges
+    n = 256
+    fl = ctx.cuda_ptr(np.float32, n)
+    fl.host[:] = 3.0
+    fl.host2dev()
+    fl.host[:] = 0.0
+    fl.dev2host()
+    ctx.sync()
+    assert np.all(fl.host == 3.0)
+    fl.set_val(12.0)
+    fl.set_val(0.0, 10, 87)
+    expect = np.full(n, 12.0, np.float32); expect[10:97] = 0.0
+    assert np.array_equal(fl.host, expect)  # host mirror
+    fl.host[:] = -1
+    fl.dev2host(5, 100)
+    ctx.sync()
+    assert np.array_equal(fl.host[5:105], expect[5:105]) and np.all(fl.host[:5] == -1)
+    fl.deallocate()
+    # pageable upload/download through the staging ring, larger than one ring half
+    from lj_gpu_b200 import _capi
+    import ctypes as C
+    big = np.arange(12 * 1024 * 1024, dtype=np.int64)
+    d = torch.empty(big.size, dtype=torch.int64, device="cuda")
+    lib = _capi.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.lj_upload(ctx.h, d.data_ptr(), big.ctypes.data, big.nbytes, st) == 0
+    back = np.zeros_like(big)
+    assert lib.lj_download(ctx.h, back.ctypes.data, d.data_ptr(), big.nbytes, st) == 0
+    ctx.sync()
+    assert np.array_equal(back, big) and torch.equal(d[-3:].cpu(), torch.from_numpy(big[-3:]))
+
+
+def test_cpp_driver_prints_the_goldens():
+    exe = os.path.join(ROOT, "lj_gpu_b200", "driver", "force_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    for args, gold in ((["--test"], "density0.5.dat"), (["--test", "--density", "1.0", "256"], "density1.dat")):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        with open(os.path.join(GOLDEN, gold)) as f:
+            assert r.stdout == f.read()
+        assert "[sec] (without Host<->Device)" in r.stderr and "force_kernel_warp_unroll2_double3" in r.stderr
+    r = subprocess.run([exe, "32"], capture_output=True, text=True)
+    assert r.returncode == 1 and "THREAD_BLOCK size is too large or small." in r.stderr
+
+
+# ------------------------------------------------------------------------ full size (config C)
+def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
+    """BASELINE config 3: FCC rho=1.0, 63 cells/side -> N=1,000,188.  Full oracle comparison
+    for the list (cell-list restatement) and 3 force steps, plus size-independent properties."""
+    from lj_gpu_b200 import init_fcc
+    from oracle import ljoracle as lo
+    q = init_fcc(1.0, 100.1)
+    pn = q.shape[0]
+    assert pn == 1000188
+    q4 = np.zeros((pn, 4)); q4[:, :3] = q
+    qd = torch.from_numpy(q4).cuda()
+    full = ctx.makepair(qd)
+    half = ctx.makepair(qd, half=True)
+    assert full.number_of_pairs == 2 * half.number_of_pairs          # every pair listed both ways
+    nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
+    nop, ptr, lst = list_to_host(full)
+    assert full.number_of_pairs == len(lst_o)
+    assert np.array_equal(nop, nop_o) and np.array_equal(ptr, ptr_o)
+    assert np.array_equal(lo.sort_rows(nop, ptr, lst), lst_o)        # bit-exact, all 1.4e8 entries
+    p_o = np.zeros_like(q)
+    oracle.force_gather(q, p_o, nop_o, ptr_o, lst_o, steps=3)
+    scale = np.abs(p_o).max()
+    results = {}
+    for variant, group in (("subwarp", 8), ("tile", 8), ("warp", 32)):
+        pd = torch.zeros_like(qd)
+        ctx.force_loop(qd, pd, full, loop=3, variant=variant, group=group)
+        ph = pd.cpu().numpy()[:, :3]
+        assert np.abs(ph - p_o).max() / scale < TOL_FP64
+        results[variant] = pd
+        # Newton's third law: the directed contributions cancel pairwise -> total momentum ~ 0
+        assert np.abs(ph.sum(axis=0)).max() < 1e-9 * scale * np.sqrt(pn)
+    # linearity in the step count with static positions: p(6 steps) == 2 * p(3 steps)
+    pd6 = torch.zeros_like(qd)
+    ctx.force_loop(qd, pd6, full, loop=6, group=8)
+    assert (pd6 - 2 * results["subwarp"])[:, :3].abs().max().item() / scale < 1e-14
+    # half list + Newton-3 and mixed precision at full size
+    pn3 = torch.zeros_like(qd)
+    ctx.force_loop(qd, pn3, half, loop=3, variant="n3", group=8)
+    assert np.abs(pn3.cpu().numpy()[:, :3] - p_o).max() / scale < TOL_FP64
+    pmx = torch.zeros_like(qd)
+    ctx.force_loop(qd, pmx, full, loop=3, group=8, precision="mixed")
+    assert np.abs(pmx.cpu().numpy()[:, :3] - p_o).max() / scale < TOL_MIXED
