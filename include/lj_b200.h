@@ -5,7 +5,7 @@
  * inside measure() (cuda/force_cuda.cu:334) and the neighbour-list build that feeds it
  * (cuda/force_cuda.cu:122-163).  Every entry point names the reference interface it replaces.
  * Plain pointers and sizes only; all device work is asynchronous on the caller's stream
- * (a cudaStream_t passed as void*, NULL = the context's own stream).  No function exits the
+ * (a cudaStream_t passed as void*, NULL = the CUDA legacy default stream).  No function exits the
  * process: each returns an lj_status and leaves a message in lj_last_error_string().
  *
  * Ownership: the caller owns every array it passes (as the reference driver owns its
@@ -76,7 +76,7 @@ typedef enum lj_precision {
 /* Creates a context on `device` (a CUDA ordinal).  LJ_ERR_NO_DEVICE when CUDA is absent. */
 LJ_API int lj_ctx_create(lj_ctx** out, int device);
 LJ_API int lj_ctx_destroy(lj_ctx* ctx);
-/* replaces cudaDeviceSynchronize() in measure() (cuda/force_cuda.cu:336); stream NULL =
+/* replaces cudaDeviceSynchronize() in measure() (cuda/force_cuda.cu:336); stream NULL = the default stream and
  * every stream the context owns */
 LJ_API int lj_sync(lj_ctx* ctx, void* stream);
 LJ_API const char* lj_last_error_string(lj_ctx* ctx);

@@ -88,7 +88,9 @@ int lj_set_error(lj_ctx* ctx, int status, const char* what, const char* detail);
     if (e__ != cudaSuccess) return lj_set_error((ctx), LJ_ERR_CUDA, "kernel launch", cudaGetErrorString(e__)); \
   } while (0)
 
-static inline cudaStream_t lj_stream(lj_ctx* ctx, void* s) { return s ? (cudaStream_t)s : ctx->stream; }
+// NULL is the CUDA legacy default stream, exactly as for a kernel launch: the reference runs
+// everything there (cuda/force_cuda.cu:334) and torch hands out 0 for its default stream.
+static inline cudaStream_t lj_stream(lj_ctx* ctx, void* s) { (void)ctx; return (cudaStream_t)s; }
 
 // internal entry points shared between translation units
 int lj_scratch_reserve(lj_ctx* ctx, int64_t pn, cudaStream_t st);

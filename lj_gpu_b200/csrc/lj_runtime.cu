@@ -115,6 +115,7 @@ int lj_sync(lj_ctx* ctx, void* stream) {
   if (stream) {
     LJ_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
   } else {
+    LJ_CUDA(ctx, cudaStreamSynchronize(nullptr));  // legacy default stream
     LJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     LJ_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   }
