@@ -1,13 +1,20 @@
 // lj_force_tile.cu -- CTA-tile gather kernel with TMA-staged neighbour indices (sm_100a).
 //
-// A CTA owns a tile of R consecutive rows.  In a compact CSR list (pointer = exclusive scan of
-// number_of_partners, which is what makepair() and lj_build_list produce) the j-indices of R
-// consecutive rows are ONE contiguous segment of sorted_list, so a producer warp fetches the
+// A CTA owns tiles of kTileRows consecutive rows.  In a compact CSR list (pointer = exclusive
+// scan of number_of_partners, which is what makepair() and lj_build_list produce) the j-indices
+// of consecutive rows are ONE contiguous segment of sorted_list, so a producer warp fetches the
 // whole segment with a single cp.async.bulk (TMA bulk copy, SASS UBLKCP) into shared memory,
-// signalled through an mbarrier, double-buffered against the consumer warps that do the
-// gather + FP64 pair math with G lanes per row.  The list -- the only compulsory HBM stream of
-// the force step -- is thus read exactly once, in 16-byte-aligned bulk transactions, and never
-// occupies L1/LSU wavefronts that the q[j] gather needs.
+// signalled through an mbarrier and double-buffered against eight consumer warps.  The list --
+// the only compulsory HBM stream of the force step -- is read exactly once, in 16-byte-aligned
+// bulk transactions, and costs the consumers one conflict-free LDS wavefront per 32 pairs instead
+// of LSU/L1 wavefronts, which the q[j] gather needs (ncu: the plain gather kernel sits at 91 % of
+// the L1 data-pipe wavefront peak).
+//
+// Consumer mapping: a group of G lanes walks its rows ONE AFTER THE OTHER, G consecutive list
+// entries per step (sorted/stencil-ordered rows make those j's runs of consecutive particles, so
+// a 32-lane gather touches ~10 128-byte lines instead of ~15 for four interleaved rows), keeps
+// one accumulator triple per row for a batch of up to 4 rows and reduces the batch with a
+// transposing butterfly: 1.5 DADD per row and component instead of log2(G).
 //
 // Robustness: nothing is assumed about pointer[].  Each row checks that its range lies inside
 // the staged segment and otherwise reads its indices from global memory, so arbitrary
@@ -16,9 +23,12 @@
 
 namespace {
 
-constexpr int kConsumerThreads = 256;
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kTileThreads = kConsumerThreads + 32;  // + one producer warp
-constexpr int kUnroll = 4;
+constexpr int kTileRows = 64;
+constexpr int kCapPerRow = 160;  // staged entries per row on average (rho=1.0, 3.3 sigma: <= 151)
+constexpr int kCapInts = kTileRows * kCapPerRow;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -56,39 +66,80 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// One row: G lanes, entries lg, lg+G, ...; two chunks in flight, single-chunk tail.
 template <int G, int LAYOUT, bool SMEM>
 __device__ __forceinline__ void row_loop(const void* __restrict__ q, int64_t plane,
-                                         const int32_t* __restrict__ row, int np, int lg, double xi,
-                                         double yi, double zi, double c24, double c48,
+                                         const int32_t* __restrict__ row, int np, int lg, int self,
+                                         unsigned gmask,
+                                         double xi, double yi, double zi, double c24, double c48,
                                          long long cl2_bits, double& fx, double& fy, double& fz) {
   int k = lg;
-  for (; k + (kUnroll - 1) * G < np; k += kUnroll * G) {
-    int j[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; u++) j[u] = SMEM ? row[k + u * G] : __ldg(row + k + u * G);
-    double xj[kUnroll], yj[kUnroll], zj[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; u++) load_pos<LAYOUT>(q, j[u], plane, xj[u], yj[u], zj[u]);
-#pragma unroll
-    for (int u = 0; u < kUnroll; u++)
-      lj_pair(xj[u] - xi, yj[u] - yi, zj[u] - zi, c24, c48, cl2_bits, fx, fy, fz);
+  for (; k + G < np; k += 2 * G) {  // both chunks have a valid entry for this lane
+    const int j0 = SMEM ? row[k] : __ldg(row + k);
+    const int j1 = SMEM ? row[k + G] : __ldg(row + k + G);
+    double x0, y0, z0, x1, y1, z1;
+    load_pos<LAYOUT>(q, j0, plane, x0, y0, z0);
+    load_pos<LAYOUT>(q, j1, plane, x1, y1, z1);
+    lj_pair(x0 - xi, y0 - yi, z0 - zi, c24, c48, cl2_bits, fx, fy, fz);
+    lj_pair(x1 - xi, y1 - yi, z1 - zi, c24, c48, cl2_bits, fx, fy, fz);
   }
-  for (; k < np; k += G) {
-    const int j = SMEM ? row[k] : __ldg(row + k);
+  // at most one more entry for this lane; lanes without one compute on `self` and are masked by
+  // an impossible cutoff (r2 bit patterns are never negative)
+  const bool valid = k < np;
+  if (__ballot_sync(gmask, valid) != 0u) {  // uniform within the group
+    const int j = valid ? (SMEM ? row[k] : __ldg(row + k)) : self;
     double xj, yj, zj;
     load_pos<LAYOUT>(q, j, plane, xj, yj, zj);
-    lj_pair(xj - xi, yj - yi, zj - zi, c24, c48, cl2_bits, fx, fy, fz);
+    lj_pair(xj - xi, yj - yi, zj - zi, c24, c48, valid ? cl2_bits : -1ll, fx, fy, fz);
   }
 }
 
+__device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
+
+// Sum over the G lanes of a group for B rows at once.  On return lane l holds in `out` the total
+// of row  ((l & G/2) ? B/2 : 0) + ((l & G/4) ? B/4 : 0) ...  (the bits consumed by the
+// transposing steps); every lane of the group holds a valid total for "its" row.
+template <int G, int B>
+__device__ __forceinline__ double batch_sum(const double (&a)[B], int lg, unsigned gmask,
+                                            int& my_row) {
+  static_assert(B == 1 || B == 2 || B == 4, "batch of 1, 2 or 4 rows");
+  double v;
+  int stride = G / 2;
+  my_row = 0;
+  if (B == 4) {
+    const bool up = (lg & stride) != 0;
+    double k0 = sel(up, a[2], a[0]) + __shfl_xor_sync(gmask, sel(up, a[0], a[2]), stride);
+    double k1 = sel(up, a[3], a[1]) + __shfl_xor_sync(gmask, sel(up, a[1], a[3]), stride);
+    my_row = up ? 2 : 0;
+    stride >>= 1;
+    const bool up2 = (lg & stride) != 0;
+    v = sel(up2, k1, k0) + __shfl_xor_sync(gmask, sel(up2, k0, k1), stride);
+    my_row += up2 ? 1 : 0;
+    stride >>= 1;
+  } else if (B == 2) {
+    const bool up = (lg & stride) != 0;
+    v = sel(up, a[1], a[0]) + __shfl_xor_sync(gmask, sel(up, a[0], a[1]), stride);
+    my_row = up ? 1 : 0;
+    stride >>= 1;
+  } else {
+    v = a[0];
+  }
+  for (; stride >= 1; stride >>= 1) v += __shfl_xor_sync(gmask, v, stride);
+  return v;
+}
+
 template <int G, int LAYOUT, bool PTR64>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 2)
 lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_begin, int64_t row_end,
                int64_t plane, double c24, double c48, long long cl2_bits,
                const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
-               const void* __restrict__ pointer, int64_t list_entries, int cap_ints) {
-  constexpr int R = kConsumerThreads / G;  // rows per tile
-  extern __shared__ __align__(16) int32_t stage[];  // 2 x cap_ints
+               const void* __restrict__ pointer, int64_t list_entries) {
+  constexpr int R = kTileRows;
+  constexpr int RG = R * G / kConsumerThreads;  // rows per group and tile
+  constexpr int B = RG >= 4 ? 4 : RG;           // rows reduced together
+  static_assert(RG >= 1 && RG % B == 0, "tile rows must split evenly over the groups");
+  static_assert(G >= 2 * B || B == 1, "the transposing butterfly needs G >= 2B lanes");
+  extern __shared__ __align__(16) int32_t stage[];  // 2 x kCapInts
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
   __shared__ long long seg_base[2];
   __shared__ int seg_len[2];
@@ -97,7 +148,7 @@ lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; b++) {
       mbar_init(&full_bar[b], 1);
-      mbar_init(&empty_bar[b], kConsumerThreads / 32);
+      mbar_init(&empty_bar[b], kConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -106,7 +157,7 @@ lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
   const int64_t rows = row_end - row_begin;
   const int64_t ntiles = (rows + R - 1) / R;
 
-  if (warp == kConsumerThreads / 32) {
+  if (warp == kConsumerWarps) {
     // ------------------------------ producer warp: one elected lane drives the TMA -------
     if (lane == 0) {
       int n = 0;
@@ -120,14 +171,14 @@ lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
         const int64_t s0a = s0 & ~(int64_t)3;  // 16-byte aligned start
         int64_t len = s1 - s0a;
         if (len < 0) len = 0;
-        if (len > cap_ints) len = cap_ints;
+        if (len > kCapInts) len = kCapInts;
         const int64_t up = (len + 3) & ~(int64_t)3;
-        len = (up <= cap_ints && s0a + up <= list_entries) ? up : (len & ~(int64_t)3);
+        len = (up <= kCapInts && s0a + up <= list_entries) ? up : (len & ~(int64_t)3);
         seg_base[b] = s0a;
         seg_len[b] = (int)len;
         if (len > 0) {
           mbar_arrive_expect_tx(&full_bar[b], (uint32_t)(len * 4));
-          bulk_g2s(stage + (size_t)b * cap_ints, list + s0a, (uint32_t)(len * 4), &full_bar[b]);
+          bulk_g2s(stage + (size_t)b * kCapInts, list + s0a, (uint32_t)(len * 4), &full_bar[b]);
         } else {
           mbar_arrive(&full_bar[b]);
         }
@@ -138,11 +189,15 @@ lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
 
   // -------------------------------- consumer warps --------------------------------------
   const int lg = threadIdx.x % G;
+  const int group = threadIdx.x / G;  // 0 .. 256/G-1
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lg));
   int n = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, n++) {
     const int b = n & 1;
-    const int64_t i = row_begin + t * R + threadIdx.x / G;
-    const bool active = i < row_end;
+    const int64_t gfirst = row_begin + t * R + (int64_t)group * RG;  // this group's first row
+    // metadata of the group's first row, fetched before waiting for the list
+    int64_t i = gfirst;
+    bool active = i < row_end;
     double xi = 0.0, yi = 0.0, zi = 0.0;
     int np = 0;
     int64_t off = 0;
@@ -152,33 +207,56 @@ lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
       off = row_offset<PTR64>(pointer, i);
     }
     mbar_wait(&full_bar[b], (n >> 1) & 1);
-    const int64_t rel = off - seg_base[b];
-    const bool in_smem = rel >= 0 && rel + np <= (int64_t)seg_len[b];
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    if (in_smem)
-      row_loop<G, LAYOUT, true>(q, plane, stage + (size_t)b * cap_ints + rel, np, lg, xi, yi, zi, c24,
-                                c48, cl2_bits, fx, fy, fz);
-    else
-      row_loop<G, LAYOUT, false>(q, plane, list + off, np, lg, xi, yi, zi, c24, c48, cl2_bits, fx, fy,
-                                 fz);
+    const int64_t sbase = seg_base[b];
+    const int slen = seg_len[b];
+    const int32_t* __restrict__ sbuf = stage + (size_t)b * kCapInts;
+
+#pragma unroll 1
+    for (int batch = 0; batch < RG / B; batch++) {
+      double ax[B], ay[B], az[B];
+#pragma unroll
+      for (int r = 0; r < B; r++) {
+        ax[r] = 0.0; ay[r] = 0.0; az[r] = 0.0;
+        // prefetch the next row's metadata while this row computes
+        const int64_t inext = i + 1;
+        const bool anext = inext < row_end && (batch * B + r + 1) < RG;
+        double xn = 0.0, yn = 0.0, zn = 0.0;
+        int npn = 0;
+        int64_t offn = 0;
+        if (anext) {
+          load_pos<LAYOUT>(q, inext, plane, xn, yn, zn);
+          npn = __ldg(nop + inext);
+          offn = row_offset<PTR64>(pointer, inext);
+        }
+        if (active) {
+          const int64_t rel = off - sbase;
+          if (rel >= 0 && rel + np <= (int64_t)slen)
+            row_loop<G, LAYOUT, true>(q, plane, sbuf + rel, np, lg, (int)i, gmask, xi, yi, zi, c24,
+                                      c48, cl2_bits, ax[r], ay[r], az[r]);
+          else
+            row_loop<G, LAYOUT, false>(q, plane, list + off, np, lg, (int)i, gmask, xi, yi, zi, c24,
+                                       c48, cl2_bits, ax[r], ay[r], az[r]);
+        }
+        i = inext; active = anext; xi = xn; yi = yn; zi = zn; np = npn; off = offn;
+      }
+      int my_row;
+      const double sx = batch_sum<G, B>(ax, lg, gmask, my_row);
+      const double sy = batch_sum<G, B>(ay, lg, gmask, my_row);
+      const double sz = batch_sum<G, B>(az, lg, gmask, my_row);
+      // one writer lane per row: the lane whose non-transposed low bits are zero
+      constexpr int kLow = (B == 4) ? G / 4 : (B == 2) ? G / 2 : G;
+      const int64_t wrow = gfirst + batch * B + my_row;
+      if ((lg & (kLow - 1)) == 0 && wrow < row_end) add_mom<LAYOUT>(p, wrow, plane, sx, sy, sz);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[b]);  // this warp no longer reads stage[b]
-    if (G > 1) {
-      fx = group_sum<G>(fx);
-      fy = group_sum<G>(fy);
-      fz = group_sum<G>(fz);
-    }
-    if (active && lg == 0) add_mom<LAYOUT>(p, i, plane, fx, fy, fz);
   }
 }
 
 template <int G, int LAYOUT, bool PTR64>
 int launch_tile(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, double c24, double c48,
                 long long cl2_bits, cudaStream_t st) {
-  constexpr int R = kConsumerThreads / G;
-  // stage capacity: 224 entries per row covers rho = 1.0 / 3.3 sigma (max 149) with slack
-  const int cap_ints = R * 224;
-  const size_t smem = (size_t)2 * cap_ints * sizeof(int32_t);
+  const size_t smem = (size_t)2 * kCapInts * sizeof(int32_t);
   auto kern = lj_gather_tile<G, LAYOUT, PTR64>;
   static bool configured = false;
   static int per_sm = 1;
@@ -188,12 +266,12 @@ int launch_tile(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, dou
     if (per_sm < 1) per_sm = 1;
     configured = true;
   }
-  const int64_t ntiles = (r1 - r0 + R - 1) / R;
-  int64_t grid = (int64_t)ctx->sm_count * per_sm;
+  const int64_t ntiles = (r1 - r0 + kTileRows - 1) / kTileRows;
+  int64_t grid = (int64_t)ctx->sm_count * per_sm;  // persistent: one wave, tiles strided
   if (grid > ntiles) grid = ntiles;
   kern<<<(unsigned)grid, kTileThreads, smem, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24, c48,
                                                     cl2_bits, a->list, a->number_of_partners,
-                                                    a->pointer, a->list_entries, cap_ints);
+                                                    a->pointer, a->list_entries);
   LJ_LAUNCHED(ctx);
   return LJ_OK;
 }

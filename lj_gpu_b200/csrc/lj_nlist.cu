@@ -49,17 +49,23 @@ k_bbox(const void* __restrict__ q, int64_t pn, int64_t plane, unsigned long long
   }
 }
 
-struct grid_ext {  // lj_grid_params + the FP32 pre-filter margin, lives right behind it
+struct grid_ext {  // lj_grid_params + the FP32 pre-filter constants, lives right behind it
   lj_grid_params g;
-  float margin;    // |r2_f32 - r2_f64| bound for candidates within two cells
-  float sl2f;
+  int ncell1;      // ncell + 1: the scanned histogram carries a sentinel (cell_start[ncell] = pn)
+  float margin;    // |r2_f32 - r2_f64| bound for stencil candidates
+  float sl2f;      // search^2
+  float edge;      // cell edge (>= search/2)
+  float inv_edge;
+  float pad;       // bound on the float error of a shifted coordinate / cell boundary
 };
 
+// Cells of edge >= search/2 and a 5x5x5 stencil: 4.6x the sphere volume instead of the 7.7x of
+// search-sized cells with 27 neighbours; the x-chord trimming in k_search brings it to ~2.5x.
 __global__ void k_grid_setup(const unsigned long long* bb, double search_len, int64_t cap_cells,
                              grid_ext* out) {
   double lo[3], hi[3];
   for (int d = 0; d < 3; d++) { lo[d] = dec_ordered(bb[d]); hi[d] = dec_ordered(bb[3 + d]); }
-  double edge = search_len * (1.0 + 1e-9);  // strictly larger: no neighbour two cells away
+  double edge = 0.5 * search_len * (1.0 + 1e-9);  // strictly larger: no neighbour 3 cells away
   int n[3];
   for (;;) {
     double cells = 1.0;
@@ -69,23 +75,27 @@ __global__ void k_grid_setup(const unsigned long long* bb, double search_len, in
       n[d] = (int)c;
       cells *= c;
     }
-    if (cells <= (double)cap_cells) break;
-    edge *= 1.26;  // sparse cloud: coarser cells stay correct for a 27-cell stencil
+    if (cells + 1.0 <= (double)cap_cells) break;
+    edge *= 1.26;  // sparse cloud: coarser cells stay correct for the +-2 stencil
   }
   out->g.ox = lo[0]; out->g.oy = lo[1]; out->g.oz = lo[2];
   out->g.inv_cell = 1.0 / edge;
   out->g.nx = n[0]; out->g.ny = n[1]; out->g.nz = n[2];
   out->g.ncell = n[0] * n[1] * n[2];
+  out->ncell1 = out->g.ncell + 1;
   // FP32 pre-filter error budget.  E = largest extent; a shifted coordinate rounds to float
-  // with error <= 2^-24 E, a float difference of two of them adds <= 2^-24 |d|, |d| <= 2 edge
+  // with error <= 2^-24 E, a float difference of two of them adds <= 2^-24 |d|, |d| <= 3 edge
   // for stencil candidates.  r2 error <= sum_c (2|d| delta + delta^2) + rounding of the
   // three multiply-adds.  Doubled for safety.
   double E = fmax(hi[0] - lo[0], fmax(hi[1] - lo[1], hi[2] - lo[2]));
   const double u = 5.9604644775390625e-8;  // 2^-24
-  double delta = 2.0 * u * E + u * 2.0 * edge;
-  double m = 3.0 * (4.0 * edge * delta + delta * delta) + 4.0 * u * 12.0 * edge * edge;
+  double delta = 2.0 * u * E + u * 3.0 * edge;
+  double m = 3.0 * (6.0 * edge * delta + delta * delta) + 4.0 * u * 27.0 * edge * edge;
   out->margin = (float)(2.0 * m);
   out->sl2f = (float)(search_len * search_len);
+  out->edge = (float)edge;
+  out->inv_edge = (float)(1.0 / edge);
+  out->pad = (float)(8.0 * u * (E + edge) + 1e-30);
 }
 
 __device__ __forceinline__ int cell_coord(double v, double o, double inv, int n) {
@@ -236,83 +246,115 @@ k_scan_down(const uint32_t* __restrict__ in, int64_t n, const int* __restrict__ 
 }
 
 // ------------------------------------------------------------------ stencil search ----
-// One warp per particle (in cell order).  For each of the 9 (dz,dy) rows of the 27-cell
-// stencil the three x-adjacent cells are one contiguous range of sorted_pos32, which the
-// warp streams with coalesced 16 B loads.  FILL=false counts, FILL=true writes the row.
+// kSearchLanes lanes per particle (visited in cell order), 4 particles per warp.  For each of
+// the 25 (dz,dy) rows of the +-2 stencil the x-adjacent cells are ONE contiguous range of
+// sorted_pos32; the range is trimmed to the chord of the search sphere at that (dy,dz) before
+// the group streams it with 16 B loads.  Classification per candidate: FP32 r2 on origin-shifted
+// coordinates; only candidates within the representation error of the threshold (or of zero:
+// the particle itself / coincident particles) take the exact FP64 path.  Hits are compacted
+// with a group ballot.  FILL=false counts, FILL=true writes the row.
+constexpr int kSearchLanes = 8;
+
 template <bool FILL, bool PTR64>
 __global__ void __launch_bounds__(256)
 k_search(int64_t pn, const grid_ext* __restrict__ ge, const int32_t* __restrict__ cell_of,
-         const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+         const uint32_t* __restrict__ cell_start,
          const double4* __restrict__ sorted_pos, const float4* __restrict__ sorted_pos32,
          double sl2, int half, int64_t row_begin, int64_t row_end,
          int32_t* __restrict__ nop, const void* __restrict__ pointer, int32_t* __restrict__ list,
          int64_t capacity, lj_list_totals* __restrict__ tot) {
-  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // slot in cell order
+  constexpr int GL = kSearchLanes;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;  // slot in cell order
   const int lane = threadIdx.x & 31;
-  if (s >= pn) return;
-  const float4 me32 = sorted_pos32[s];
+  const int lg = lane % GL;
+  const unsigned gbits = ((1u << GL) - 1u) << (lane - lg);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // The four groups of a warp stay CONVERGED: every loop below has a warp-uniform trip count
+  // and inactive / finished groups ride along predicated off.  (Letting groups diverge made
+  // each instruction issue once per group: 4x the instruction count, ncu round 1.)
+  bool active = s < pn;
+  float4 me32 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) me32 = sorted_pos32[s];
   const int i = __float_as_int(me32.w);
-  if (i < row_begin || i >= row_end) return;
+  active = active && i >= row_begin && i < row_end;
   const lj_grid_params g = ge->g;
-  const float margin = ge->margin, sl2f = ge->sl2f;
+  const float margin = ge->margin, sl2f = ge->sl2f, edge = ge->edge, pad = ge->pad;
   const float lo_f = sl2f - margin, hi_f = sl2f + margin;
-  const int c = cell_of[i];
+  const int c = active ? cell_of[i] : 0;
   const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
-  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
 
   int64_t base = 0;
-  bool fits = true;
-  if (FILL) {
+  if (FILL && active) {
     base = row_offset<PTR64>(pointer, i);
-    fits = base + nop[i] <= capacity;
-    if (!fits) {
-      if (lane == 0) atomicOr(&tot->overflow, 1);
-      return;
+    if (base + nop[i] > capacity) {
+      if (lg == 0) atomicOr(&tot->overflow, 1);
+      active = false;
     }
+  }
+  // squared gap between me and the slab of cells at offset o = -2..2 along each axis (0 for my
+  // own slab, +inf outside the grid), shrunk by the float error bound
+  const float kInf = __int_as_float(0x7f800000);
+  float gx2[5], gy2[5], gz2[5];
+#pragma unroll
+  for (int o = 0; o < 5; o++) {
+    const int x = cx + o - 2, y = cy + o - 2, z = cz + o - 2;
+    const float ax = fmaxf(fmaxf(x * edge - me32.x, me32.x - (x + 1) * edge) - pad, 0.f);
+    const float ay = fmaxf(fmaxf(y * edge - me32.y, me32.y - (y + 1) * edge) - pad, 0.f);
+    const float az = fmaxf(fmaxf(z * edge - me32.z, me32.z - (z + 1) * edge) - pad, 0.f);
+    gx2[o] = (active && x >= 0 && x < g.nx) ? ax * ax : kInf;
+    gy2[o] = (active && y >= 0 && y < g.ny) ? ay * ay : kInf;
+    gz2[o] = (active && z >= 0 && z < g.nz) ? az * az : kInf;
   }
   int count = 0;
   double4 me = make_double4(0, 0, 0, 0);
   bool have_me = false;
 
-  for (int dz = -1; dz <= 1; dz++) {
-    const int z = cz + dz;
-    if (z < 0 || z >= g.nz) continue;
-    for (int dy = -1; dy <= 1; dy++) {
-      const int y = cy + dy;
-      if (y < 0 || y >= g.ny) continue;
-      const int rowc = (z * g.ny + y) * g.nx;
-      const uint32_t mb = cell_start[rowc + x0];
-      const uint32_t me_ = cell_start[rowc + x1] + cell_count[rowc + x1];
-      for (uint32_t m0 = mb; m0 < me_; m0 += 32) {
-        const uint32_t m = m0 + lane;
+#pragma unroll
+  for (int dz = 0; dz < 5; dz++) {
+#pragma unroll
+    for (int dy = 0; dy < 5; dy++) {
+      // chord of the search sphere in this (dy,dz) row of cells: x-cells whose gap fits
+      const float rem = hi_f - gz2[dz] - gy2[dy];
+      const bool run = gx2[2] < rem;  // my own x-slab (gap 0) is in: rem > 0
+      if (!__any_sync(0xffffffffu, run)) continue;
+      uint32_t m = 0, m_end = 0;
+      if (run) {
+        const int xa = cx - ((gx2[0] < rem) ? 2 : (gx2[1] < rem) ? 1 : 0);
+        const int xb = cx + ((gx2[4] < rem) ? 2 : (gx2[3] < rem) ? 1 : 0);
+        const int rowc = ((cz + dz - 2) * g.ny + (cy + dy - 2)) * g.nx;
+        m = cell_start[rowc + xa] + lg;
+        m_end = cell_start[rowc + xb + 1];  // sentinel-terminated scan
+      }
+      while (__any_sync(0xffffffffu, m < m_end)) {
         bool hit = false;
-        int j = -1;
-        if (m < me_) {
+        int j = 0;
+        if (m < m_end) {
           const float4 c32 = sorted_pos32[m];
           j = __float_as_int(c32.w);
           const float dx = me32.x - c32.x, dy_ = me32.y - c32.y, dz_ = me32.z - c32.z;
           const float r2f = fmaf(dz_, dz_, fmaf(dy_, dy_, dx * dx));
-          const bool wanted = (j != i) && (!half || j > i);
-          if (wanted && r2f < hi_f) {
-            if (r2f < lo_f) {
+          if (r2f < hi_f) {
+            if (r2f < lo_f && r2f > margin) {
               hit = true;
-            } else {  // within the error margin of the threshold: decide in FP64, exactly
+            } else {  // near the threshold, or near zero (myself / coincident): exact FP64
               if (!have_me) { me = sorted_pos[s]; have_me = true; }
               const double4 cj = sorted_pos[m];
               const double ddx = me.x - cj.x, ddy = me.y - cj.y, ddz = me.z - cj.z;
-              hit = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2;
+              hit = (j != i) && (fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2);
             }
+            if (half) hit = hit && (j > i);
           }
         }
-        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-        if (FILL && hit) list[base + count + __popc(ballot & ((1u << lane) - 1u))] = j;
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit) & gbits;
+        if (FILL && hit) list[base + count + __popc(ballot & lt_mask)] = j;
         count += __popc(ballot);
+        m += GL;
       }
     }
   }
-  if (!FILL && lane == 0) {
+  if (!FILL && active && lg == 0) {
     nop[i] = count;
-    atomicMax(&tot->max_np, count);
+    if (count > *(volatile int*)&tot->max_np) atomicMax(&tot->max_np, count);
   }
 }
 
@@ -454,7 +496,7 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
   unsigned long long* bb = reinterpret_cast<unsigned long long*>(ctx->bbox);
   grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
   float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
-  const int* ncell_dev = &ge->g.ncell;
+  const int* ncell_dev = &ge->ncell1;  // histogram + sentinel
   const int64_t cells = ctx->scratch_cells;
   int64_t r0 = a->row_begin, r1 = a->row_end;
   if (r0 == 0 && r1 == 0) r1 = pn;
@@ -486,13 +528,13 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
   LJ_LAUNCHED(ctx);
 
   const double sl2 = a->search_len * a->search_len;
-  const unsigned search_blocks = (unsigned)blocks_for(pn * 32, 256);
+  const unsigned search_blocks = (unsigned)blocks_for(pn * kSearchLanes, 256);
   if (r0 > 0 || r1 < pn) {  // rows outside the range stay empty
     k_zero_i32_rows<<<4 * ctx->sm_count, 256, 0, st>>>(a->number_of_partners, pn);
     LJ_LAUNCHED(ctx);
   }
   k_search<false, false><<<search_blocks, 256, 0, st>>>(
-      pn, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_pos, sorted_pos32, sl2,
+      pn, ge, ctx->cell_of, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2,
       a->half, r0, r1, a->number_of_partners, nullptr, nullptr, 0, ctx->totals);
   LJ_LAUNCHED(ctx);
   // pointer[] = exclusive scan of number_of_partners, carried in 64 bits
@@ -513,11 +555,11 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
   LJ_LAUNCHED(ctx);
   if (a->pointer64)
     k_search<true, true><<<search_blocks, 256, 0, st>>>(
-        pn, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_pos, sorted_pos32, sl2,
+        pn, ge, ctx->cell_of, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2,
         a->half, r0, r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity, ctx->totals);
   else
     k_search<true, false><<<search_blocks, 256, 0, st>>>(
-        pn, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_pos, sorted_pos32, sl2,
+        pn, ge, ctx->cell_of, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2,
         a->half, r0, r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity, ctx->totals);
   LJ_LAUNCHED(ctx);
   ctx->last_capacity = a->capacity;
