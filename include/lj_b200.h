@@ -255,6 +255,10 @@ LJ_API int lj_measure(lj_ctx* ctx, lj_measure_args* args);
 /* ---------------------------------------------------------------- multi-GPU helpers --- */
 /* z-slab decomposition support (no reference counterpart: the reference is single-GPU).
  * Peer access by CUDA IPC: export a handle for a device allocation, open a peer's. */
+/* IPC-shareable device memory (plain cudaMalloc: the legacy IPC handles cannot describe
+ * stream-ordered pool allocations).  Export/open work on pointers returned by lj_ipc_alloc. */
+LJ_API int lj_ipc_alloc(lj_ctx* ctx, size_t bytes, void** out);
+LJ_API int lj_ipc_free(lj_ctx* ctx, void* ptr);
 LJ_API int lj_ipc_export(lj_ctx* ctx, void* dev_ptr, uint8_t handle_out[64]);
 LJ_API int lj_ipc_open(lj_ctx* ctx, const uint8_t handle[64], void** peer_ptr_out);
 LJ_API int lj_ipc_close(lj_ctx* ctx, void* peer_ptr);

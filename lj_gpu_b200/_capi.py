@@ -93,6 +93,8 @@ PROTOTYPES = {
     "lj_validate_list": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp]),
     "lj_init_fcc": (_i64, [_dbl, _dbl, _vp, _i64, C.POINTER(_i32)]),
     "lj_measure": (C.c_int, [_vp, C.POINTER(LjMeasureArgs)]),
+    "lj_ipc_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "lj_ipc_free": (C.c_int, [_vp, _vp]),
     "lj_ipc_export": (C.c_int, [_vp, _vp, C.c_char_p]),
     "lj_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "lj_ipc_close": (C.c_int, [_vp, _vp]),

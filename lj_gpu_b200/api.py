@@ -320,6 +320,20 @@ class LJContext:
         return CudaPtr(self, np.dtype(dtype), count)
 
     # ------------------------------------------------------------------ multi-GPU helpers
+    def ipc_tensor(self, shape, dtype):
+        """A torch tensor on IPC-shareable memory (lj_ipc_alloc = plain cudaMalloc)."""
+        import torch
+        n = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        ptr = C.c_void_p()
+        self._check(self.lib.lj_ipc_alloc(self.h, n, C.byref(ptr)))
+
+        class _Mem:  # torch.as_tensor consumes the CUDA array interface
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr.value, False),
+                                        "version": 2}
+        t = torch.as_tensor(_Mem(), device="cuda:%d" % self.device).view(dtype).view(*shape)
+        t._lj_ipc_base = ptr.value
+        return t
+
     def ipc_export(self, tensor) -> bytes:
         buf = C.create_string_buffer(64)
         self._check(self.lib.lj_ipc_export(self.h, tensor.data_ptr(), buf))

@@ -436,6 +436,19 @@ done:
 }
 
 // ------------------------------------------------------------------ multi-GPU helpers --
+int lj_ipc_alloc(lj_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return LJ_ERR_BAD_ARG;
+  *out = nullptr;
+  LJ_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 16));
+  return LJ_OK;
+}
+
+int lj_ipc_free(lj_ctx* ctx, void* ptr) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (ptr) LJ_CUDA(ctx, cudaFree(ptr));
+  return LJ_OK;
+}
+
 int lj_ipc_export(lj_ctx* ctx, void* dev_ptr, uint8_t handle_out[64]) {
   if (!ctx || !dev_ptr || !handle_out) return LJ_ERR_BAD_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
