@@ -193,7 +193,8 @@ def run_cuda(args):
     q4 = np.zeros((pn, 4)); q4[:, :3] = q
     qd = torch.from_numpy(q4).cuda()
     pd = torch.zeros_like(qd)
-    pl = ctx.makepair(qd, pointer64=False)
+    use_cl = args.variant in ("auto", "cluster") and args.prec == "fp64"
+    pl = ctx.makepair(qd, pointer64=False, clusters=use_cl)
     P = pl.number_of_pairs
     fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
                threads_per_block=args.threads_per_block)
@@ -203,7 +204,7 @@ def run_cuda(args):
         s = n0
         while s < n0 + n:
             if s % REBUILD_EVERY == 0:
-                ctx.rebuild(qd, pl)
+                ctx.rebuild(qd, pl, clusters=use_cl)
             m = min(REBUILD_EVERY - s % REBUILD_EVERY, n0 + n - s)
             ctx.force_loop(qd, pd, pl, loop=m, **fkw)
             s += m
@@ -237,7 +238,7 @@ def run_cuda(args):
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record(stream)
     for _ in range(5):
-        ctx.rebuild(qd, pl)
+        ctx.rebuild(qd, pl, clusters=use_cl)
     b1.record(stream)
     torch.cuda.synchronize()
     ms_build = b0.elapsed_time(b1) / 5

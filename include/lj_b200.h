@@ -63,8 +63,10 @@ typedef enum lj_variant {
                                (kernel.cuh:821-904), 1 = thread-per-i (kernel.cuh:67-236)     */
   LJ_VARIANT_TILE_TMA = 2,  /* CTA tile of rows, j-indices staged in shared memory by a TMA
                                bulk copy, `group` lanes per i (CSR only)                     */
-  LJ_VARIANT_NEWTON3 = 3    /* half list, reaction scattered with FP64 atomics
+  LJ_VARIANT_NEWTON3 = 3,   /* half list, reaction scattered with FP64 atomics
                                (the *_with_aar kernels, kernel.cuh:238-469)                  */
+  LJ_VARIANT_CLUSTER = 4    /* cluster pair list built by lj_build_list(LJ_LIST_CLUSTERS) for
+                               exactly these list arrays; error if there is none             */
 } lj_variant;
 
 typedef enum lj_precision {
@@ -159,7 +161,15 @@ LJ_API int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int u
  * Output in the caller's numbering: number_of_partners[i], pointer = exclusive scan (pn
  * entries, no sentinel), sorted_list rows in a deterministic but unspecified order (or
  * ascending j with LJ_LIST_SORT_ROWS, which is what makepair() produces). */
-enum { LJ_LIST_SORT_ROWS = 1 };
+enum {
+  LJ_LIST_SORT_ROWS = 1,
+  /* also build the library-owned CLUSTER PAIR LIST (union of 4 consecutive rows with member
+   * masks) that LJ_VARIANT_CLUSTER / AUTO use: q[j] is gathered once per cluster entry and serves
+   * up to four i-particles from registers.  Full lists only; one small host read-back per build.
+   * The mirror is tied to the three output arrays: rebuilding into them, lj_shuffle_rows on them
+   * or lj_list_invalidate() drops it. */
+  LJ_LIST_CLUSTERS = 2
+};
 
 typedef struct lj_list_args {
   const void* q;                /* device, layout below (FP64 layouts only)               */
@@ -185,6 +195,8 @@ typedef struct lj_list_args {
  * lj_list_result(). */
 LJ_API int lj_build_list(lj_ctx* ctx, const lj_list_args* args, int64_t* number_of_pairs_out,
                   void* stream);
+/* drop the cluster mirror (call after modifying the list arrays yourself) */
+LJ_API int lj_list_invalidate(lj_ctx* ctx);
 /* status + totals of the most recent lj_build_list on this context (synchronises `stream`) */
 LJ_API int lj_list_result(lj_ctx* ctx, int64_t* number_of_pairs_out, int32_t* max_partners_out,
                    void* stream);

@@ -18,9 +18,10 @@ LJ_OK, LJ_ERR_CUDA, LJ_ERR_BAD_ARG, LJ_ERR_CAPACITY, LJ_ERR_OVERFLOW32, LJ_ERR_N
     LJ_ERR_INVALID_LIST = range(7)
 LJ_AOS_D3, LJ_AOS_D4, LJ_SOA_D, LJ_AOS_F4 = range(4)
 LJ_LIST_CSR, LJ_LIST_ELL = 0, 1
-LJ_VARIANT_AUTO, LJ_VARIANT_SUBWARP, LJ_VARIANT_TILE_TMA, LJ_VARIANT_NEWTON3 = range(4)
+LJ_VARIANT_AUTO, LJ_VARIANT_SUBWARP, LJ_VARIANT_TILE_TMA, LJ_VARIANT_NEWTON3, LJ_VARIANT_CLUSTER = range(5)
 LJ_PREC_FP64, LJ_PREC_MIXED = 0, 1
 LJ_LIST_SORT_ROWS = 1
+LJ_LIST_CLUSTERS = 2
 
 
 class LjBuf(C.Structure):
@@ -87,6 +88,7 @@ PROTOTYPES = {
     "lj_force_step": (C.c_int, [_vp, C.POINTER(LjForceArgs), _vp]),
     "lj_force_loop": (C.c_int, [_vp, C.POINTER(LjForceArgs), C.c_int, C.c_int, _vp]),
     "lj_build_list": (C.c_int, [_vp, C.POINTER(LjListArgs), C.POINTER(_i64), _vp]),
+    "lj_list_invalidate": (C.c_int, [_vp]),
     "lj_list_result": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i32), _vp]),
     "lj_build_ell": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, C.POINTER(_i32), _vp]),
     "lj_shuffle_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_uint32, _vp]),

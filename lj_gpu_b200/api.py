@@ -28,7 +28,8 @@ LOOP = 100
 
 LAYOUTS = {"aos3": LJ_AOS_D3, "aos4": LJ_AOS_D4, "soa": LJ_SOA_D}
 VARIANTS = {"auto": LJ_VARIANT_AUTO, "subwarp": LJ_VARIANT_SUBWARP, "warp": LJ_VARIANT_SUBWARP,
-            "thread": LJ_VARIANT_SUBWARP, "tile": LJ_VARIANT_TILE_TMA, "n3": LJ_VARIANT_NEWTON3}
+            "thread": LJ_VARIANT_SUBWARP, "tile": LJ_VARIANT_TILE_TMA, "n3": LJ_VARIANT_NEWTON3,
+            "cluster": capi.LJ_VARIANT_CLUSTER}
 
 
 class LJError(RuntimeError):
@@ -139,8 +140,11 @@ class LJContext:
     # ------------------------------------------------------------------ list build
     def makepair(self, q, search_len: float = SEARCH_LENGTH, half: bool = False, layout=None,
                  pointer64: bool = False, sort_rows: bool = False, capacity: int | None = None,
-                 rows=None, pn=None, out: PairList | None = None, stream=None) -> PairList:
-        """makepair() (cuda/force_cuda.cu:122-163) on the GPU.  Returns device arrays."""
+                 rows=None, pn=None, out: PairList | None = None, clusters: bool = False,
+                 stream=None) -> PairList:
+        """makepair() (cuda/force_cuda.cu:122-163) on the GPU.  Returns device arrays.
+        clusters=True also builds the library-owned cluster pair list (LJ_LIST_CLUSTERS) that the
+        "auto"/"cluster" force variants use for exactly these arrays."""
         import torch
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
@@ -158,7 +162,8 @@ class LJContext:
         a.q, a.pn, a.layout, a.half, a.plane_stride = q.data_ptr(), n, lay, int(half), stride
         a.search_len = search_len
         a.number_of_partners, a.pointer = nop.data_ptr(), ptr.data_ptr()
-        a.pointer64, a.flags = int(pointer64), (capi.LJ_LIST_SORT_ROWS if sort_rows else 0)
+        a.pointer64 = int(pointer64)
+        a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         total = C.c_int64(0)
@@ -176,7 +181,7 @@ class LJContext:
         return PairList(nop, ptr, lst, int(total.value), int(mx.value), half)
 
     def rebuild(self, q, pl: PairList, search_len: float = SEARCH_LENGTH, layout=None,
-                sort_rows: bool = False, rows=None, pn=None, stream=None):
+                sort_rows: bool = False, rows=None, pn=None, clusters: bool = False, stream=None):
         """Asynchronous rebuild into existing arrays (no host sync, no reallocation)."""
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
@@ -187,10 +192,14 @@ class LJContext:
         a.search_len = search_len
         a.number_of_partners, a.pointer = pl.number_of_partners.data_ptr(), pl.pointer.data_ptr()
         a.sorted_list, a.capacity = pl.sorted_list.data_ptr(), pl.sorted_list.numel()
-        a.pointer64, a.flags = int(pl.pointer64), (capi.LJ_LIST_SORT_ROWS if sort_rows else 0)
+        a.pointer64 = int(pl.pointer64)
+        a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         self._check(self.lib.lj_build_list(self.h, C.byref(a), None, self._stream(stream)))
+
+    def list_invalidate(self):
+        self._check(self.lib.lj_list_invalidate(self.h))
 
     def list_result(self, stream=None):
         total, mx = C.c_int64(0), C.c_int32(0)

@@ -15,7 +15,8 @@
 struct lj_list_totals {      // written by the list-build kernels, read back on demand
   unsigned long long total;  // entries of the list
   int max_np;                // longest row
-  int overflow;              // bit0: capacity, bit1: int32 pointer overflow
+  int overflow;              // bit0: capacity, bit1: int32 pointer overflow, bit2: cluster list
+  unsigned long long cl_total;  // entries of the cluster pair list
 };
 
 struct lj_grid_params {  // cell grid derived ON THE DEVICE from the bounding box
@@ -55,6 +56,19 @@ struct lj_ctx {
   lj_list_totals* totals = nullptr;  // device
   lj_list_totals* totals_host = nullptr;  // pinned
   int64_t last_capacity = 0;
+
+  // cluster pair list: library-owned mirror of the CSR list most recently built with
+  // LJ_LIST_CLUSTERS (union of 4 consecutive rows, entries (member mask << 28) | j)
+  uint32_t* cl_list = nullptr;
+  int64_t cl_cap = 0;
+  long long* cl_ptr = nullptr;   // [nc+1]
+  uint32_t* cl_cnt = nullptr;    // [nc+1]
+  int64_t cl_nc_cap = 0;
+  bool cl_valid = false;
+  const void* cl_id_list = nullptr;  // identity of the CSR arrays it mirrors
+  const void* cl_id_nop = nullptr;
+  const void* cl_id_ptr = nullptr;
+  int64_t cl_pn = 0, cl_r0 = 0, cl_r1 = 0, cl_entries = 0;
 
   // mixed-precision scratch: origin-shifted float4 positions
   float4* q32 = nullptr;

@@ -211,6 +211,9 @@ int lj_force_tile_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_
                          double c24, double c48, long long cl2_bits, cudaStream_t st);
 int lj_force_mixed_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, int g, int tb,
                           cudaStream_t st);
+bool lj_cluster_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1);
+int lj_force_cluster_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, double c24,
+                            double c48, long long cl2_bits, cudaStream_t st);
 
 int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
   LJ_REQUIRE(ctx, a != nullptr, "lj_force_step: null args");
@@ -239,7 +242,7 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
              "lj_force_step: THREAD_BLOCK must be a multiple of 32 in [64,1024]");
 
   int variant = a->variant;
-  if (variant == LJ_VARIANT_AUTO) variant = LJ_VARIANT_SUBWARP;
+  if (variant == LJ_VARIANT_AUTO || variant == LJ_VARIANT_CLUSTER) variant = LJ_VARIANT_SUBWARP;
   const bool n3 = variant == LJ_VARIANT_NEWTON3;
   LJ_REQUIRE(ctx, !(n3 && a->list_layout == LJ_LIST_ELL), "lj_force_step: Newton-3 needs a CSR list");
   int g = a->group;
@@ -255,6 +258,14 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
     memcpy(&cl2_bits, &c, sizeof c);
   }
 
+  // AUTO prefers the cluster pair list when lj_build_list(LJ_LIST_CLUSTERS) mirrored exactly
+  // these list arrays; LJ_VARIANT_CLUSTER insists on it
+  if (a->variant == LJ_VARIANT_AUTO || a->variant == LJ_VARIANT_CLUSTER) {
+    if (lj_cluster_usable(ctx, a, r0, r1)) return lj_force_cluster_launch(ctx, a, r0, r1, c24, c48, cl2_bits, st);
+    LJ_REQUIRE(ctx, a->variant != LJ_VARIANT_CLUSTER,
+               "lj_force_step: no cluster pair list for these arrays (build with LJ_LIST_CLUSTERS; FP64, "
+               "CSR, row range on 4-row boundaries)");
+  }
   if (a->precision == LJ_PREC_MIXED) {
     LJ_REQUIRE(ctx, !n3 && a->list_layout == LJ_LIST_CSR, "lj_force_step: mixed precision is gather/CSR only");
     return lj_force_mixed_launch(ctx, a, r0, r1, g, tb, st);

@@ -20,7 +20,7 @@ namespace {
 __global__ void k_bbox_init(unsigned long long* bb, lj_list_totals* tot) {
   if (threadIdx.x < 3) bb[threadIdx.x] = ~0ull;      // mins
   else if (threadIdx.x < 6) bb[threadIdx.x] = 0ull;  // maxs
-  if (threadIdx.x == 0 && tot) { tot->total = 0; tot->max_np = 0; tot->overflow = 0; }
+  if (threadIdx.x == 0 && tot) { tot->total = 0; tot->max_np = 0; tot->overflow = 0; tot->cl_total = 0; }
 }
 
 template <int LAYOUT>
@@ -358,6 +358,154 @@ k_search(int64_t pn, const grid_ext* __restrict__ ge, const int32_t* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ cluster search -----
+// Same search, organised around CLUSTERS of four consecutive particles (rows r0+4c .. r0+4c+3):
+// one candidate stream per cluster, each candidate tested against the four cluster members.
+// Emits, from one pass over the candidates,
+//   * the reference's CSR arrays (number_of_partners / sorted_list rows of the four members),
+//   * the library-owned CLUSTER PAIR LIST: the union of the four rows, one packed entry per
+//     candidate  (member mask << 28) | j,  which lets the cluster force kernel gather q[j] once
+//     and use it for up to four i-particles from registers.
+// Eight lanes per cluster, four clusters per warp, warp-uniform control flow as in k_search.
+// Candidate ranges are derived from the cluster's bounding box, so any particle order is
+// handled correctly; it is efficient when consecutive particles are spatially close (lattice
+// order), which is what the cluster force kernel needs anyway.
+template <bool FILL, bool PTR64, int LAYOUT>
+__global__ void __launch_bounds__(256)
+k_search_cluster(const void* __restrict__ q, int64_t plane, int64_t pn, const grid_ext* __restrict__ ge,
+                 const uint32_t* __restrict__ cell_start, const double4* __restrict__ sorted_pos,
+                 const float4* __restrict__ sorted_pos32, double sl2, int half, int64_t row_begin,
+                 int64_t row_end, int32_t* __restrict__ nop, const void* __restrict__ pointer,
+                 int32_t* __restrict__ list, int64_t capacity, uint32_t* __restrict__ cl_cnt,
+                 const long long* __restrict__ cl_ptr, uint32_t* __restrict__ cl_list,
+                 int64_t cl_cap, lj_list_totals* __restrict__ tot) {
+  constexpr int GL = kSearchLanes;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;  // cluster index
+  const int lane = threadIdx.x & 31;
+  const int lg = lane % GL;
+  const unsigned gbits = ((1u << GL) - 1u) << (lane - lg);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int64_t i0 = row_begin + 4 * c;
+  const int nrows = (int)max((int64_t)0, min((int64_t)4, row_end - i0));  // members of this cluster
+  bool active = nrows > 0;
+  const lj_grid_params g = ge->g;
+  const float margin = ge->margin, sl2f = ge->sl2f, edge = ge->edge, inv_edge = ge->inv_edge,
+              pad = ge->pad;
+  const float lo_f = sl2f - margin, hi_f = sl2f + margin;
+  const float search_f = sqrtf(hi_f) + pad;
+
+  // member positions, origin-shifted floats (same expression as k_cell_order: bit-identical)
+  float px[4], py[4], pz[4];
+  float bx0 = 3.0e38f, by0 = 3.0e38f, bz0 = 3.0e38f, bx1 = -3.0e38f, by1 = -3.0e38f, bz1 = -3.0e38f;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    px[r] = py[r] = pz[r] = 3.0e18f;  // absent member: far away from everything
+    if (r < nrows) {
+      double x, y, z;
+      load_pos<LAYOUT>(q, i0 + r, plane, x, y, z);
+      px[r] = (float)(x - g.ox); py[r] = (float)(y - g.oy); pz[r] = (float)(z - g.oz);
+      bx0 = fminf(bx0, px[r]); bx1 = fmaxf(bx1, px[r]);
+      by0 = fminf(by0, py[r]); by1 = fmaxf(by1, py[r]);
+      bz0 = fminf(bz0, pz[r]); bz1 = fmaxf(bz1, pz[r]);
+    }
+  }
+  int64_t base[4] = {0, 0, 0, 0};
+  long long cbase = 0;
+  bool emit_cl = cl_cnt != nullptr;
+  if (FILL && active) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (r < nrows) {
+        base[r] = row_offset<PTR64>(pointer, i0 + r);
+        if (base[r] + nop[i0 + r] > capacity) active = false;
+      }
+    if (!active && lg == 0) atomicOr(&tot->overflow, 1);
+    if (emit_cl) {
+      cbase = cl_ptr[c];
+      if (cl_ptr[c + 1] > cl_cap) {
+        emit_cl = false;
+        if (lg == 0) atomicOr(&tot->overflow, 4);
+      }
+    }
+  }
+  // rows/slabs of cells that can hold a neighbour of the cluster's bounding box
+  int y = 0, z = 0, cy0 = 0, cy1 = -1, cz1 = -1;
+  if (active) {
+    cy0 = max((int)floorf((by0 - search_f) * inv_edge), 0);
+    cy1 = min((int)floorf((by1 + search_f) * inv_edge), g.ny - 1);
+    z = max((int)floorf((bz0 - search_f) * inv_edge), 0);
+    cz1 = min((int)floorf((bz1 + search_f) * inv_edge), g.nz - 1);
+    y = cy0;
+  }
+  int cnt[4] = {0, 0, 0, 0};
+  int ucnt = 0;
+
+  while (__any_sync(0xffffffffu, active && z <= cz1)) {
+    uint32_t m = 0, m_end = 0;
+    if (active && z <= cz1) {
+      const float gy = fmaxf(fmaxf(y * edge - by1, by0 - (y + 1) * edge) - pad, 0.f);
+      const float gz = fmaxf(fmaxf(z * edge - bz1, bz0 - (z + 1) * edge) - pad, 0.f);
+      const float rem = hi_f - gy * gy - gz * gz;
+      if (rem > 0.f) {
+        const float w = sqrtf(rem) + pad;  // half chord of the search sphere along x
+        const int xa = max((int)floorf((bx0 - w) * inv_edge), 0);
+        const int xb = min((int)floorf((bx1 + w) * inv_edge), g.nx - 1);
+        if (xa <= xb) {
+          const int rowc = (z * g.ny + y) * g.nx;
+          m = cell_start[rowc + xa] + lg;
+          m_end = cell_start[rowc + xb + 1];
+        }
+      }
+      if (++y > cy1) { y = cy0; z++; }
+    }
+    while (__any_sync(0xffffffffu, m < m_end)) {
+      unsigned bits = 0;
+      int j = 0;
+      if (m < m_end) {
+        const float4 c32 = sorted_pos32[m];
+        j = __float_as_int(c32.w);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const float dx = px[r] - c32.x, dy = py[r] - c32.y, dz = pz[r] - c32.z;
+          const float r2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          if (r2f < hi_f) {
+            bool hit;
+            if (r2f < lo_f && r2f > margin) {
+              hit = true;
+            } else {  // near the threshold or near zero (the member itself / coincident): FP64
+              double xi, yi, zi;
+              load_pos<LAYOUT>(q, i0 + r, plane, xi, yi, zi);
+              const double4 cj = sorted_pos[m];
+              const double ddx = xi - cj.x, ddy = yi - cj.y, ddz = zi - cj.z;
+              hit = (j != (int)(i0 + r)) && (fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2);
+            }
+            if (half) hit = hit && (j > (int)(i0 + r));
+            bits |= hit ? (1u << r) : 0u;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const unsigned b = __ballot_sync(0xffffffffu, (bits >> r) & 1u) & gbits;
+        if (FILL && ((bits >> r) & 1u)) list[base[r] + cnt[r] + __popc(b & lt_mask)] = j;
+        cnt[r] += __popc(b);
+      }
+      const unsigned bu = __ballot_sync(0xffffffffu, bits != 0u) & gbits;
+      if (FILL && emit_cl && bits != 0u) cl_list[cbase + ucnt + __popc(bu & lt_mask)] = (bits << 28) | (unsigned)j;
+      ucnt += __popc(bu);
+      m += GL;
+    }
+  }
+  if (!FILL && nrows > 0) {
+    if (lg < nrows) {
+      const int mine = lg == 0 ? cnt[0] : lg == 1 ? cnt[1] : lg == 2 ? cnt[2] : cnt[3];
+      nop[i0 + lg] = mine;
+      if (mine > *(volatile int*)&tot->max_np) atomicMax(&tot->max_np, mine);
+    }
+    if (emit_cl && lg == 0) cl_cnt[c] = (uint32_t)ucnt;
+  }
+}
+
 __global__ void k_zero_u32(uint32_t* p, int64_t n, const int* n_dev) {
   if (n_dev) n = *n_dev;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -528,18 +676,98 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
   LJ_LAUNCHED(ctx);
 
   const double sl2 = a->search_len * a->search_len;
-  const unsigned search_blocks = (unsigned)blocks_for(pn * kSearchLanes, 256);
   if (r0 > 0 || r1 < pn) {  // rows outside the range stay empty
     k_zero_i32_rows<<<4 * ctx->sm_count, 256, 0, st>>>(a->number_of_partners, pn);
     LJ_LAUNCHED(ctx);
   }
+  const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
+  const uint32_t* nop_u = reinterpret_cast<const uint32_t*>(a->number_of_partners);
+  // any list these arrays were mirrored by is stale from here on
+  if (ctx->cl_valid && (ctx->cl_id_list == a->sorted_list || ctx->cl_id_nop == a->number_of_partners ||
+                        ctx->cl_id_ptr == a->pointer))
+    ctx->cl_valid = false;
+
+  if ((a->flags & LJ_LIST_CLUSTERS) && pn < (1LL << 28) && r1 > r0) {
+    // ---------------- cluster search: CSR arrays + the cluster pair list in one go ----------
+    const int64_t nc = (r1 - r0 + 3) / 4;
+    if (nc + 1 > ctx->cl_nc_cap) {
+      if (ctx->cl_cnt) LJ_CUDA(ctx, cudaFreeAsync(ctx->cl_cnt, st));
+      if (ctx->cl_ptr) LJ_CUDA(ctx, cudaFreeAsync(ctx->cl_ptr, st));
+      ctx->cl_cnt = nullptr; ctx->cl_ptr = nullptr;
+      LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_cnt, sizeof(uint32_t) * (nc + 1), ctx->pool, st));
+      LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_ptr, sizeof(long long) * (nc + 1), ctx->pool, st));
+      ctx->cl_nc_cap = nc + 1;
+    }
+    const bool emit = !a->half;
+    LJ_CUDA(ctx, cudaMemsetAsync(ctx->cl_cnt + nc, 0, sizeof(uint32_t), st));
+    const unsigned cblocks = (unsigned)blocks_for(nc * kSearchLanes, 256);
+    k_search_cluster<false, false, LAYOUT><<<cblocks, 256, 0, st>>>(
+        a->q, a->plane_stride, pn, ge, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2, a->half, r0,
+        r1, a->number_of_partners, nullptr, nullptr, 0, emit ? ctx->cl_cnt : nullptr, nullptr, nullptr, 0,
+        ctx->totals);
+    LJ_LAUNCHED(ctx);
+    k_scan_reduce<<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp);
+    LJ_LAUNCHED(ctx);
+    k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, row_tiles, &ctx->totals->total);
+    LJ_LAUNCHED(ctx);
+    if (a->pointer64)
+      k_scan_down<long long><<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp,
+                                                                  reinterpret_cast<long long*>(a->pointer));
+    else
+      k_scan_down<uint32_t><<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp,
+                                                                 reinterpret_cast<uint32_t*>(a->pointer));
+    LJ_LAUNCHED(ctx);
+    if (emit) {
+      const unsigned ctiles = (unsigned)blocks_for(nc + 1, kScanTile);
+      k_scan_reduce<<<ctiles, kScanThreads, 0, st>>>(ctx->cl_cnt, nc + 1, nullptr, ctx->scan_tmp);
+      LJ_LAUNCHED(ctx);
+      k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, ctiles, &ctx->totals->cl_total);
+      LJ_LAUNCHED(ctx);
+      k_scan_down<long long><<<ctiles, kScanThreads, 0, st>>>(ctx->cl_cnt, nc + 1, nullptr, ctx->scan_tmp,
+                                                               ctx->cl_ptr);
+      LJ_LAUNCHED(ctx);
+    }
+    k_finish_totals<<<1, 1, 0, st>>>(ctx->totals, a->capacity, a->pointer64);
+    LJ_LAUNCHED(ctx);
+    // one small read-back per build: sizes the library-owned cluster list and lets an
+    // over-capacity build skip the fill pass altogether
+    LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals),
+                                 cudaMemcpyDeviceToHost, st));
+    LJ_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->last_capacity = a->capacity;
+    if (ctx->totals_host->overflow) return LJ_OK;  // reported by lj_list_result
+    const int64_t need = (int64_t)ctx->totals_host->cl_total;
+    if (emit && need > ctx->cl_cap) {
+      if (ctx->cl_list) LJ_CUDA(ctx, cudaFreeAsync(ctx->cl_list, st));
+      ctx->cl_list = nullptr;
+      ctx->cl_cap = need + need / 32 + 4096;
+      LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_list, sizeof(uint32_t) * ctx->cl_cap, ctx->pool, st));
+    }
+    if (a->pointer64)
+      k_search_cluster<true, true, LAYOUT><<<cblocks, 256, 0, st>>>(
+          a->q, a->plane_stride, pn, ge, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2, a->half, r0,
+          r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity,
+          emit ? ctx->cl_cnt : nullptr, ctx->cl_ptr, ctx->cl_list, ctx->cl_cap, ctx->totals);
+    else
+      k_search_cluster<true, false, LAYOUT><<<cblocks, 256, 0, st>>>(
+          a->q, a->plane_stride, pn, ge, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2, a->half, r0,
+          r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity,
+          emit ? ctx->cl_cnt : nullptr, ctx->cl_ptr, ctx->cl_list, ctx->cl_cap, ctx->totals);
+    LJ_LAUNCHED(ctx);
+    if (emit) {
+      ctx->cl_valid = true;
+      ctx->cl_id_list = a->sorted_list; ctx->cl_id_nop = a->number_of_partners; ctx->cl_id_ptr = a->pointer;
+      ctx->cl_pn = pn; ctx->cl_r0 = r0; ctx->cl_r1 = r1; ctx->cl_entries = need;
+    }
+    return LJ_OK;
+  }
+
+  const unsigned search_blocks = (unsigned)blocks_for(pn * kSearchLanes, 256);
   k_search<false, false><<<search_blocks, 256, 0, st>>>(
       pn, ge, ctx->cell_of, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2,
       a->half, r0, r1, a->number_of_partners, nullptr, nullptr, 0, ctx->totals);
   LJ_LAUNCHED(ctx);
   // pointer[] = exclusive scan of number_of_partners, carried in 64 bits
-  const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
-  const uint32_t* nop_u = reinterpret_cast<const uint32_t*>(a->number_of_partners);
   k_scan_reduce<<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp);
   LJ_LAUNCHED(ctx);
   k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, row_tiles, &ctx->totals->total);
@@ -656,6 +884,9 @@ extern "C" int lj_shuffle_rows(lj_ctx* ctx, int32_t* sorted_list, const int32_t*
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (pn <= 0) return LJ_OK;
   LJ_REQUIRE(ctx, sorted_list && nop && pointer, "lj_shuffle_rows: null array");
+  // the cluster mirror stays correct as a SET, but drop it so that a shuffled list really is
+  // consumed in its shuffled order
+  if (ctx->cl_id_list == sorted_list) ctx->cl_valid = false;
   cudaStream_t st = lj_stream(ctx, stream);
   const unsigned blocks = (unsigned)blocks_for(pn, 256);
   if (pointer64) k_shuffle_rows<true><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, seed);

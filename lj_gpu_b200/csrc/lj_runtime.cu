@@ -92,7 +92,8 @@ int lj_ctx_destroy(lj_ctx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   void* frees[] = {ctx->bbox, ctx->grid, ctx->totals, ctx->cell_of, ctx->cell_slot, ctx->cell_count,
-                   ctx->cell_start, ctx->sorted_pos, ctx->sorted_tmp, ctx->scan_tmp, ctx->q32};
+                   ctx->cell_start, ctx->sorted_pos, ctx->sorted_tmp, ctx->scan_tmp, ctx->q32,
+                   ctx->cl_list, ctx->cl_ptr, ctx->cl_cnt};
   for (void* f : frees)
     if (f) cudaFreeAsync(f, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
@@ -119,6 +120,12 @@ int lj_sync(lj_ctx* ctx, void* stream) {
     LJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     LJ_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   }
+  return LJ_OK;
+}
+
+int lj_list_invalidate(lj_ctx* ctx) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  ctx->cl_valid = false;
   return LJ_OK;
 }
 
@@ -368,6 +375,9 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
     la.q = q; la.pn = pn; la.layout = m->layout; la.half = m->half; la.plane_stride = m->plane_stride;
     la.search_len = m->search_len; la.number_of_partners = nop; la.pointer = ptr; la.pointer64 = ptr64;
     la.flags = m->list_flags;
+    if (!m->half && m->precision == LJ_PREC_FP64 &&
+        (m->variant == LJ_VARIANT_AUTO || m->variant == LJ_VARIANT_CLUSTER))
+      la.flags |= LJ_LIST_CLUSTERS;
     if (own_list) {
       // first build sizes the list: count pass only needs capacity 0 to learn the total
       la.sorted_list = nullptr; la.capacity = 0;

@@ -112,10 +112,11 @@ def test_init_fcc_bit_exact(oracle, golden):
 # ------------------------------------------------------------------------ neighbour list
 @pytest.mark.parametrize("which", ["A", "B"])
 @pytest.mark.parametrize("half", [False, True])
-def test_list_bit_exact(ctx, torch, sysA, sysB, golden, which, half):
+@pytest.mark.parametrize("clusters", [False, True])
+def test_list_bit_exact(ctx, torch, sysA, sysB, golden, which, half, clusters):
     s = sysA if which == "A" else sysB
     qd, _ = s.device_arrays(torch, "aos4")
-    pl = ctx.makepair(qd, half=half)
+    pl = ctx.makepair(qd, half=half, clusters=clusters)  # both search kernels emit the same CSR list
     nop, ptr, lst = list_to_host(pl)
     nop_o, ptr_o, lst_o = s.half if half else s.full
     assert pl.number_of_pairs == len(lst_o)
@@ -233,7 +234,8 @@ FORCE_CASES = [("aos4", "subwarp", 8), ("aos4", "warp", 32), ("aos4", "thread", 
                ("aos4", "subwarp", 4), ("aos4", "subwarp", 16), ("aos4", "subwarp", 2),
                ("aos4", "tile", 8), ("aos4", "tile", 32), ("aos4", "tile", 4),
                ("aos3", "subwarp", 8), ("aos3", "warp", 32), ("aos3", "tile", 16),
-               ("soa", "subwarp", 8), ("soa", "thread", 1), ("soa", "tile", 8)]
+               ("soa", "subwarp", 8), ("soa", "thread", 1), ("soa", "tile", 8),
+               ("aos4", "cluster", 0), ("aos3", "cluster", 0), ("soa", "cluster", 0)]
 
 
 @pytest.mark.parametrize("layout,variant,group", FORCE_CASES)
@@ -241,7 +243,7 @@ def test_force_fp64_config_A(ctx, torch, sysA, golden, layout, variant, group):
     s = sysA
     qd, pd = s.device_arrays(torch, layout)
     pn = s.pn if layout == "soa" else None
-    pl = ctx.makepair(qd, layout=layout, pn=pn)
+    pl = ctx.makepair(qd, layout=layout, pn=pn, clusters=(variant == "cluster"))
     ctx.force_loop(qd, pd, pl, loop=100, layout=layout, variant=variant, group=group, pn=pn)
     ctx.sync()
     assert s.err(pd, layout) < TOL_FP64
@@ -255,12 +257,13 @@ def test_force_fp64_config_A(ctx, torch, sysA, golden, layout, variant, group):
 
 
 @pytest.mark.parametrize("layout,variant,group", [("aos4", "subwarp", 8), ("aos4", "tile", 8),
-                                                   ("aos3", "warp", 32), ("soa", "subwarp", 16)])
+                                                   ("aos3", "warp", 32), ("soa", "subwarp", 16),
+                                                   ("aos4", "cluster", 0), ("aos4", "auto", 0)])
 def test_force_fp64_config_B(ctx, torch, sysB, golden, layout, variant, group):
     s = sysB
     qd, pd = s.device_arrays(torch, layout)
     pn = s.pn if layout == "soa" else None
-    pl = ctx.makepair(qd, layout=layout, pn=pn)
+    pl = ctx.makepair(qd, layout=layout, pn=pn, clusters=variant in ("cluster", "auto"))
     ctx.force_loop(qd, pd, pl, loop=100, layout=layout, variant=variant, group=group, pn=pn,
                    use_graph=True)
     ctx.sync()
@@ -375,6 +378,53 @@ def test_force_row_range(ctx, torch, sysS):
         assert np.abs(ph[r0:r1] - s.p[r0:r1]).max() / s.scale < TOL_FP64
 
 
+def test_cluster_list_identity_row_ranges_and_invalidation(ctx, torch, sysS):
+    from lj_gpu_b200 import LJError
+    s = sysS
+    qd, pd = s.device_arrays(torch, "aos4")
+    plain = ctx.makepair(qd)
+    with pytest.raises(LJError):                       # no mirror for these arrays
+        ctx.force_step(qd, pd, plain, variant="cluster")
+    pl = ctx.makepair(qd, clusters=True)
+    launches = ctx.launches
+    ctx.force_loop(qd, pd, pl, loop=s.steps, variant="cluster")
+    assert ctx.launches - launches == s.steps and s.err(pd, "aos4") < TOL_FP64
+    with pytest.raises(LJError):                       # the mirror belongs to pl, not to plain
+        ctx.force_step(qd, pd, plain, variant="cluster")
+    # row sub-ranges on 4-row boundaries use the mirror, others fall back to the per-row kernel
+    for r0, r1 in ((128, s.pn - 400), (0, s.pn), (4, 8), (s.pn - 4, s.pn)):
+        pd.zero_()
+        ctx.force_loop(qd, pd, pl, loop=s.steps, variant="cluster", rows=(r0, r1))
+        ph = pd.cpu().numpy()[:, :3]
+        assert np.all(ph[:r0] == 0) and np.all(ph[r1:] == 0)
+        assert np.abs(ph[r0:r1] - s.p[r0:r1]).max() / s.scale < TOL_FP64
+    pd.zero_()
+    ctx.force_loop(qd, pd, pl, loop=s.steps, variant="auto", rows=(3, s.pn - 2))   # unaligned: AUTO falls back
+    ph = pd.cpu().numpy()[:, :3]
+    assert np.abs(ph[3:s.pn - 2] - s.p[3:s.pn - 2]).max() / s.scale < TOL_FP64 and np.all(ph[:3] == 0)
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl, variant="cluster", rows=(3, s.pn - 2))
+    # partial row ranges at build time (ghost particles as candidates only)
+    own = (s.pn // 3) // 4 * 4 + 2
+    plr = ctx.makepair(qd, clusters=True, rows=(0, own))
+    pd.zero_()
+    ctx.force_loop(qd, pd, plr, loop=s.steps, variant="cluster", rows=(0, own))
+    ph = pd.cpu().numpy()[:, :3]
+    assert np.abs(ph[:own] - s.p[:own]).max() / s.scale < TOL_FP64 and np.all(ph[own:] == 0)
+    # a shuffle or an explicit invalidate drops the mirror
+    pl2 = ctx.makepair(qd, clusters=True)
+    ctx.random_shfl(pl2)
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl2, variant="cluster")
+    pl3 = ctx.makepair(qd, clusters=True)
+    ctx.list_invalidate()
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl3, variant="cluster")
+    pd.zero_()
+    ctx.force_loop(qd, pd, pl3, loop=s.steps)          # AUTO still works (per-row kernel)
+    assert s.err(pd, "aos4") < TOL_FP64
+
+
 def test_bad_arguments_are_rejected(ctx, torch, sysS):
     from lj_gpu_b200 import LJError
     from lj_gpu_b200 import _capi
@@ -480,8 +530,8 @@ def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
     assert pn == 1000188
     q4 = np.zeros((pn, 4)); q4[:, :3] = q
     qd = torch.from_numpy(q4).cuda()
-    full = ctx.makepair(qd)
     half = ctx.makepair(qd, half=True)
+    full = ctx.makepair(qd, clusters=True)
     assert full.number_of_pairs == 2 * half.number_of_pairs          # every pair listed both ways
     nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
     nop, ptr, lst = list_to_host(full)
@@ -492,7 +542,7 @@ def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
     oracle.force_gather(q, p_o, nop_o, ptr_o, lst_o, steps=3)
     scale = np.abs(p_o).max()
     results = {}
-    for variant, group in (("subwarp", 8), ("tile", 8), ("warp", 32)):
+    for variant, group in (("subwarp", 8), ("tile", 8), ("warp", 32), ("cluster", 0)):
         pd = torch.zeros_like(qd)
         ctx.force_loop(qd, pd, full, loop=3, variant=variant, group=group)
         ph = pd.cpu().numpy()[:, :3]
@@ -502,7 +552,7 @@ def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
         assert np.abs(ph.sum(axis=0)).max() < 1e-9 * scale * np.sqrt(pn)
     # linearity in the step count with static positions: p(6 steps) == 2 * p(3 steps)
     pd6 = torch.zeros_like(qd)
-    ctx.force_loop(qd, pd6, full, loop=6, group=8)
+    ctx.force_loop(qd, pd6, full, loop=6, variant="subwarp", group=8)
     assert (pd6 - 2 * results["subwarp"])[:, :3].abs().max().item() / scale < 1e-14
     # half list + Newton-3 and mixed precision at full size
     pn3 = torch.zeros_like(qd)

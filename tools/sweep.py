@@ -57,15 +57,15 @@ def main():
         qd, pd = arrays(layout)
         npn = pn if layout == "soa" else None
         for sort_rows in ([False] if (args.quick or layout != "aos4") else [False, True]):
-            pl = ctx.makepair(qd, layout=layout, pn=npn, sort_rows=sort_rows)
+            pl = ctx.makepair(qd, layout=layout, pn=npn, sort_rows=sort_rows, clusters=True)
             P = pl.number_of_pairs
             svec = 32 if layout == "aos4" else 24
             B = algorithmic_bytes(pn, P, svec)
-            ms_build = timeit(lambda: ctx.rebuild(qd, pl, layout=layout, pn=npn, sort_rows=sort_rows), 5)
+            ms_build = timeit(lambda: ctx.rebuild(qd, pl, layout=layout, pn=npn, sort_rows=sort_rows, clusters=True), 5)
             print("layout=%s sort_rows=%d N=%d P=%d max_np=%d  list build %.3f ms" % (
                 layout, sort_rows, pn, P, pl.max_partners, ms_build), flush=True)
             results.append(dict(kind="build", layout=layout, sort_rows=sort_rows, ms=ms_build, pn=pn, pairs=P))
-            cases = []
+            cases = [("cluster", 0, 0, "fp64")]
             for g in (1, 2, 4, 8, 16, 32):
                 for tb in ((128, 256) if layout == "aos4" and not sort_rows else (128,)):
                     cases.append(("subwarp", g, tb, "fp64"))
