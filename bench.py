@@ -193,7 +193,7 @@ def run_cuda(args):
     q4 = np.zeros((pn, 4)); q4[:, :3] = q
     qd = torch.from_numpy(q4).cuda()
     pd = torch.zeros_like(qd)
-    use_cl = args.variant in ("auto", "cluster") and args.prec == "fp64"
+    use_cl = args.variant == "cluster" and args.prec == "fp64"
     pl = ctx.makepair(qd, pointer64=False, clusters=use_cl)
     P = pl.number_of_pairs
     fkw = dict(variant=args.variant, group=args.group, precision=args.prec,

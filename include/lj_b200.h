@@ -140,7 +140,8 @@ typedef struct lj_force_args {
   int32_t precision;                 /* lj_precision                                       */
   int32_t pointer64;                 /* 0: pointer is int32[], 1: int64[]                  */
   int32_t threads_per_block;         /* THREAD_BLOCK (CLI argv[1], 64..1024); 0 = default  */
-  int32_t reserved;
+  int32_t list_scalar;               /* 0/1: 4-byte list loads (default, fastest measured);
+                                        2: 16-byte int4 list loads (experiment) */
   int64_t plane_stride;              /* LJ_SOA_D: doubles between planes (>= pn)           */
   int64_t row_begin, row_end;        /* update only rows [row_begin,row_end); 0,0 = all    */
   int64_t list_entries;              /* optional: entries allocated in `list` (number_of_pairs);

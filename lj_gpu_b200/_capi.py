@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblj_b200.so")
+LIB_PATH = os.environ.get("LJ_B200_LIB", os.path.join(HERE, "liblj_b200.so"))  # override: A/B builds
 
 # enums of include/lj_b200.h
 LJ_OK, LJ_ERR_CUDA, LJ_ERR_BAD_ARG, LJ_ERR_CAPACITY, LJ_ERR_OVERFLOW32, LJ_ERR_NO_DEVICE, \
@@ -34,7 +34,7 @@ class LjForceArgs(C.Structure):
         ("cl2", C.c_double), ("list", C.c_void_p), ("number_of_partners", C.c_void_p),
         ("pointer", C.c_void_p), ("layout", C.c_int32), ("list_layout", C.c_int32),
         ("variant", C.c_int32), ("group", C.c_int32), ("precision", C.c_int32),
-        ("pointer64", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32),
+        ("pointer64", C.c_int32), ("threads_per_block", C.c_int32), ("list_scalar", C.c_int32),
         ("plane_stride", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
         ("list_entries", C.c_int64),
     ]

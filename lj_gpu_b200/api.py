@@ -237,7 +237,7 @@ class LJContext:
     # ------------------------------------------------------------------ force
     def force_args(self, q, p, pl: PairList, dt: float = DT, cl2: float = CL2, layout=None,
                    ell: bool = False, variant="auto", group: int = 0, precision: str = "fp64",
-                   threads_per_block: int = 0, rows=None, pn=None) -> capi.LjForceArgs:
+                   threads_per_block: int = 0, rows=None, pn=None, list_scalar: int = 0) -> capi.LjForceArgs:
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
         if pn is not None:
@@ -264,6 +264,7 @@ class LJContext:
         a.precision = {"fp64": LJ_PREC_FP64, "mixed": LJ_PREC_MIXED}[precision]
         a.pointer64 = int(pl.pointer64)
         a.threads_per_block = threads_per_block
+        a.list_scalar = int(list_scalar)
         a.plane_stride = stride
         if rows is not None:
             a.row_begin, a.row_end = rows

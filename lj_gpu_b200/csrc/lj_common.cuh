@@ -117,6 +117,10 @@ int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t p
 // ------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+#ifndef LJ_POS_LOAD
+#define LJ_POS_LOAD 256  // how a double4 position is fetched: 256 | 128 | 64
+#endif
+
 // order-preserving double <-> uint64 encoding (atomicMin/Max on doubles)
 __device__ __forceinline__ unsigned long long enc_ordered(double v) {
   unsigned long long u = (unsigned long long)__double_as_longlong(v);
@@ -154,8 +158,17 @@ template <int LAYOUT>
 __device__ __forceinline__ void load_pos(const void* __restrict__ q, int64_t i, int64_t plane,
                                          double& x, double& y, double& z) {
   if (LAYOUT == LJ_AOS_D4) {
+#if LJ_POS_LOAD == 256
     const double4 v = ld_nc_d4(reinterpret_cast<const double4*>(q) + i);
     x = v.x; y = v.y; z = v.z;
+#elif LJ_POS_LOAD == 128   // LDG.128 (x,y) + LDG.64 (z): 24 of the 32 bytes
+    const double2* b = reinterpret_cast<const double2*>(q) + 2 * i;
+    const double2 xy = __ldg(b);
+    x = xy.x; y = xy.y; z = __ldg(reinterpret_cast<const double*>(b + 1));
+#else                      // three LDG.64
+    const double* b = reinterpret_cast<const double*>(q) + 4 * i;
+    x = __ldg(b); y = __ldg(b + 1); z = __ldg(b + 2);
+#endif
   } else if (LAYOUT == LJ_AOS_D3) {
     const double* b = reinterpret_cast<const double*>(q) + 3 * i;
     x = __ldg(b); y = __ldg(b + 1); z = __ldg(b + 2);

@@ -23,7 +23,10 @@ constexpr int kUnroll = 4;
 // Gather on a CSR list, G lanes per row.  G=32 is the reference's warp_unroll mapping
 // (cuda/kernel.cuh:821-904), G=1 its thread-per-i mapping (cuda/kernel.cuh:67-100).
 // --------------------------------------------------------------------------------------
-template <int G, int LAYOUT, bool PTR64>
+// MODE 0: the kernel.  MODE 1/2 are diagnostics selected by variant 100/101 (tools/sweep.py):
+// 1 = memory path only (pair math replaced by one add per component), 2 = math only (gather
+// confined to 1024 L1-resident particles).  They bracket what the real kernel can reach.
+template <int G, int LAYOUT, bool PTR64, int MODE = 0>
 __global__ void __launch_bounds__(1024)
 lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begin, int64_t row_end,
               int64_t plane, double c24, double c48, long long cl2_bits,
@@ -42,23 +45,53 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
 
   double fx = 0.0, fy = 0.0, fz = 0.0;
   int k = lg;
-  // full tiles: kUnroll independent index loads, then kUnroll independent gathers
+  // Full tiles: kUnroll independent gathers per lane and trip.  The list words of the NEXT trip
+  // are requested before this trip's gathers: every trip of a group starts a fresh 128-byte line
+  // of the list that comes straight from HBM (~1 us), and without the prefetch that latency sits
+  // in front of every gather (ncu: long-scoreboard stalls on the first use of j).
+  int jn[kUnroll];
+  const bool any_full = k + (kUnroll - 1) * G < np;
+  if (any_full) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) jn[u] = __ldg(row + k + u * G);
+  }
   for (; k + (kUnroll - 1) * G < np; k += kUnroll * G) {
     int j[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) j[u] = __ldg(row + k + u * G);
+    for (int u = 0; u < kUnroll; u++) j[u] = jn[u];
+    if (k + kUnroll * G + (kUnroll - 1) * G < np) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) jn[u] = __ldg(row + k + kUnroll * G + u * G);
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) j[u] &= 1023;
+    }
+    if (MODE == 3) {  // list only
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) fx += (double)j[u];
+      continue;
+    }
+    if (MODE == 4) {  // gather only: indices made up from the loop counter, no list traffic
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) j[u] = (int)i + ((k + u * G) & 255) - 128 < 0 ? 0 : (int)i + ((k + u * G) & 255) - 128;
+    }
     double xj[kUnroll], yj[kUnroll], zj[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; u++) load_pos<LAYOUT>(q, j[u], plane, xj[u], yj[u], zj[u]);
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++)
-      lj_pair(xj[u] - xi, yj[u] - yi, zj[u] - zi, c24, c48, cl2_bits, fx, fy, fz);
+    for (int u = 0; u < kUnroll; u++) {
+      if (MODE == 1 || MODE == 4) { fx += xj[u]; fy += yj[u]; fz += zj[u]; }
+      else lj_pair(xj[u] - xi, yj[u] - yi, zj[u] - zi, c24, c48, cl2_bits, fx, fy, fz);
+    }
   }
   for (; k < np; k += G) {
-    const int j = __ldg(row + k);
+    int j = __ldg(row + k);
+    if (MODE == 2) j &= 1023;
     double xj, yj, zj;
     load_pos<LAYOUT>(q, j, plane, xj, yj, zj);
-    lj_pair(xj - xi, yj - yi, zj - zi, c24, c48, cl2_bits, fx, fy, fz);
+    if (MODE == 1) { fx += xj; fy += yj; fz += zj; }
+    else lj_pair(xj - xi, yj - yi, zj - zi, c24, c48, cl2_bits, fx, fy, fz);
   }
 
   if (G > 1) {
@@ -66,6 +99,79 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
     fy = group_sum<G>(fy);
     fz = group_sum<G>(fz);
   }
+  if (lg == 0) add_mom<LAYOUT>(p, i, plane, fx, fy, fz);
+}
+
+// --------------------------------------------------------------------------------------
+// List words fetched four at a time.  Diagnostics (tools/diag_force.py, config C): the scalar
+// kernel is bound by the L1/LSU pipe -- "memory instructions only" takes 0.39 of its 0.42 ms,
+// of which the 4-byte list loads are 0.17-0.22 ms (one LDG.32 per pair-iteration touching four
+// sectors) and the 256-bit gathers 0.235 ms (16 SM-cycles per warp instruction whatever the
+// address pattern).  Here every lane loads one 16-byte-ALIGNED int4 of its row (G lanes = one
+// contiguous 16G-byte span) and uses its own four consecutive entries as the four unrolled
+// gathers: one list instruction per FOUR pair-iterations.  Entries of the first/last int4 that
+// lie outside the row are masked (cutoff -1).  Needs a 16-byte aligned list and a known
+// allocation length so that the last int4 never reads past it.  Summation order differs from the
+// scalar kernel (lane <-> entry mapping), results agree to rounding.
+// --------------------------------------------------------------------------------------
+template <int G, int LAYOUT, bool PTR64>
+__global__ void __launch_bounds__(1024)
+lj_gather_csr_v4(const void* __restrict__ q, void* __restrict__ p, int64_t row_begin, int64_t row_end,
+                 int64_t plane, double c24, double c48, long long cl2_bits,
+                 const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
+                 const void* __restrict__ pointer, int64_t list_entries) {
+  static_assert(G >= 4 && G % 4 == 0, "the int4 transpose needs G a multiple of 4");
+  const int rows_per_block = blockDim.x / G;
+  const int64_t i = row_begin + (int64_t)blockIdx.x * rows_per_block + threadIdx.x / G;
+  const int lane = threadIdx.x & 31;
+  const int lg = threadIdx.x % G;
+  if (i >= row_end) return;  // whole groups leave together
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lg));
+
+  double xi, yi, zi;
+  load_pos<LAYOUT>(q, i, plane, xi, yi, zi);
+  const int np = __ldg(nop + i);
+  const int64_t off = row_offset<PTR64>(pointer, i);
+  const int64_t a0 = off & ~(int64_t)3;      // aligned start of the row's first int4
+  const int lead = (int)(off - a0);          // entries of that int4 belonging to the previous row
+  const int total = lead + np;               // aligned entries up to the end of the row
+  const int4* __restrict__ row4 = reinterpret_cast<const int4*>(list + a0);
+
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  for (int c0 = 0; c0 < total; c0 += 4 * G) {  // uniform within the group
+    // my int4 of this chunk: aligned entries [c0 + 4 lg, c0 + 4 lg + 4)
+    int4 v = make_int4((int)i, (int)i, (int)i, (int)i);
+    const int e0 = c0 + 4 * lg;
+    if (e0 < total) {
+      if (a0 + e0 + 4 <= list_entries) {
+        v = __ldg(row4 + (e0 >> 2));
+      } else {  // the very last int4 of the array may be partial
+        const int32_t* s = list + a0 + e0;
+        if (a0 + e0 + 0 < list_entries) v.x = __ldg(s + 0);
+        if (a0 + e0 + 1 < list_entries) v.y = __ldg(s + 1);
+        if (a0 + e0 + 2 < list_entries) v.z = __ldg(s + 2);
+      }
+    }
+    // each lane keeps ITS four consecutive entries: the scattered gather costs the L1 pipe the
+    // same ~16 cycles whatever the address pattern (tools/diag_force.py), so no transpose
+    int j[4] = {v.x, v.y, v.z, v.w};
+    double xj[4], yj[4], zj[4];
+    long long lim[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u;  // aligned entry index of j[u]
+      const bool valid = e >= lead && e < total;
+      if (!valid) j[u] = (int)i;      // masked: any valid particle
+      lim[u] = valid ? cl2_bits : -1ll;
+      load_pos<LAYOUT>(q, j[u], plane, xj[u], yj[u], zj[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      lj_pair(xj[u] - xi, yj[u] - yi, zj[u] - zi, c24, c48, lim[u], fx, fy, fz);
+  }
+  fx = group_sum<G>(fx);
+  fy = group_sum<G>(fy);
+  fz = group_sum<G>(fz);
   if (lg == 0) add_mom<LAYOUT>(p, i, plane, fx, fy, fz);
 }
 
@@ -171,6 +277,26 @@ void launch_csr(const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c
     lj_newton3_csr<G, LAYOUT, PTR64><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                              c48, cl2_bits, a->list,
                                                              a->number_of_partners, a->pointer);
+  else if (G >= 4 && a->list_entries > 0 && (uintptr_t)a->list % 16 == 0 && a->list_scalar == 2 && a->variant < 100)
+    lj_gather_csr_v4<(G >= 4 ? G : 4), LAYOUT, PTR64><<<blocks, tb, 0, st>>>(
+        a->q, a->p, r0, r1, a->plane_stride, c24, c48, cl2_bits, a->list, a->number_of_partners,
+        a->pointer, a->list_entries);
+  else if (a->variant == 100 && G == 8 && LAYOUT == LJ_AOS_D4)
+    lj_gather_csr<G, LAYOUT, PTR64, 1><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
+                                                               c48, cl2_bits, a->list,
+                                                               a->number_of_partners, a->pointer);
+  else if (a->variant == 101 && G == 8 && LAYOUT == LJ_AOS_D4)
+    lj_gather_csr<G, LAYOUT, PTR64, 2><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
+                                                               c48, cl2_bits, a->list,
+                                                               a->number_of_partners, a->pointer);
+  else if (a->variant == 102 && G == 8 && LAYOUT == LJ_AOS_D4)
+    lj_gather_csr<G, LAYOUT, PTR64, 3><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
+                                                               c48, cl2_bits, a->list,
+                                                               a->number_of_partners, a->pointer);
+  else if (a->variant == 103 && G == 8 && LAYOUT == LJ_AOS_D4)
+    lj_gather_csr<G, LAYOUT, PTR64, 4><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
+                                                               c48, cl2_bits, a->list,
+                                                               a->number_of_partners, a->pointer);
   else
     lj_gather_csr<G, LAYOUT, PTR64><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                             c48, cl2_bits, a->list,
@@ -242,7 +368,7 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
              "lj_force_step: THREAD_BLOCK must be a multiple of 32 in [64,1024]");
 
   int variant = a->variant;
-  if (variant == LJ_VARIANT_AUTO || variant == LJ_VARIANT_CLUSTER) variant = LJ_VARIANT_SUBWARP;
+  if (variant == LJ_VARIANT_AUTO || variant == LJ_VARIANT_CLUSTER || variant >= 100) variant = LJ_VARIANT_SUBWARP;
   const bool n3 = variant == LJ_VARIANT_NEWTON3;
   LJ_REQUIRE(ctx, !(n3 && a->list_layout == LJ_LIST_ELL), "lj_force_step: Newton-3 needs a CSR list");
   int g = a->group;
@@ -258,13 +384,14 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
     memcpy(&cl2_bits, &c, sizeof c);
   }
 
-  // AUTO prefers the cluster pair list when lj_build_list(LJ_LIST_CLUSTERS) mirrored exactly
-  // these list arrays; LJ_VARIANT_CLUSTER insists on it
-  if (a->variant == LJ_VARIANT_AUTO || a->variant == LJ_VARIANT_CLUSTER) {
-    if (lj_cluster_usable(ctx, a, r0, r1)) return lj_force_cluster_launch(ctx, a, r0, r1, c24, c48, cl2_bits, st);
-    LJ_REQUIRE(ctx, a->variant != LJ_VARIANT_CLUSTER,
+  // LJ_VARIANT_CLUSTER runs on the cluster pair list that lj_build_list(LJ_LIST_CLUSTERS)
+  // mirrored for exactly these list arrays.  AUTO stays on the per-row gather: on B200 the
+  // cluster kernel trades L1 wavefronts for 1.5x FP64 work and measures slower.
+  if (a->variant == LJ_VARIANT_CLUSTER) {
+    LJ_REQUIRE(ctx, lj_cluster_usable(ctx, a, r0, r1),
                "lj_force_step: no cluster pair list for these arrays (build with LJ_LIST_CLUSTERS; FP64, "
                "CSR, row range on 4-row boundaries)");
+    return lj_force_cluster_launch(ctx, a, r0, r1, c24, c48, cl2_bits, st);
   }
   if (a->precision == LJ_PREC_MIXED) {
     LJ_REQUIRE(ctx, !n3 && a->list_layout == LJ_LIST_CSR, "lj_force_step: mixed precision is gather/CSR only");

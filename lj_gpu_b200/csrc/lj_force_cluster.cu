@@ -19,9 +19,22 @@
 
 namespace {
 
+template <int LAYOUT>
+__device__ __forceinline__ void red_mom(void* __restrict__ p, int64_t i, int64_t plane, double fx,
+                                        double fy, double fz) {
+  double* b;
+  int64_t s;
+  if (LAYOUT == LJ_AOS_D4) { b = reinterpret_cast<double*>(p) + 4 * i; s = 1; }
+  else if (LAYOUT == LJ_AOS_D3) { b = reinterpret_cast<double*>(p) + 3 * i; s = 1; }
+  else { b = reinterpret_cast<double*>(p) + i; s = plane; }
+  atomicAdd(b, fx);
+  atomicAdd(b + s, fy);
+  atomicAdd(b + 2 * s, fz);
+}
+
 constexpr int kClWarps = 8;
 constexpr int kClThreads = kClWarps * 32 + 32;  // + producer warp
-constexpr int kClPerWarp = 4;
+constexpr int kClPerWarp = 2;
 constexpr int kClTile = kClWarps * kClPerWarp;  // clusters per tile (128 rows)
 constexpr int kClCapInts = kClTile * 256;       // staged entries per tile (rho=1: ~200/cluster)
 
@@ -118,24 +131,30 @@ lj_gather_cluster(const void* __restrict__ q, void* __restrict__ p, int64_t row0
       const unsigned self = (unsigned)(row0 + 4 * c);  // a valid particle for idle lanes, mask 0
       double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, az[4] = {0, 0, 0, 0};
 
-      for (int k = lane; k < U; k += 64) {
-        // two entries per lane and trip; the second may be past the end (mask 0 -> no effect)
-        uint32_t e0, e1;
-        const bool v1 = k + 32 < U;
-        if (in_smem) { e0 = src[k]; e1 = v1 ? src[k + 32] : self; }
-        else { e0 = __ldg(src + k); e1 = v1 ? __ldg(src + k + 32) : self; }
-        double x0, y0, z0, x1, y1, z1;
-        load_pos<LAYOUT>(q, e0 & 0x0fffffffu, plane, x0, y0, z0);
-        load_pos<LAYOUT>(q, e1 & 0x0fffffffu, plane, x1, y1, z1);
+      // software pipeline over 32-entry chunks: the next chunk's entry and q[j] are in flight
+      // while the current chunk's four pair evaluations run
+      auto fetch = [&](int k, uint32_t& e, double& x, double& y, double& z) {
+        e = k < U ? (in_smem ? src[k] : __ldg(src + k)) : self;  // past the end: mask 0
+        load_pos<LAYOUT>(q, e & 0x0fffffffu, plane, x, y, z);
+      };
+      // two chunks ahead, ping-pong register sets (no register moves on the critical path)
+      auto eval = [&](uint32_t e, double xj, double yj, double zj) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-          const long long lim = ((e0 >> (28 + r)) & 1u) ? cl2_bits : -1ll;
-          lj_pair(x0 - xi[r], y0 - yi[r], z0 - zi[r], c24, c48, lim, ax[r], ay[r], az[r]);
+          const long long lim = ((e >> (28 + r)) & 1u) ? cl2_bits : -1ll;
+          lj_pair(xj - xi[r], yj - yi[r], zj - zi[r], c24, c48, lim, ax[r], ay[r], az[r]);
         }
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const long long lim = ((e1 >> (28 + r)) & 1u) ? cl2_bits : -1ll;
-          lj_pair(x1 - xi[r], y1 - yi[r], z1 - zi[r], c24, c48, lim, ax[r], ay[r], az[r]);
+      };
+      uint32_t ea, eb = 0;
+      double xa, ya, za, xb = 0.0, yb = 0.0, zb = 0.0;
+      fetch(lane, ea, xa, ya, za);
+      if (32 < U) fetch(32 + lane, eb, xb, yb, zb);
+      for (int k0 = 0; k0 < U; k0 += 64) {
+        eval(ea, xa, ya, za);
+        if (k0 + 64 < U) fetch(k0 + 64 + lane, ea, xa, ya, za);
+        if (k0 + 32 < U) {
+          eval(eb, xb, yb, zb);
+          if (k0 + 96 < U) fetch(k0 + 96 + lane, eb, xb, yb, zb);
         }
       }
       int my_row;
@@ -143,11 +162,83 @@ lj_gather_cluster(const void* __restrict__ q, void* __restrict__ p, int64_t row0
       const double sy = batch_sum<32, 4>(ay, lane, 0xffffffffu, my_row);
       const double sz = batch_sum<32, 4>(az, lane, 0xffffffffu, my_row);
       const int64_t wrow = row0 + 4 * c + my_row;
-      if ((lane & 7) == 0 && wrow < row_end) add_mom<LAYOUT>(p, wrow, plane, sx, sy, sz);
+      // one writer per member row; RED (no return value) so that the warp does not stall on a
+      // load of p at the end of every cluster.  Exactly one add per component and step:
+      // the result is deterministic.
+      if ((lane & 7) == 0 && wrow < row_end) red_mom<LAYOUT>(p, wrow, plane, sx, sy, sz);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[b]);  // this warp no longer reads stage[b] / qi_s
   }
+}
+
+// --------------------------------------------------------------------------------------
+// Lane-per-member variant: a warp = 8 entry slots x 4 cluster members.  The four lanes of a slot
+// load the SAME q[j] (one sector request, coalesced by the LSU), every lane evaluates ONE pair per
+// entry like the per-row kernel, so registers stay at the per-row level (~50, 58 % occupancy)
+// instead of the 96 of the register-blocked kernel above, whose two resident CTAs cannot hide
+// the gather latency (ncu: 27 % warps active, FP64 pipe 39 %).  No shared memory, no TMA: eight
+// consecutive entries are one 32-byte sector.
+// --------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(1024)
+lj_gather_cluster_lanes(const void* __restrict__ q, void* __restrict__ p, int64_t row0, int64_t row_end,
+                        int64_t c_begin, int64_t c_end, int64_t plane, double c24, double c48,
+                        long long cl2_bits, const uint32_t* __restrict__ cl_list,
+                        const long long* __restrict__ cl_ptr) {
+  const int64_t c = c_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (c >= c_end) return;  // whole warps leave
+  const int lane = threadIdx.x & 31;
+  const int r = lane & 3, slot = lane >> 2;
+  const int64_t i = row0 + 4 * c + r;
+  const bool member = i < row_end;
+  const int64_t iq = member ? i : row0 + 4 * c;  // absent member: compute on a valid particle, masked
+  double xi, yi, zi;
+  load_pos<LAYOUT>(q, iq, plane, xi, yi, zi);
+  const long long off = __ldg(cl_ptr + c);
+  const int U = (int)(__ldg(cl_ptr + c + 1) - off);
+  const uint32_t* __restrict__ src = cl_list + off;
+  const unsigned self = (unsigned)iq;
+  const unsigned rbit = member ? (1u << (28 + r)) : 0u;
+
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  int k = slot;
+  for (; k + 24 < U; k += 32) {  // four entries per lane, all valid
+    uint32_t e[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) e[u] = __ldg(src + k + 8 * u);
+    double xj[4], yj[4], zj[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) load_pos<LAYOUT>(q, e[u] & 0x0fffffffu, plane, xj[u], yj[u], zj[u]);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      lj_pair(xj[u] - xi, yj[u] - yi, zj[u] - zi, c24, c48, (e[u] & rbit) ? cl2_bits : -1ll, fx, fy, fz);
+  }
+  for (; k - slot < U; k += 8) {  // warp-uniform trip count; lanes past the end are masked
+    const uint32_t e = k < U ? __ldg(src + k) : self;
+    double xj, yj, zj;
+    load_pos<LAYOUT>(q, e & 0x0fffffffu, plane, xj, yj, zj);
+    lj_pair(xj - xi, yj - yi, zj - zi, c24, c48, (e & rbit) ? cl2_bits : -1ll, fx, fy, fz);
+  }
+#pragma unroll
+  for (int m = 4; m <= 16; m <<= 1) {
+    fx += __shfl_xor_sync(0xffffffffu, fx, m);
+    fy += __shfl_xor_sync(0xffffffffu, fy, m);
+    fz += __shfl_xor_sync(0xffffffffu, fz, m);
+  }
+  if (slot == 0 && member) add_mom<LAYOUT>(p, i, plane, fx, fy, fz);
+}
+
+template <int LAYOUT>
+int launch_cluster_lanes(lj_ctx* ctx, const lj_force_args* a, int64_t c0, int64_t c1, double c24,
+                         double c48, long long cl2_bits, int tb, cudaStream_t st) {
+  const int64_t warps_per_block = tb / 32;
+  const unsigned blocks = (unsigned)((c1 - c0 + warps_per_block - 1) / warps_per_block);
+  lj_gather_cluster_lanes<LAYOUT><<<blocks, tb, 0, st>>>(a->q, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1,
+                                                          a->plane_stride, c24, c48, cl2_bits,
+                                                          ctx->cl_list, ctx->cl_ptr);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
 }
 
 template <int LAYOUT>
@@ -191,6 +282,14 @@ bool lj_cluster_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, in
 int lj_force_cluster_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, double c24,
                             double c48, long long cl2_bits, cudaStream_t st) {
   const int64_t c0 = (r0 - ctx->cl_r0) / 4, c1 = (r1 - ctx->cl_r0 + 3) / 4;
+  if (a->group != 32) {  // default: lane-per-member; group = 32 selects the register-blocked kernel
+    const int tb = a->threads_per_block ? a->threads_per_block : 128;
+    switch (a->layout) {
+      case LJ_AOS_D4: return launch_cluster_lanes<LJ_AOS_D4>(ctx, a, c0, c1, c24, c48, cl2_bits, tb, st);
+      case LJ_AOS_D3: return launch_cluster_lanes<LJ_AOS_D3>(ctx, a, c0, c1, c24, c48, cl2_bits, tb, st);
+      case LJ_SOA_D: return launch_cluster_lanes<LJ_SOA_D>(ctx, a, c0, c1, c24, c48, cl2_bits, tb, st);
+    }
+  }
   switch (a->layout) {
     case LJ_AOS_D4: return launch_cluster<LJ_AOS_D4>(ctx, a, c0, c1, c24, c48, cl2_bits, st);
     case LJ_AOS_D3: return launch_cluster<LJ_AOS_D3>(ctx, a, c0, c1, c24, c48, cl2_bits, st);

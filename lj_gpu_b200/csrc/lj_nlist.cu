@@ -459,50 +459,73 @@ k_search_cluster(const void* __restrict__ q, int64_t plane, int64_t pn, const gr
       if (++y > cy1) { y = cy0; z++; }
     }
     while (__any_sync(0xffffffffu, m < m_end)) {
-      unsigned bits = 0;
+      unsigned bits = 0, exact = 0;
       int j = 0;
-      if (m < m_end) {
-        const float4 c32 = sorted_pos32[m];
-        j = __float_as_int(c32.w);
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const float dx = px[r] - c32.x, dy = py[r] - c32.y, dz = pz[r] - c32.z;
-          const float r2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          if (r2f < hi_f) {
-            bool hit;
-            if (r2f < lo_f && r2f > margin) {
-              hit = true;
-            } else {  // near the threshold or near zero (the member itself / coincident): FP64
-              double xi, yi, zi;
-              load_pos<LAYOUT>(q, i0 + r, plane, xi, yi, zi);
-              const double4 cj = sorted_pos[m];
-              const double ddx = xi - cj.x, ddy = yi - cj.y, ddz = zi - cj.z;
-              hit = (j != (int)(i0 + r)) && (fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2);
-            }
-            if (half) hit = hit && (j > (int)(i0 + r));
-            bits |= hit ? (1u << r) : 0u;
-          }
-        }
-      }
+      const bool inb = m < m_end;
+      float4 c32 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inb) c32 = sorted_pos32[m];
+      j = __float_as_int(c32.w);
+      // straight-line classification of the candidate against the four members
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        const unsigned b = __ballot_sync(0xffffffffu, (bits >> r) & 1u) & gbits;
-        if (FILL && ((bits >> r) & 1u)) list[base[r] + cnt[r] + __popc(b & lt_mask)] = j;
-        cnt[r] += __popc(b);
+        const float dx = px[r] - c32.x, dy = py[r] - c32.y, dz = pz[r] - c32.z;
+        const float r2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool sure = r2f < lo_f && r2f > margin;
+        bits |= (sure ? 1u : 0u) << r;
+        exact |= ((r2f < hi_f && !sure) ? 1u : 0u) << r;
       }
-      const unsigned bu = __ballot_sync(0xffffffffu, bits != 0u) & gbits;
-      if (FILL && emit_cl && bits != 0u) cl_list[cbase + ucnt + __popc(bu & lt_mask)] = (bits << 28) | (unsigned)j;
-      ucnt += __popc(bu);
+      if (!inb) { bits = 0; exact = 0; }
+      if (exact) {  // rare: within the FP32 error of the threshold, or of zero (self / coincident)
+        const double4 cj = sorted_pos[m];
+#pragma unroll 1
+        for (int r = 0; r < 4; r++)
+          if ((exact >> r) & 1u) {
+            double xi, yi, zi;
+            load_pos<LAYOUT>(q, i0 + r, plane, xi, yi, zi);
+            const double ddx = xi - cj.x, ddy = yi - cj.y, ddz = zi - cj.z;
+            if ((j != (int)(i0 + r)) && (fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2)) bits |= 1u << r;
+          }
+      }
+      if (half) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (j <= (int)(i0 + r)) bits &= ~(1u << r);
+      }
+      if (FILL) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const unsigned b = __ballot_sync(0xffffffffu, (bits >> r) & 1u) & gbits;
+          if ((bits >> r) & 1u) list[base[r] + cnt[r] + __popc(b & lt_mask)] = j;
+          cnt[r] += __popc(b);
+        }
+        if (emit_cl) {
+          const unsigned bu = __ballot_sync(0xffffffffu, bits != 0u) & gbits;
+          if (bits != 0u) cl_list[cbase + ucnt + __popc(bu & lt_mask)] = (bits << 28) | (unsigned)j;
+          ucnt += __popc(bu);
+        }
+      } else {  // counting needs no ordering: per-lane tallies, reduced once at the end
+#pragma unroll
+        for (int r = 0; r < 4; r++) cnt[r] += (bits >> r) & 1u;
+        ucnt += bits != 0u;
+      }
       m += GL;
     }
   }
-  if (!FILL && nrows > 0) {
-    if (lg < nrows) {
-      const int mine = lg == 0 ? cnt[0] : lg == 1 ? cnt[1] : lg == 2 ? cnt[2] : cnt[3];
-      nop[i0 + lg] = mine;
-      if (mine > *(volatile int*)&tot->max_np) atomicMax(&tot->max_np, mine);
+  if (!FILL) {
+#pragma unroll
+    for (int s = GL / 2; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) cnt[r] += __shfl_xor_sync(0xffffffffu, cnt[r], s);
+      ucnt += __shfl_xor_sync(0xffffffffu, ucnt, s);
     }
-    if (emit_cl && lg == 0) cl_cnt[c] = (uint32_t)ucnt;
+    if (nrows > 0) {
+      if (lg < nrows) {
+        const int mine = lg == 0 ? cnt[0] : lg == 1 ? cnt[1] : lg == 2 ? cnt[2] : cnt[3];
+        nop[i0 + lg] = mine;
+        if (mine > *(volatile int*)&tot->max_np) atomicMax(&tot->max_np, mine);
+      }
+      if (emit_cl && lg == 0) cl_cnt[c] = (uint32_t)ucnt;
+    }
   }
 }
 

@@ -376,7 +376,7 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
     la.search_len = m->search_len; la.number_of_partners = nop; la.pointer = ptr; la.pointer64 = ptr64;
     la.flags = m->list_flags;
     if (!m->half && m->precision == LJ_PREC_FP64 &&
-        (m->variant == LJ_VARIANT_AUTO || m->variant == LJ_VARIANT_CLUSTER))
+        m->variant == LJ_VARIANT_CLUSTER)
       la.flags |= LJ_LIST_CLUSTERS;
     if (own_list) {
       // first build sizes the list: count pass only needs capacity 0 to learn the total

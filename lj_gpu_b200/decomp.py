@@ -167,7 +167,7 @@ class DecomposedSystem:
         self.p = torch.zeros_like(self.q)
         self.compute = torch.cuda.current_stream()
         self.comm = torch.cuda.Stream()
-        self.pl = self.ctx.makepair(self.q, rows=(0, self.slab.n_own), search_len=search_len, clusters=True)
+        self.pl = self.ctx.makepair(self.q, rows=(0, self.slab.n_own), search_len=search_len)
         self.search_len = search_len
         self.pairs_local = self.pl.number_of_pairs
         self.peer_ptr = {}
@@ -223,7 +223,7 @@ class DecomposedSystem:
             ctx.force_step(self.q, self.p, self.pl, rows=(0, s.n_own), **fkw)
 
     def rebuild(self):
-        self.ctx.rebuild(self.q, self.pl, search_len=self.search_len, rows=(0, self.slab.n_own), clusters=True)
+        self.ctx.rebuild(self.q, self.pl, search_len=self.search_len, rows=(0, self.slab.n_own))
 
     def run(self, steps: int, rebuild_every: int, first_step: int = 0, **fkw):
         for k in range(first_step, first_step + steps):

@@ -235,7 +235,8 @@ FORCE_CASES = [("aos4", "subwarp", 8), ("aos4", "warp", 32), ("aos4", "thread", 
                ("aos4", "tile", 8), ("aos4", "tile", 32), ("aos4", "tile", 4),
                ("aos3", "subwarp", 8), ("aos3", "warp", 32), ("aos3", "tile", 16),
                ("soa", "subwarp", 8), ("soa", "thread", 1), ("soa", "tile", 8),
-               ("aos4", "cluster", 0), ("aos3", "cluster", 0), ("soa", "cluster", 0)]
+               ("aos4", "cluster", 0), ("aos3", "cluster", 0), ("soa", "cluster", 0),
+               ("aos4", "cluster", 32), ("aos3", "cluster", 32)]
 
 
 @pytest.mark.parametrize("layout,variant,group", FORCE_CASES)
@@ -274,6 +275,31 @@ def test_force_fp64_config_B(ctx, torch, sysB, golden, layout, variant, group):
     from lj_gpu_b200 import print_results
     with open(os.path.join(GOLDEN, "density1.dat")) as f:
         assert print_results(ph) == f.read()  # byte-identical to ref_data/density1.dat
+
+
+def test_int4_and_scalar_list_paths_agree(ctx, torch, sysS):
+    # different lane -> entry mapping, so different summation order: agreement to rounding
+    s = sysS
+    for layout in ("aos4", "aos3", "soa"):
+        qd, _ = s.device_arrays(torch, layout)
+        pn = s.pn if layout == "soa" else None
+        pl = ctx.makepair(qd, layout=layout, pn=pn)
+        for group in (4, 8, 16, 32):
+            a, b = torch.zeros_like(qd), torch.zeros_like(qd)
+            ctx.force_loop(qd, a, pl, loop=s.steps, layout=layout, variant="subwarp", group=group, pn=pn,
+                           list_scalar=2)
+            ctx.force_loop(qd, b, pl, loop=s.steps, layout=layout, variant="subwarp", group=group, pn=pn)
+            assert s.err(a, layout) < TOL_FP64
+            assert s.err(b, layout) < TOL_FP64
+            assert (a - b).abs().max().item() / s.scale < 1e-14, (layout, group)
+    # a list that is NOT 16-byte aligned silently takes the scalar path
+    qd, pd = s.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd)
+    shifted = torch.empty(pl.sorted_list.numel() + 1, dtype=torch.int32, device="cuda")
+    shifted[1:] = pl.sorted_list
+    pl.sorted_list = shifted[1:]
+    ctx.force_loop(qd, pd, pl, loop=s.steps, variant="subwarp", group=8, list_scalar=2)
+    assert s.err(pd, "aos4") < TOL_FP64
 
 
 def test_force_pointer64_and_thread_block(ctx, torch, sysS):
@@ -399,7 +425,7 @@ def test_cluster_list_identity_row_ranges_and_invalidation(ctx, torch, sysS):
         assert np.all(ph[:r0] == 0) and np.all(ph[r1:] == 0)
         assert np.abs(ph[r0:r1] - s.p[r0:r1]).max() / s.scale < TOL_FP64
     pd.zero_()
-    ctx.force_loop(qd, pd, pl, loop=s.steps, variant="auto", rows=(3, s.pn - 2))   # unaligned: AUTO falls back
+    ctx.force_loop(qd, pd, pl, loop=s.steps, variant="auto", rows=(3, s.pn - 2))   # AUTO: per-row kernel
     ph = pd.cpu().numpy()[:, :3]
     assert np.abs(ph[3:s.pn - 2] - s.p[3:s.pn - 2]).max() / s.scale < TOL_FP64 and np.all(ph[:3] == 0)
     with pytest.raises(LJError):

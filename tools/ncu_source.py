@@ -7,7 +7,7 @@ txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 lines = txt.splitlines()
 # find header line
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rows = list(csv.reader(io.StringIO("\n".join(lines[start:]))))
+rows = [r for r in csv.reader(io.StringIO("\n".join(lines[start:]))) if not (r and r[0] == "Address" and r is not None and False)]
 hdr = rows[0]; idx = {k: i for i, k in enumerate(hdr)}
 tot = sum(int(r[idx["# Samples"]] or 0) for r in rows[1:] if len(r) == len(hdr))
 print("total samples", tot)

@@ -62,19 +62,25 @@ def main():
             svec = 32 if layout == "aos4" else 24
             B = algorithmic_bytes(pn, P, svec)
             ms_build = timeit(lambda: ctx.rebuild(qd, pl, layout=layout, pn=npn, sort_rows=sort_rows, clusters=True), 5)
-            print("layout=%s sort_rows=%d N=%d P=%d max_np=%d  list build %.3f ms" % (
-                layout, sort_rows, pn, P, pl.max_partners, ms_build), flush=True)
+            plain = ctx.makepair(qd, layout=layout, pn=npn, sort_rows=sort_rows)
+            ms_plain = timeit(lambda: ctx.rebuild(qd, plain, layout=layout, pn=npn, sort_rows=sort_rows), 5)
+            del plain
+            print("layout=%s sort_rows=%d N=%d P=%d max_np=%d  list build %.3f ms (+cluster list: %.3f ms)" % (
+                layout, sort_rows, pn, P, pl.max_partners, ms_plain, ms_build), flush=True)
             results.append(dict(kind="build", layout=layout, sort_rows=sort_rows, ms=ms_build, pn=pn, pairs=P))
-            cases = [("cluster", 0, 0, "fp64")]
+            cases = [("cluster", 0, 0, "fp64"), ("cluster", 0, 256, "fp64"), ("cluster", 32, 0, "fp64")]
             for g in (1, 2, 4, 8, 16, 32):
                 for tb in ((128, 256) if layout == "aos4" and not sort_rows else (128,)):
                     cases.append(("subwarp", g, tb, "fp64"))
             for g in (4, 8, 16, 32):
                 cases.append(("tile", g, 0, "fp64"))
+            for g in (4, 8, 16):
+                cases.append(("subwarp", g, 128, "fp64-int4-list"))
             for g in (4, 8, 16, 32):
                 cases.append(("subwarp", g, 128, "mixed"))
             for variant, g, tb, prec in cases:
-                kw = dict(layout=layout, pn=npn, variant=variant, group=g, threads_per_block=tb, precision=prec)
+                kw = dict(layout=layout, pn=npn, variant=variant, group=g, threads_per_block=tb,
+                          precision=prec.split("-")[0], list_scalar=2 if prec.endswith("int4-list") else 0)
                 try:
                     ms = timeit(lambda: ctx.force_step(qd, pd, pl, **kw), args.reps)
                 except Exception as e:  # noqa: BLE001
