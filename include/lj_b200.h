@@ -169,7 +169,10 @@ enum {
    * up to four i-particles from registers.  Full lists only; one small host read-back per build.
    * The mirror is tied to the three output arrays: rebuilding into them, lj_shuffle_rows on them
    * or lj_list_invalidate() drops it. */
-  LJ_LIST_CLUSTERS = 2
+  LJ_LIST_CLUSTERS = 2,
+  /* use the one-search-per-particle kernel instead of the default cluster-organised search
+   * (identical output; kept for A/B measurements) */
+  LJ_LIST_PER_PARTICLE_SEARCH = 4
 };
 
 typedef struct lj_list_args {

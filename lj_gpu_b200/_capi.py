@@ -22,6 +22,7 @@ LJ_VARIANT_AUTO, LJ_VARIANT_SUBWARP, LJ_VARIANT_TILE_TMA, LJ_VARIANT_NEWTON3, LJ
 LJ_PREC_FP64, LJ_PREC_MIXED = 0, 1
 LJ_LIST_SORT_ROWS = 1
 LJ_LIST_CLUSTERS = 2
+LJ_LIST_PER_PARTICLE_SEARCH = 4
 
 
 class LjBuf(C.Structure):

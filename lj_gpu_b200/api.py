@@ -141,7 +141,7 @@ class LJContext:
     def makepair(self, q, search_len: float = SEARCH_LENGTH, half: bool = False, layout=None,
                  pointer64: bool = False, sort_rows: bool = False, capacity: int | None = None,
                  rows=None, pn=None, out: PairList | None = None, clusters: bool = False,
-                 stream=None) -> PairList:
+                 per_particle: bool = False, stream=None) -> PairList:
         """makepair() (cuda/force_cuda.cu:122-163) on the GPU.  Returns device arrays.
         clusters=True also builds the library-owned cluster pair list (LJ_LIST_CLUSTERS) that the
         "auto"/"cluster" force variants use for exactly these arrays."""
@@ -163,7 +163,8 @@ class LJContext:
         a.search_len = search_len
         a.number_of_partners, a.pointer = nop.data_ptr(), ptr.data_ptr()
         a.pointer64 = int(pointer64)
-        a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0)
+        a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0) | \
+            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         total = C.c_int64(0)
@@ -181,7 +182,8 @@ class LJContext:
         return PairList(nop, ptr, lst, int(total.value), int(mx.value), half)
 
     def rebuild(self, q, pl: PairList, search_len: float = SEARCH_LENGTH, layout=None,
-                sort_rows: bool = False, rows=None, pn=None, clusters: bool = False, stream=None):
+                sort_rows: bool = False, rows=None, pn=None, clusters: bool = False,
+                per_particle: bool = False, stream=None):
         """Asynchronous rebuild into existing arrays (no host sync, no reallocation)."""
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
@@ -193,7 +195,8 @@ class LJContext:
         a.number_of_partners, a.pointer = pl.number_of_partners.data_ptr(), pl.pointer.data_ptr()
         a.sorted_list, a.capacity = pl.sorted_list.data_ptr(), pl.sorted_list.numel()
         a.pointer64 = int(pl.pointer64)
-        a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0)
+        a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0) | \
+            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         self._check(self.lib.lj_build_list(self.h, C.byref(a), None, self._stream(stream)))

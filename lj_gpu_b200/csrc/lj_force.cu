@@ -297,10 +297,18 @@ void launch_csr(const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c
     lj_gather_csr<G, LAYOUT, PTR64, 4><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                                c48, cl2_bits, a->list,
                                                                a->number_of_partners, a->pointer);
-  else
+  else {
+    // the gather kernels use no shared memory: give the whole 228 KB array to L1
+    static bool carved = false;
+    if (!carved) {
+      cudaFuncSetAttribute(lj_gather_csr<G, LAYOUT, PTR64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxL1);
+      carved = true;
+    }
     lj_gather_csr<G, LAYOUT, PTR64><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                             c48, cl2_bits, a->list,
                                                             a->number_of_partners, a->pointer);
+  }
 }
 
 template <int LAYOUT, bool PTR64>

@@ -229,6 +229,61 @@ lj_gather_cluster_lanes(const void* __restrict__ q, void* __restrict__ p, int64_
   if (slot == 0 && member) add_mom<LAYOUT>(p, i, plane, fx, fy, fz);
 }
 
+// --------------------------------------------------------------------------------------
+// Register-blocked variant WITHOUT the tile machinery: one warp per cluster, entries read
+// straight from global memory (32 consecutive words = one line), two chunks in flight.
+// --------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+lj_gather_cluster_rb(const void* __restrict__ q, void* __restrict__ p, int64_t row0, int64_t row_end,
+                     int64_t c_begin, int64_t c_end, int64_t plane, double c24, double c48,
+                     long long cl2_bits, const uint32_t* __restrict__ cl_list,
+                     const long long* __restrict__ cl_ptr) {
+  const int64_t c = c_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (c >= c_end) return;
+  const int lane = threadIdx.x & 31;
+  const long long off = __ldg(cl_ptr + c);
+  const int U = (int)(__ldg(cl_ptr + c + 1) - off);
+  const uint32_t* __restrict__ src = cl_list + off;
+  const unsigned self = (unsigned)(row0 + 4 * c);
+  auto fetch = [&](int k, uint32_t& e, double& x, double& y, double& z) {
+    e = k < U ? __ldg(src + k) : self;
+    load_pos<LAYOUT>(q, e & 0x0fffffffu, plane, x, y, z);
+  };
+  uint32_t ea, eb = 0;
+  double xa, ya, za, xb = 0.0, yb = 0.0, zb = 0.0;
+  fetch(lane, ea, xa, ya, za);
+  if (32 < U) fetch(32 + lane, eb, xb, yb, zb);
+  double xi[4], yi[4], zi[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int64_t i = row0 + 4 * c + r;
+    load_pos<LAYOUT>(q, i < row_end ? i : row0 + 4 * c, plane, xi[r], yi[r], zi[r]);
+  }
+  double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, az[4] = {0, 0, 0, 0};
+  auto eval = [&](uint32_t e, double xj, double yj, double zj) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const long long lim = ((e >> (28 + r)) & 1u) ? cl2_bits : -1ll;
+      lj_pair(xj - xi[r], yj - yi[r], zj - zi[r], c24, c48, lim, ax[r], ay[r], az[r]);
+    }
+  };
+  for (int k0 = 0; k0 < U; k0 += 64) {
+    eval(ea, xa, ya, za);
+    if (k0 + 64 < U) fetch(k0 + 64 + lane, ea, xa, ya, za);
+    if (k0 + 32 < U) {
+      eval(eb, xb, yb, zb);
+      if (k0 + 96 < U) fetch(k0 + 96 + lane, eb, xb, yb, zb);
+    }
+  }
+  int my_row;
+  const double sx = batch_sum<32, 4>(ax, lane, 0xffffffffu, my_row);
+  const double sy = batch_sum<32, 4>(ay, lane, 0xffffffffu, my_row);
+  const double sz = batch_sum<32, 4>(az, lane, 0xffffffffu, my_row);
+  const int64_t wrow = row0 + 4 * c + my_row;
+  if ((lane & 7) == 0 && wrow < row_end) red_mom<LAYOUT>(p, wrow, plane, sx, sy, sz);
+}
+
 template <int LAYOUT>
 int launch_cluster_lanes(lj_ctx* ctx, const lj_force_args* a, int64_t c0, int64_t c1, double c24,
                          double c48, long long cl2_bits, int tb, cudaStream_t st) {
@@ -282,7 +337,17 @@ bool lj_cluster_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, in
 int lj_force_cluster_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, double c24,
                             double c48, long long cl2_bits, cudaStream_t st) {
   const int64_t c0 = (r0 - ctx->cl_r0) / 4, c1 = (r1 - ctx->cl_r0 + 3) / 4;
-  if (a->group != 32) {  // default: lane-per-member; group = 32 selects the register-blocked kernel
+  if (a->group == 16) {  // register-blocked, one warp per cluster, no tile staging
+    const unsigned blocks = (unsigned)((c1 - c0 + 3) / 4);
+    switch (a->layout) {
+      case LJ_AOS_D4: lj_gather_cluster_rb<LJ_AOS_D4><<<blocks, 128, 0, st>>>(a->q, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2_bits, ctx->cl_list, ctx->cl_ptr); break;
+      case LJ_AOS_D3: lj_gather_cluster_rb<LJ_AOS_D3><<<blocks, 128, 0, st>>>(a->q, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2_bits, ctx->cl_list, ctx->cl_ptr); break;
+      default: lj_gather_cluster_rb<LJ_SOA_D><<<blocks, 128, 0, st>>>(a->q, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2_bits, ctx->cl_list, ctx->cl_ptr); break;
+    }
+    LJ_LAUNCHED(ctx);
+    return LJ_OK;
+  }
+  if (a->group != 32) {  // default: lane-per-member; group = 32 selects the tiled register-blocked kernel
     const int tb = a->threads_per_block ? a->threads_per_block : 128;
     switch (a->layout) {
       case LJ_AOS_D4: return launch_cluster_lanes<LJ_AOS_D4>(ctx, a, c0, c1, c24, c48, cl2_bits, tb, st);

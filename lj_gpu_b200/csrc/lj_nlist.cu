@@ -710,8 +710,10 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
                         ctx->cl_id_ptr == a->pointer))
     ctx->cl_valid = false;
 
-  if ((a->flags & LJ_LIST_CLUSTERS) && pn < (1LL << 28) && r1 > r0) {
-    // ---------------- cluster search: CSR arrays + the cluster pair list in one go ----------
+  // The cluster-organised search is the default engine (one candidate stream per four rows is
+  // cheaper than four per-particle searches); LJ_LIST_PER_PARTICLE_SEARCH selects k_search.
+  if (!(a->flags & LJ_LIST_PER_PARTICLE_SEARCH) && pn < (1LL << 28) && r1 > r0) {
+    // ---------------- cluster search: CSR arrays (+ the cluster pair list on request) -------
     const int64_t nc = (r1 - r0 + 3) / 4;
     if (nc + 1 > ctx->cl_nc_cap) {
       if (ctx->cl_cnt) LJ_CUDA(ctx, cudaFreeAsync(ctx->cl_cnt, st));
@@ -721,7 +723,7 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
       LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_ptr, sizeof(long long) * (nc + 1), ctx->pool, st));
       ctx->cl_nc_cap = nc + 1;
     }
-    const bool emit = !a->half;
+    const bool emit = !a->half && (a->flags & LJ_LIST_CLUSTERS);
     LJ_CUDA(ctx, cudaMemsetAsync(ctx->cl_cnt + nc, 0, sizeof(uint32_t), st));
     const unsigned cblocks = (unsigned)blocks_for(nc * kSearchLanes, 256);
     k_search_cluster<false, false, LAYOUT><<<cblocks, 256, 0, st>>>(
@@ -752,14 +754,17 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
     }
     k_finish_totals<<<1, 1, 0, st>>>(ctx->totals, a->capacity, a->pointer64);
     LJ_LAUNCHED(ctx);
-    // one small read-back per build: sizes the library-owned cluster list and lets an
-    // over-capacity build skip the fill pass altogether
-    LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals),
-                                 cudaMemcpyDeviceToHost, st));
-    LJ_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->last_capacity = a->capacity;
-    if (ctx->totals_host->overflow) return LJ_OK;  // reported by lj_list_result
-    const int64_t need = (int64_t)ctx->totals_host->cl_total;
+    int64_t need = 0;
+    if (emit) {
+      // one small read-back per build: sizes the library-owned cluster list and lets an
+      // over-capacity build skip the fill pass altogether
+      LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals),
+                                   cudaMemcpyDeviceToHost, st));
+      LJ_CUDA(ctx, cudaStreamSynchronize(st));
+      if (ctx->totals_host->overflow) return LJ_OK;  // reported by lj_list_result
+      need = (int64_t)ctx->totals_host->cl_total;
+    }
     if (emit && need > ctx->cl_cap) {
       if (ctx->cl_list) LJ_CUDA(ctx, cudaFreeAsync(ctx->cl_list, st));
       ctx->cl_list = nullptr;

@@ -112,11 +112,12 @@ def test_init_fcc_bit_exact(oracle, golden):
 # ------------------------------------------------------------------------ neighbour list
 @pytest.mark.parametrize("which", ["A", "B"])
 @pytest.mark.parametrize("half", [False, True])
-@pytest.mark.parametrize("clusters", [False, True])
-def test_list_bit_exact(ctx, torch, sysA, sysB, golden, which, half, clusters):
+@pytest.mark.parametrize("engine", ["cluster-search", "cluster-search+mirror", "per-particle-search"])
+def test_list_bit_exact(ctx, torch, sysA, sysB, golden, which, half, engine):
     s = sysA if which == "A" else sysB
     qd, _ = s.device_arrays(torch, "aos4")
-    pl = ctx.makepair(qd, half=half, clusters=clusters)  # both search kernels emit the same CSR list
+    pl = ctx.makepair(qd, half=half, clusters=engine.endswith("mirror"),
+                      per_particle=engine.startswith("per"))  # every engine emits the same CSR list
     nop, ptr, lst = list_to_host(pl)
     nop_o, ptr_o, lst_o = s.half if half else s.full
     assert pl.number_of_pairs == len(lst_o)
@@ -236,7 +237,7 @@ FORCE_CASES = [("aos4", "subwarp", 8), ("aos4", "warp", 32), ("aos4", "thread", 
                ("aos3", "subwarp", 8), ("aos3", "warp", 32), ("aos3", "tile", 16),
                ("soa", "subwarp", 8), ("soa", "thread", 1), ("soa", "tile", 8),
                ("aos4", "cluster", 0), ("aos3", "cluster", 0), ("soa", "cluster", 0),
-               ("aos4", "cluster", 32), ("aos3", "cluster", 32)]
+               ("aos4", "cluster", 32), ("aos3", "cluster", 32), ("aos4", "cluster", 16), ("soa", "cluster", 16)]
 
 
 @pytest.mark.parametrize("layout,variant,group", FORCE_CASES)

@@ -64,11 +64,12 @@ def main():
             ms_build = timeit(lambda: ctx.rebuild(qd, pl, layout=layout, pn=npn, sort_rows=sort_rows, clusters=True), 5)
             plain = ctx.makepair(qd, layout=layout, pn=npn, sort_rows=sort_rows)
             ms_plain = timeit(lambda: ctx.rebuild(qd, plain, layout=layout, pn=npn, sort_rows=sort_rows), 5)
+            ms_pp = timeit(lambda: ctx.rebuild(qd, plain, layout=layout, pn=npn, sort_rows=sort_rows, per_particle=True), 5)
             del plain
-            print("layout=%s sort_rows=%d N=%d P=%d max_np=%d  list build %.3f ms (+cluster list: %.3f ms)" % (
-                layout, sort_rows, pn, P, pl.max_partners, ms_plain, ms_build), flush=True)
+            print("layout=%s sort_rows=%d N=%d P=%d max_np=%d  list build %.3f ms (+cluster list: %.3f ms, "
+                  "per-particle search: %.3f ms)" % (layout, sort_rows, pn, P, pl.max_partners, ms_plain, ms_build, ms_pp), flush=True)
             results.append(dict(kind="build", layout=layout, sort_rows=sort_rows, ms=ms_build, pn=pn, pairs=P))
-            cases = [("cluster", 0, 0, "fp64"), ("cluster", 0, 256, "fp64"), ("cluster", 32, 0, "fp64")]
+            cases = [("cluster", 0, 0, "fp64"), ("cluster", 0, 256, "fp64"), ("cluster", 32, 0, "fp64"), ("cluster", 16, 0, "fp64")]
             for g in (1, 2, 4, 8, 16, 32):
                 for tb in ((128, 256) if layout == "aos4" and not sort_rows else (128,)):
                     cases.append(("subwarp", g, tb, "fp64"))
