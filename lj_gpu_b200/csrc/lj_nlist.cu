@@ -392,6 +392,10 @@ k_search_cluster(const void* __restrict__ q, int64_t plane, int64_t pn, const gr
   const float margin = ge->margin, sl2f = ge->sl2f, edge = ge->edge, inv_edge = ge->inv_edge,
               pad = ge->pad;
   const float lo_f = sl2f - margin, hi_f = sl2f + margin;
+  // sure-hit band margin < r2 < lo_f as |r2 - mid_s| < hw_s, shrunk so that the rounding of the
+  // subtraction cannot admit a value outside the band
+  const float mid_s = 0.5f * (lo_f + margin);
+  const float hw_s = 0.5f * (lo_f - margin) * (1.0f - 4.0e-6f);
   const float search_f = sqrtf(hi_f) + pad;
 
   // member positions, origin-shifted floats (same expression as k_cell_order: bit-identical)
@@ -459,54 +463,60 @@ k_search_cluster(const void* __restrict__ q, int64_t plane, int64_t pn, const gr
       if (++y > cy1) { y = cy0; z++; }
     }
     while (__any_sync(0xffffffffu, m < m_end)) {
-      unsigned bits = 0, exact = 0;
-      int j = 0;
-      const bool inb = m < m_end;
-      float4 c32 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (inb) c32 = sorted_pos32[m];
-      j = __float_as_int(c32.w);
-      // straight-line classification of the candidate against the four members
+      // lanes past the end of the range test a far-away dummy: no hit, no exact path
+      float4 c32 = make_float4(3.0e18f, 0.f, 0.f, 0.f);
+      if (m < m_end) c32 = sorted_pos32[m];
+      const int j = __float_as_int(c32.w);
+      // straight-line classification against the four members: two band tests per member
+      //   sure hit  <=> margin < r2 < lo_f   (|r2 - mid_s| < hw_s)
+      //   exact     <=> r2 < hi_f and not a sure hit (near the threshold, or near zero)
+      bool hit[4];
+      bool ex = false;
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const float dx = px[r] - c32.x, dy = py[r] - c32.y, dz = pz[r] - c32.z;
         const float r2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        const bool sure = r2f < lo_f && r2f > margin;
-        bits |= (sure ? 1u : 0u) << r;
-        exact |= ((r2f < hi_f && !sure) ? 1u : 0u) << r;
+        hit[r] = fabsf(r2f - mid_s) < hw_s;
+        ex = ex || (r2f < hi_f && !hit[r]);
       }
-      if (!inb) { bits = 0; exact = 0; }
-      if (exact) {  // rare: within the FP32 error of the threshold, or of zero (self / coincident)
+      if (ex) {  // rare
         const double4 cj = sorted_pos[m];
-#pragma unroll 1
-        for (int r = 0; r < 4; r++)
-          if ((exact >> r) & 1u) {
+#pragma unroll  // fully unrolled: no dynamic indexing of the register arrays
+        for (int r = 0; r < 4; r++) {
+          const float dx = px[r] - c32.x, dy = py[r] - c32.y, dz = pz[r] - c32.z;
+          const float r2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          if (r2f < hi_f && !(fabsf(r2f - mid_s) < hw_s)) {
             double xi, yi, zi;
             load_pos<LAYOUT>(q, i0 + r, plane, xi, yi, zi);
             const double ddx = xi - cj.x, ddy = yi - cj.y, ddz = zi - cj.z;
-            if ((j != (int)(i0 + r)) && (fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2)) bits |= 1u << r;
+            hit[r] = (j != (int)(i0 + r)) && (fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2);
           }
+        }
       }
       if (half) {
 #pragma unroll
-        for (int r = 0; r < 4; r++)
-          if (j <= (int)(i0 + r)) bits &= ~(1u << r);
+        for (int r = 0; r < 4; r++) hit[r] = hit[r] && j > (int)(i0 + r);
       }
+      const bool any = hit[0] || hit[1] || hit[2] || hit[3];
       if (FILL) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-          const unsigned b = __ballot_sync(0xffffffffu, (bits >> r) & 1u) & gbits;
-          if ((bits >> r) & 1u) list[base[r] + cnt[r] + __popc(b & lt_mask)] = j;
+          const unsigned b = __ballot_sync(0xffffffffu, hit[r]) & gbits;
+          if (hit[r]) list[base[r] + cnt[r] + __popc(b & lt_mask)] = j;
           cnt[r] += __popc(b);
         }
         if (emit_cl) {
-          const unsigned bu = __ballot_sync(0xffffffffu, bits != 0u) & gbits;
-          if (bits != 0u) cl_list[cbase + ucnt + __popc(bu & lt_mask)] = (bits << 28) | (unsigned)j;
+          const unsigned bu = __ballot_sync(0xffffffffu, any) & gbits;
+          if (any) {
+            const unsigned bits = (hit[0] ? 1u : 0u) | (hit[1] ? 2u : 0u) | (hit[2] ? 4u : 0u) | (hit[3] ? 8u : 0u);
+            cl_list[cbase + ucnt + __popc(bu & lt_mask)] = (bits << 28) | (unsigned)j;
+          }
           ucnt += __popc(bu);
         }
       } else {  // counting needs no ordering: per-lane tallies, reduced once at the end
 #pragma unroll
-        for (int r = 0; r < 4; r++) cnt[r] += (bits >> r) & 1u;
-        ucnt += bits != 0u;
+        for (int r = 0; r < 4; r++) cnt[r] += hit[r] ? 1 : 0;
+        ucnt += any ? 1 : 0;
       }
       m += GL;
     }

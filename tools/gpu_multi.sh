@@ -3,7 +3,18 @@
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 echo "GPUs: $N"
-timeout -s KILL 900 python -m pytest tests/test_gpu_decomp.py -x -q > gpurun_out/pytest_decomp.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_decomp.log
-for mode in nccl p2p; do
-  LJ_HALO=$mode timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 100 --warmup 20 > gpurun_out/bench_n${N}_$mode.json 2> gpurun_out/bench_n${N}_$mode.err; echo "bench $mode rc=$?"; cat gpurun_out/bench_n${N}_$mode.json; tail -3 gpurun_out/bench_n${N}_$mode.err
+timeout -s KILL 900 python -m pytest tests/test_gpu_decomp.py -x -q > gpurun_out/pytest_decomp.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_decomp.log
+timeout -s KILL 300 python bench.py --impl reference --steps 40 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json | cut -c1-400
+for n in 1 2 4 8; do
+  if [ $n -le $N ]; then
+    if [ $n -eq 1 ]; then CMD="python bench.py"; else CMD="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py"; fi
+    timeout -s KILL 600 $CMD --gpus $n --steps 100 --warmup 20 --no-cpu > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; echo "bench n=$n rc=$?"; python - <<PY
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/scale_n$n.json") if l.startswith("{")][-1])
+    print("n=%d value=%.4g ms/step=%.4f launches=%s halo=%s"%(d["n_gpus"],d["value"],d["ms_per_step"],d["gpu_launches"],d.get("halo")))
+except Exception as e:
+    print("parse failed",e); print(open("gpurun_out/scale_n$n.err").read()[-1500:])
+PY
+  fi
 done
