@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Hot instructions (stall samples) of the first kernel in an ncu --set full report.
+  python tools/ncu_hot.py report.ncu-rep"""
 import csv, subprocess, io, sys
 rep=sys.argv[1]
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
@@ -5,7 +8,10 @@ lines = txt.splitlines()
 st=[i for i,l in enumerate(lines) if l.startswith('"Address"')][0]
 rows=list(csv.reader(io.StringIO("\n".join(lines[st:]))))
 hdr=rows[0]; idx={k:i for i,k in enumerate(hdr)}
-data=[r for r in rows[1:] if len(r)==len(hdr)]
+data=[]
+for r in rows[1:]:
+    if r and r[0]=="Address": break  # next kernel of the report
+    if len(r)==len(hdr): data.append(r)
 tot=sum(int(r[idx["# Samples"]]) for r in data)
 base=int(data[0][0],16)
 stall_cols=[k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
