@@ -18,6 +18,9 @@
 namespace {
 
 constexpr int kUnroll = 4;
+#ifndef LJ_LIST_PREFETCH_TRIPS
+#define LJ_LIST_PREFETCH_TRIPS 0
+#endif
 
 // --------------------------------------------------------------------------------------
 // Gather on a CSR list, G lanes per row.  G=32 is the reference's warp_unroll mapping
@@ -63,6 +66,12 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
 #pragma unroll
       for (int u = 0; u < kUnroll; u++) jn[u] = __ldg(row + k + kUnroll * G + u * G);
     }
+#if LJ_LIST_PREFETCH_TRIPS > 0
+    // pull the list line that is LJ_LIST_PREFETCH_TRIPS trips ahead towards L2/L1 (no register,
+    // no fault); one lane per group issues it
+    if (lg == 0 && k + LJ_LIST_PREFETCH_TRIPS * kUnroll * G < np)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row + k + LJ_LIST_PREFETCH_TRIPS * kUnroll * G));
+#endif
     if (MODE == 2) {
 #pragma unroll
       for (int u = 0; u < kUnroll; u++) j[u] &= 1023;

@@ -262,6 +262,8 @@ def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_p
     # cubic lattice with ~1.0e6 * world particles and a layer count divisible by world
     n = int(round((250047.0 * world) ** (1.0 / 3.0)))
     n = max(world, (n + world - 1) // world * world)
+    if os.environ.get("LJ_BENCH_CELLS"):  # e.g. 320 at rho=0.8: BASELINE config 5 (N=131,072,000)
+        n = int(os.environ["LJ_BENCH_CELLS"])
     L = (n + 0.05) * s
     halo_mode = os.environ.get("LJ_HALO", "p2p")
     system = DecomposedSystem(density, L, halo_mode=halo_mode)
