@@ -231,6 +231,25 @@ LJ_API int lj_validate_list(lj_ctx* ctx, const int32_t* sorted_list, const int32
  * writes packed xyz doubles.  Returns the particle count, or -(needed) if cap is too small. */
 LJ_API int64_t lj_init_fcc(double density, double L, double* q_xyz_host, int64_t cap_particles,
                     int32_t* cells_per_side_out);
+/* Pair-list cache files of the reference, for exchanging lists with its binaries (host only).
+ * Text `.cache_pair_{all,half}.dat`: makepaircache()/loadpair() of cuda/force_cuda.cu:165-227
+ * (the reader applies check_loadedpair()'s range checks and the header pn check, :183-213).
+ * Arrays may be NULL to query pn/npairs only; pn_expected < 0 accepts any particle count. */
+LJ_API int lj_paircache_write_text(const char* path, int64_t pn, int64_t npairs,
+                                   const int32_t* number_of_partners, const int32_t* pointer,
+                                   const int32_t* sorted_list);
+LJ_API int lj_paircache_read_text(const char* path, int64_t pn_expected, int64_t* pn_out,
+                                  int64_t* npairs_out, int32_t* number_of_partners, int32_t* pointer,
+                                  int64_t cap_particles, int32_t* sorted_list, int64_t cap_pairs);
+/* Binary `pair.dat` of cpu_ref (savepair()/loadpair(), cpu_ref/force_soa.cpp:360-377):
+ * int npairs; int number_of_partners[N]; int i_particles[MAX_PAIRS]; int j_particles[MAX_PAIRS];
+ * n_static / max_pairs_static are the reference's compile-time N = 400000 and MAX_PAIRS = 30*N. */
+LJ_API int lj_pairdat_write(const char* path, int64_t n_static, int64_t max_pairs_static, int64_t pn,
+                            int64_t npairs, const int32_t* number_of_partners,
+                            const int32_t* i_particles, const int32_t* j_particles);
+LJ_API int lj_pairdat_read(const char* path, int64_t n_static, int64_t max_pairs_static, int64_t pn,
+                           int64_t* npairs_out, int32_t* number_of_partners, int32_t* i_particles,
+                           int32_t* j_particles, int64_t cap_pairs);
 /* same lattice generated on the device for sizes where a host loop is too slow is NOT
  * offered: the generator is sequential by definition (one RNG stream). */
 

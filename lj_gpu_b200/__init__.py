@@ -6,7 +6,9 @@ the thin ctypes mirror used by tests and bench.py.  No CPU fallback exists.
 """
 from . import _capi  # noqa: F401
 from .api import (CL2, CUTOFF_LENGTH, DENSITY, DT, LOOP, L_BOX, SEARCH_LENGTH, CudaPtr, LJContext,
-                  LJError, PairList, init_fcc, print_results)
+                  LJError, PairList, init_fcc, loadpair, loadpair_dat, makepaircache, print_results,
+                  savepair_dat)
 
-__all__ = ["LJContext", "LJError", "PairList", "CudaPtr", "init_fcc", "print_results", "DENSITY",
+__all__ = ["LJContext", "LJError", "PairList", "CudaPtr", "init_fcc", "print_results", "makepaircache",
+           "loadpair", "savepair_dat", "loadpair_dat", "DENSITY",
            "L_BOX", "DT", "CUTOFF_LENGTH", "SEARCH_LENGTH", "CL2", "LOOP"]

@@ -95,6 +95,10 @@ PROTOTYPES = {
     "lj_shuffle_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_uint32, _vp]),
     "lj_validate_list": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp]),
     "lj_init_fcc": (_i64, [_dbl, _dbl, _vp, _i64, C.POINTER(_i32)]),
+    "lj_paircache_write_text": (C.c_int, [C.c_char_p, _i64, _i64, _vp, _vp, _vp]),
+    "lj_paircache_read_text": (C.c_int, [C.c_char_p, _i64, C.POINTER(_i64), C.POINTER(_i64), _vp, _vp, _i64, _vp, _i64]),
+    "lj_pairdat_write": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "lj_pairdat_read": (C.c_int, [C.c_char_p, _i64, _i64, _i64, C.POINTER(_i64), _vp, _vp, _vp, _i64]),
     "lj_measure": (C.c_int, [_vp, C.POINTER(LjMeasureArgs)]),
     "lj_ipc_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "lj_ipc_free": (C.c_int, [_vp, _vp]),

@@ -58,6 +58,63 @@ def print_results(p_xyz: np.ndarray) -> str:
     return "".join("%.10f %.10f %.10f\n" % tuple(p_xyz[i, :3]) for i in rows)
 
 
+# ---------------------------------------------------------------------- pair-list cache files
+REF_N_STATIC = 400000           # cpu_ref/force_soa.cpp:11
+REF_MAX_PAIRS = 30 * REF_N_STATIC  # cpu_ref/force_soa.cpp:12
+
+
+def makepaircache(path: str, number_of_partners, pointer, sorted_list) -> None:
+    """makepaircache() (cuda/force_cuda.cu:165-176): the text cache `.cache_pair_{all,half}.dat`."""
+    nop, ptr, lst = (np.ascontiguousarray(x, np.int32) for x in (number_of_partners, pointer, sorted_list))
+    rc = capi.load().lj_paircache_write_text(path.encode(), len(nop), len(lst), nop.ctypes.data,
+                                             ptr.ctypes.data, lst.ctypes.data)
+    if rc:
+        raise LJError(rc, "lj_paircache_write_text(%s)" % path)
+
+
+def loadpair(path: str, particle_number: int = -1):
+    """loadpair() + check_loadedpair() (cuda/force_cuda.cu:183-227) -> (nop, pointer, sorted_list)."""
+    lib = capi.load()
+    pn, npairs = C.c_int64(0), C.c_int64(0)
+    rc = lib.lj_paircache_read_text(path.encode(), particle_number, C.byref(pn), C.byref(npairs), None, None,
+                                    0, None, 0)
+    if rc:
+        raise LJError(rc, "pair-list cache %s is missing or broken" % path)
+    nop, ptr = np.empty(pn.value, np.int32), np.empty(pn.value, np.int32)
+    lst = np.empty(npairs.value, np.int32)
+    rc = lib.lj_paircache_read_text(path.encode(), particle_number, C.byref(pn), C.byref(npairs),
+                                    nop.ctypes.data, ptr.ctypes.data, len(nop), lst.ctypes.data, len(lst))
+    if rc:
+        raise LJError(rc, "pair-list cache %s is broken" % path)
+    return nop, ptr, lst
+
+
+def savepair_dat(path: str, number_of_partners, i_particles, j_particles) -> None:
+    """cpu_ref's binary pair.dat (savepair(), cpu_ref/force_soa.cpp:369-377)."""
+    nop, ip, jp = (np.ascontiguousarray(x, np.int32) for x in (number_of_partners, i_particles, j_particles))
+    rc = capi.load().lj_pairdat_write(path.encode(), REF_N_STATIC, REF_MAX_PAIRS, len(nop), len(ip),
+                                      nop.ctypes.data, ip.ctypes.data, jp.ctypes.data)
+    if rc:
+        raise LJError(rc, "lj_pairdat_write(%s)" % path)
+
+
+def loadpair_dat(path: str, particle_number: int):
+    """cpu_ref's loadpair() (cpu_ref/force_soa.cpp:360-367) -> (nop, i_particles, j_particles)."""
+    lib = capi.load()
+    npairs = C.c_int64(0)
+    rc = lib.lj_pairdat_read(path.encode(), REF_N_STATIC, REF_MAX_PAIRS, particle_number, C.byref(npairs),
+                             None, None, None, 0)
+    if rc:
+        raise LJError(rc, "pair.dat %s is missing or broken" % path)
+    nop = np.empty(particle_number, np.int32)
+    ip, jp = np.empty(npairs.value, np.int32), np.empty(npairs.value, np.int32)
+    rc = lib.lj_pairdat_read(path.encode(), REF_N_STATIC, REF_MAX_PAIRS, particle_number, C.byref(npairs),
+                             nop.ctypes.data, ip.ctypes.data, jp.ctypes.data, len(ip))
+    if rc:
+        raise LJError(rc, "pair.dat %s is broken" % path)
+    return nop, ip, jp
+
+
 @dataclass
 class PairList:
     """The reference's three list arrays on the device (+ optional ELL table)."""

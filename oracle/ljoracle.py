@@ -220,6 +220,21 @@ class Ref:
         lst = np.ctypeslib.as_array(self.lib.ljref_sorted_list(), shape=(npairs,)).astype(np.int32)
         return nop, ptr, lst
 
+    def savepair(self):
+        """reference savepair(): makepair() + write ./pair.dat (cpu_ref/force_soa.cpp:369-377)."""
+        self.lib.ljref_savepair()
+
+    def loadpair(self):
+        """reference loadpair(): read ./pair.dat into its globals (cpu_ref/force_soa.cpp:360-367)."""
+        self.lib.ljref_loadpair()
+
+    def pair_arrays(self):
+        npairs = self.lib.ljref_number_of_pairs()
+        nop = np.ctypeslib.as_array(self.lib.ljref_number_of_partners(), shape=(self.pn,)).astype(np.int32)
+        ip = np.ctypeslib.as_array(self.lib.ljref_i_particles(), shape=(npairs,)).astype(np.int32)
+        jp = np.ctypeslib.as_array(self.lib.ljref_j_particles(), shape=(npairs,)).astype(np.int32)
+        return nop, ip, jp
+
     def force(self, kind: str = "sorted", steps: int = 100):
         self.lib.ljref_force({"pair": 0, "sorted": 1, "next": 2, "intrin": 3}[kind], steps)
 

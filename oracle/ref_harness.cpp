@@ -30,6 +30,8 @@ void force_pair(void);
 void force_sorted(void);
 void force_next(void);
 void force_intrin(void);
+void savepair(void);
+void loadpair(void);
 
 extern "C" {
 
@@ -44,6 +46,12 @@ void ljref_makepair(void) {
   makepair();
 }
 void ljref_sortpair(void) { sortpair(); }
+// the reference's own pair.dat writer / reader (cpu_ref/force_soa.cpp:360-377), in the CWD
+void ljref_savepair(void) {
+  number_of_pairs = 0;
+  savepair();
+}
+void ljref_loadpair(void) { loadpair(); }
 void ljref_zero_p(void) {
   for (int c = 0; c < 4; c++) std::fill(p[c], p[c] + 400000, 0.0);
 }
