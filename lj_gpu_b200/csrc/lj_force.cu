@@ -406,8 +406,9 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
   // cluster kernel trades L1 wavefronts for 1.5x FP64 work and measures slower.
   if (a->variant == LJ_VARIANT_CLUSTER) {
     LJ_REQUIRE(ctx, lj_cluster_usable(ctx, a, r0, r1),
-               "lj_force_step: no cluster pair list for these arrays (build with LJ_LIST_CLUSTERS; FP64, "
+               "lj_force_step: no cluster pair list for these arrays (build with LJ_LIST_CLUSTERS; "
                "CSR, row range on 4-row boundaries)");
+    if (a->precision == LJ_PREC_MIXED) return lj_force_mixed_launch(ctx, a, r0, r1, g, tb, st);
     return lj_force_cluster_launch(ctx, a, r0, r1, c24, c48, cl2_bits, st);
   }
   if (a->precision == LJ_PREC_MIXED) {

@@ -324,7 +324,7 @@ int launch_cluster(lj_ctx* ctx, const lj_force_args* a, int64_t c0, int64_t c1, 
 // true when the cluster mirror describes exactly the list arrays of this call and the requested
 // row range falls on cluster boundaries
 bool lj_cluster_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1) {
-  if (!ctx->cl_valid || a->list_layout != LJ_LIST_CSR || a->precision != LJ_PREC_FP64) return false;
+  if (!ctx->cl_valid || a->list_layout != LJ_LIST_CSR) return false;
   if (a->list != ctx->cl_id_list || a->number_of_partners != ctx->cl_id_nop ||
       a->pointer != ctx->cl_id_ptr || a->pn != ctx->cl_pn)
     return false;

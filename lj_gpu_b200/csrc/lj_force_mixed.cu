@@ -153,7 +153,90 @@ bool launch_mixed_g(int g, const lj_force_args* a, const int4* q32, const fix_pa
   return false;
 }
 
+// --------------------------------------------------------------------------------------
+// Mixed precision on the CLUSTER PAIR LIST: one warp per cluster of four rows, 32 consecutive
+// union entries per trip, each lane gathers its fixed-point q[j] once (LDG.128) and evaluates it
+// against the four members held in registers (12 ints + 12 FP32 accumulators: ~64 registers, so
+// unlike the FP64 register-blocked kernel the occupancy stays high).  The FP32 pipe has four
+// times the FP64 rate, so the 1.5x extra pair evaluations of the union are cheap here, while
+// the L1/LSU cost per real pair drops 2.6x.
+// --------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+lj_gather_cluster_mixed(const void* __restrict__ q, const int4* __restrict__ q32, void* __restrict__ p,
+                        int64_t row0, int64_t row_end, int64_t c_begin, int64_t c_end, int64_t plane,
+                        float c24, float c48, float cl2f, double cl2, const fix_params* __restrict__ fp,
+                        const uint32_t* __restrict__ cl_list, const long long* __restrict__ cl_ptr) {
+  const int64_t c = c_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (c >= c_end) return;
+  const int lane = threadIdx.x & 31;
+  const long long off = __ldg(cl_ptr + c);
+  const int U = (int)(__ldg(cl_ptr + c + 1) - off);
+  const uint32_t* __restrict__ src = cl_list + off;
+  const int64_t i0 = row0 + 4 * c;
+  const unsigned self = (unsigned)i0;
+  const float unit = fp->unit, margin = fp->margin;
+  const float unit2 = unit * unit;
+  const float lo_c = cl2f - margin, hi_c = cl2f + margin;
+  int mx[4], my[4], mz[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int4 m = __ldg(q32 + (i0 + r < row_end ? i0 + r : i0));
+    mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
+  }
+  float ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, az[4] = {0, 0, 0, 0};
+
+  auto eval = [&](uint32_t e, int4 pj) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const float dx = (float)(pj.x - mx[r]), dy = (float)(pj.y - my[r]), dz = (float)(pj.z - mz[r]);
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) * unit2;
+      const float x = rcp_f32(r2);
+      const float x3 = x * x * x;
+      const float t = fmaf(-c48, x3, c24);
+      const bool listed = (e >> (28 + r)) & 1u;
+      bool in = r2 <= lo_c;
+      if (listed && !in && r2 < hi_c) {  // too close to the cutoff for FP32 to call: decide in FP64
+        double xi, yi, zi, xj, yj, zj;
+        load_pos<LAYOUT>(q, i0 + r, plane, xi, yi, zi);
+        load_pos<LAYOUT>(q, e & 0x0fffffffu, plane, xj, yj, zj);
+        const double ex = xj - xi, ey = yj - yi, ez = zj - zi;
+        in = fma(ez, ez, fma(ey, ey, ex * ex)) <= cl2;
+      }
+      const float df = (listed && in) ? (x * x3) * (t * unit) : 0.f;
+      ax[r] = fmaf(df, dx, ax[r]);
+      ay[r] = fmaf(df, dy, ay[r]);
+      az[r] = fmaf(df, dz, az[r]);
+    }
+  };
+  auto fetch = [&](int k, uint32_t& e, int4& pj) {
+    e = k < U ? __ldg(src + k) : self;  // past the end: mask 0
+    pj = __ldg(q32 + (e & 0x0fffffffu));
+  };
+  uint32_t ea, eb = 0;
+  int4 pa, pb = make_int4(0, 0, 0, 0);
+  fetch(lane, ea, pa);
+  if (32 < U) fetch(32 + lane, eb, pb);
+  for (int k0 = 0; k0 < U; k0 += 64) {
+    eval(ea, pa);
+    if (k0 + 64 < U) fetch(k0 + 64 + lane, ea, pa);
+    if (k0 + 32 < U) {
+      eval(eb, pb);
+      if (k0 + 96 < U) fetch(k0 + 96 + lane, eb, pb);
+    }
+  }
+  // FP32 per-lane partial sums -> FP64 butterfly over the warp for the four members
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    double sx = (double)ax[r], sy = (double)ay[r], sz = (double)az[r];
+    sx = group_sum<32>(sx); sy = group_sum<32>(sy); sz = group_sum<32>(sz);
+    if (lane == r && i0 + r < row_end) add_mom<LAYOUT>(p, i0 + r, plane, sx, sy, sz);
+  }
+}
+
 }  // namespace
+
+bool lj_cluster_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1);
 
 int lj_force_mixed_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, int g, int tb,
                           cudaStream_t st) {
@@ -182,6 +265,24 @@ int lj_force_mixed_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64
     default: k_to_fixed<LJ_SOA_D><<<cb, 256, 0, st>>>(a->q, pn, a->plane_stride, fp, q32); break;
   }
   LJ_LAUNCHED(ctx);
+  if (a->variant == LJ_VARIANT_CLUSTER) {
+    const int64_t c0 = (r0 - ctx->cl_r0) / 4, c1 = (r1 - ctx->cl_r0 + 3) / 4;
+    const unsigned blocks = (unsigned)((c1 - c0 + 3) / 4);
+    const float c24 = (float)(24.0 * a->dt), c48 = (float)(48.0 * a->dt), cl2f = (float)a->cl2;
+    switch (a->layout) {
+      case LJ_AOS_D3:
+        lj_gather_cluster_mixed<LJ_AOS_D3><<<blocks, 128, 0, st>>>(a->q, q32, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2f, a->cl2, fp, ctx->cl_list, ctx->cl_ptr);
+        break;
+      case LJ_AOS_D4:
+        lj_gather_cluster_mixed<LJ_AOS_D4><<<blocks, 128, 0, st>>>(a->q, q32, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2f, a->cl2, fp, ctx->cl_list, ctx->cl_ptr);
+        break;
+      default:
+        lj_gather_cluster_mixed<LJ_SOA_D><<<blocks, 128, 0, st>>>(a->q, q32, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2f, a->cl2, fp, ctx->cl_list, ctx->cl_ptr);
+        break;
+    }
+    LJ_LAUNCHED(ctx);
+    return LJ_OK;
+  }
   bool ok = false;
   switch (a->layout) {
     case LJ_AOS_D3:

@@ -432,19 +432,38 @@ k_search_cluster(const void* __restrict__ q, int64_t plane, int64_t pn, const gr
       }
     }
   }
-  // rows/slabs of cells that can hold a neighbour of the cluster's bounding box
+  // A cluster whose members are far apart (particle order without spatial coherence) would make
+  // the bounding-box candidate set explode; such LOOSE clusters are searched one member per pass
+  // (the member's own position as the box, only its bit live).  Union entries may then repeat a j
+  // for different members, which the cluster force kernel does not mind.
+  const bool loose = active && (bx1 - bx0 > 2.f * edge || by1 - by0 > 2.f * edge || bz1 - bz0 > 2.f * edge);
+  const int npass = loose ? nrows : 1;
+  int pass = 0;
+  unsigned live = loose ? 1u : 0xfu;
+  // rows/slabs of cells that can hold a neighbour of the (cluster's or member's) bounding box
   int y = 0, z = 0, cy0 = 0, cy1 = -1, cz1 = -1;
-  if (active) {
+  auto begin_pass = [&]() {
+    if (loose) {
+      bx0 = bx1 = pass == 0 ? px[0] : pass == 1 ? px[1] : pass == 2 ? px[2] : px[3];
+      by0 = by1 = pass == 0 ? py[0] : pass == 1 ? py[1] : pass == 2 ? py[2] : py[3];
+      bz0 = bz1 = pass == 0 ? pz[0] : pass == 1 ? pz[1] : pass == 2 ? pz[2] : pz[3];
+    }
     cy0 = max((int)floorf((by0 - search_f) * inv_edge), 0);
     cy1 = min((int)floorf((by1 + search_f) * inv_edge), g.ny - 1);
     z = max((int)floorf((bz0 - search_f) * inv_edge), 0);
     cz1 = min((int)floorf((bz1 + search_f) * inv_edge), g.nz - 1);
     y = cy0;
-  }
+  };
+  if (active) begin_pass();
   int cnt[4] = {0, 0, 0, 0};
   int ucnt = 0;
 
-  while (__any_sync(0xffffffffu, active && z <= cz1)) {
+  while (__any_sync(0xffffffffu, active && (z <= cz1 || pass + 1 < npass))) {
+    if (active && z > cz1 && pass + 1 < npass) {  // next member of a loose cluster
+      pass++;
+      live = 1u << pass;
+      begin_pass();
+    }
     uint32_t m = 0, m_end = 0;
     if (active && z <= cz1) {
       const float gy = fmaxf(fmaxf(y * edge - by1, by0 - (y + 1) * edge) - pad, 0.f);
@@ -496,6 +515,10 @@ k_search_cluster(const void* __restrict__ q, int64_t plane, int64_t pn, const gr
       if (half) {
 #pragma unroll
         for (int r = 0; r < 4; r++) hit[r] = hit[r] && j > (int)(i0 + r);
+      }
+      if (live != 0xfu) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) hit[r] = hit[r] && ((live >> r) & 1u);
       }
       const bool any = hit[0] || hit[1] || hit[2] || hit[3];
       if (FILL) {

@@ -375,8 +375,7 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
     la.q = q; la.pn = pn; la.layout = m->layout; la.half = m->half; la.plane_stride = m->plane_stride;
     la.search_len = m->search_len; la.number_of_partners = nop; la.pointer = ptr; la.pointer64 = ptr64;
     la.flags = m->list_flags;
-    if (!m->half && m->precision == LJ_PREC_FP64 &&
-        m->variant == LJ_VARIANT_CLUSTER)
+    if (!m->half && m->variant == LJ_VARIANT_CLUSTER)
       la.flags |= LJ_LIST_CLUSTERS;
     if (own_list) {
       // first build sizes the list: count pass only needs capacity 0 to learn the total

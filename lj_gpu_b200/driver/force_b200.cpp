@@ -14,6 +14,9 @@
 // Extra flags (the reference has compile-time constants instead, SURVEY 5 "Config"):
 //   --density R  --L X  --layout aos3|aos4|soa  --variant auto|warp|thread|subwarp|tile|n3
 //   --group G  --prec fp64|mixed  --steps K  --rebuild-every M  --graph  --test  --all
+//   --cache   use / create the reference's text pair cache .cache_pair_{all,half}.dat in the CWD
+//             (loadpair()/makepaircache(), cuda/force_cuda.cu:165-227): a cached list is uploaded
+//             like the reference does, otherwise the list is built on the GPU and written out
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,7 +32,7 @@ struct Options {
   double density = 0.5, L = 50.0;
   std::string layout = "aos4", variant = "auto", prec = "fp64";
   int group = 0, steps = 100, rebuild_every = 0;
-  bool graph = false, test = false, all = false;
+  bool graph = false, test = false, all = false, cache = false;
 };
 
 [[noreturn]] void die(lj_ctx* ctx, int rc, const char* where) {
@@ -65,6 +68,32 @@ void print_results(const std::vector<double>& p, int64_t pn, int layout) {
   for (int64_t i = pn - 5; i < pn; i++) std::fprintf(stdout, "%.10f %.10f %.10f\n", at(i, 0), at(i, 1), at(i, 2));
 }
 
+// build the list once more on the GPU into caller-owned arrays and write the reference's cache
+void write_cache(lj_ctx* ctx, const char* file, const std::vector<double>& xyz, int64_t pn, int half) {
+  void *q = nullptr, *nop = nullptr, *ptr = nullptr, *list = nullptr;
+  lj_list_args l{};
+  int rc = lj_dev_alloc(ctx, (size_t)pn * 24, &q, nullptr);
+  if (!rc) rc = lj_dev_alloc(ctx, (size_t)pn * 4, &nop, nullptr);
+  if (!rc) rc = lj_dev_alloc(ctx, (size_t)pn * 4, &ptr, nullptr);
+  if (!rc) rc = lj_upload(ctx, q, xyz.data(), (size_t)pn * 24, nullptr);
+  l.q = q; l.pn = pn; l.layout = LJ_AOS_D3; l.half = half; l.search_len = 3.3;
+  l.number_of_partners = (int32_t*)nop; l.pointer = ptr; l.flags = LJ_LIST_SORT_ROWS;
+  int64_t npairs = 0;
+  if (!rc) { rc = lj_build_list(ctx, &l, &npairs, nullptr); if (rc == LJ_ERR_CAPACITY) rc = LJ_OK; }
+  if (!rc) rc = lj_dev_alloc(ctx, (size_t)(npairs ? npairs : 1) * 4, &list, nullptr);
+  l.sorted_list = (int32_t*)list; l.capacity = npairs;
+  if (!rc) rc = lj_build_list(ctx, &l, &npairs, nullptr);
+  std::vector<int32_t> h_nop(pn), h_ptr(pn), h_list(npairs ? npairs : 1);
+  if (!rc) rc = lj_download(ctx, h_nop.data(), nop, (size_t)pn * 4, nullptr);
+  if (!rc) rc = lj_download(ctx, h_ptr.data(), ptr, (size_t)pn * 4, nullptr);
+  if (!rc) rc = lj_download(ctx, h_list.data(), list, (size_t)npairs * 4, nullptr);
+  if (!rc) rc = lj_sync(ctx, nullptr);
+  if (!rc) rc = lj_paircache_write_text(file, pn, npairs, h_nop.data(), h_ptr.data(), h_list.data());
+  lj_dev_free(ctx, q, nullptr); lj_dev_free(ctx, nop, nullptr); lj_dev_free(ctx, ptr, nullptr);
+  lj_dev_free(ctx, list, nullptr);
+  if (rc) die(ctx, rc, "write_cache");
+}
+
 void measure(lj_ctx* ctx, const Options& o, const std::vector<double>& xyz, int64_t pn,
              const std::string& layout, const std::string& variant, int group, const char* name,
              bool print) {
@@ -82,8 +111,28 @@ void measure(lj_ctx* ctx, const Options& o, const std::vector<double>& xyz, int6
   m.group = group ? group : (variant == "warp" ? 32 : variant == "thread" ? 1 : 0);
   m.precision = o.prec == "mixed" ? LJ_PREC_MIXED : LJ_PREC_FP64;
   m.threads_per_block = o.thread_block; m.use_graph = o.graph;
+  // pair cache of the reference driver: same file names, same text format
+  const char* cache_file = m.half ? ".cache_pair_half.dat" : ".cache_pair_all.dat";
+  std::vector<int32_t> c_nop, c_ptr, c_list;
+  if (o.cache) {
+    int64_t cpn = 0, cnp = 0;
+    if (lj_paircache_read_text(cache_file, pn, &cpn, &cnp, nullptr, nullptr, 0, nullptr, 0) == LJ_OK) {
+      c_nop.resize(cpn); c_ptr.resize(cpn); c_list.resize(cnp ? cnp : 1);
+      if (lj_paircache_read_text(cache_file, pn, &cpn, &cnp, c_nop.data(), c_ptr.data(), cpn, c_list.data(),
+                                 cnp) == LJ_OK) {
+        std::fprintf(stderr, "%s is successfully loaded.\n", cache_file);
+        m.list_host = c_list.data(); m.number_of_partners_host = c_nop.data(); m.pointer_host = c_ptr.data();
+        m.number_of_pairs_in = cnp;
+      } else {
+        std::fprintf(stderr, "Pairlist cache data may be broken.\n");
+      }
+    } else {
+      std::fprintf(stderr, "Now make pairlist %s.\n", cache_file);
+    }
+  }
   const int rc = lj_measure(ctx, &m);
   if (rc) die(ctx, rc, "lj_measure");
+  if (o.cache && !m.list_host) write_cache(ctx, cache_file, xyz, pn, m.half);
   std::fprintf(stderr, "N=%d, %s %f [sec]\n", (int)pn, name, m.seconds_total);
   std::fprintf(stderr, "N=%d, %s %f [sec] (without Host<->Device)\n", (int)pn, name, m.seconds_kernel);
   std::fprintf(stderr, "  pairs=%lld max_partners=%d list_builds=%d  %.4g pair-interactions/s\n",
@@ -113,6 +162,7 @@ int main(int argc, char** argv) {
     else if (s == "--graph") o.graph = true;
     else if (s == "--test") o.test = true;
     else if (s == "--all") o.all = true;
+    else if (s == "--cache") o.cache = true;
     else if (s[0] != '-') o.thread_block = std::atoi(s.c_str());
     else { std::fprintf(stderr, "unknown option %s\n", s.c_str()); return 1; }
   }

@@ -216,6 +216,35 @@ def test_list_edge_sizes(ctx, torch, oracle):
     assert np.array_equal(nop, nop_o) and np.array_equal(lo.sort_rows(nop, ptr, lst), lst_o)
 
 
+def test_particle_order_without_spatial_coherence(ctx, torch, sysA, oracle):
+    """The reference's commented-out std::shuffle(q) idea (cuda/force_cuda.cu:92-93): same lattice,
+    particle order permuted.  Clusters of 4 consecutive particles are then spatially loose; list and
+    forces must stay exact (and the build must not degenerate into an all-pairs scan)."""
+    import time
+    s = sysA
+    perm = np.random.RandomState(123).permutation(s.pn)
+    q = np.ascontiguousarray(s.q[perm])
+    q4 = np.zeros((s.pn, 4)); q4[:, :3] = q
+    qd = torch.from_numpy(q4).cuda()
+    nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
+    for kw in (dict(), dict(clusters=True), dict(per_particle=True)):
+        torch.cuda.synchronize(); t0 = time.time()
+        pl = ctx.makepair(qd, **kw)
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 5.0
+        nop, ptr, lst = list_to_host(pl)
+        assert np.array_equal(nop, nop_o) and np.array_equal(s.lo.sort_rows(nop, ptr, lst), lst_o)
+    p_o = np.zeros_like(q)
+    oracle.force_gather(q, p_o, nop_o, ptr_o, lst_o, steps=5)
+    pl = ctx.makepair(qd, clusters=True)
+    for variant, group in (("subwarp", 8), ("cluster", 0), ("cluster", 32), ("tile", 8)):
+        pd = torch.zeros_like(qd)
+        ctx.force_loop(qd, pd, pl, loop=5, variant=variant, group=group)
+        assert np.abs(pd.cpu().numpy()[:, :3] - p_o).max() / np.abs(p_o).max() < TOL_FP64, variant
+    # momenta are a permutation of the lattice-order result
+    assert np.abs(p_o - s.p[perm] * (5 / s.steps)).max() / s.scale < 1e-13
+
+
 def test_row_range_build_for_ghosts(ctx, torch, sysS):
     # rows only for "owned" particles [r0,r1); all particles remain candidates
     s = sysS
@@ -341,13 +370,16 @@ def test_force_newton3_half_list(ctx, torch, sysA, layout, group):
 
 
 @pytest.mark.parametrize("which", ["A", "B"])
-@pytest.mark.parametrize("layout,group", [("aos4", 8), ("aos4", 32), ("aos3", 4), ("soa", 8)])
+@pytest.mark.parametrize("layout,group", [("aos4", 8), ("aos4", 32), ("aos3", 4), ("soa", 8), ("aos4", -1),
+                                          ("soa", -1)])
 def test_force_mixed(ctx, torch, sysA, sysB, which, layout, group):
     s = sysA if which == "A" else sysB
     qd, pd = s.device_arrays(torch, layout)
     pn = s.pn if layout == "soa" else None
-    pl = ctx.makepair(qd, layout=layout, pn=pn)
-    ctx.force_loop(qd, pd, pl, loop=100, layout=layout, group=group, precision="mixed", pn=pn)
+    cluster = group < 0   # group -1: the cluster-list mixed kernel
+    pl = ctx.makepair(qd, layout=layout, pn=pn, clusters=cluster)
+    ctx.force_loop(qd, pd, pl, loop=100, layout=layout, group=max(group, 0), precision="mixed", pn=pn,
+                   variant="cluster" if cluster else "auto")
     e = s.err(pd, layout)
     assert e < TOL_MIXED, e
     assert e > 1e-14  # it really is the FP32 path
@@ -546,6 +578,26 @@ def test_cpp_driver_prints_the_goldens():
     assert r.returncode == 1 and "THREAD_BLOCK size is too large or small." in r.stderr
 
 
+def test_cpp_driver_pair_cache(tmp_path, oracle):
+    """--cache: first run builds on the GPU and writes the reference's text cache, second run loads
+    it (the reference's own flow: host list uploaded) and prints the same goldens."""
+    from lj_gpu_b200 import loadpair
+    exe = os.path.join(ROOT, "lj_gpu_b200", "driver", "force_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    gold = open(os.path.join(GOLDEN, "density0.5.dat")).read()
+    r1 = subprocess.run([exe, "--test", "--cache"], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert r1.returncode == 0, r1.stderr
+    assert r1.stdout == gold and "Now make pairlist .cache_pair_all.dat." in r1.stderr
+    nop, ptr, lst = loadpair(str(tmp_path / ".cache_pair_all.dat"), 62500)
+    q = oracle.init_fcc(0.5, 50.0)
+    nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
+    assert np.array_equal(nop, nop_o) and np.array_equal(ptr, ptr_o) and np.array_equal(lst, lst_o)
+    r2 = subprocess.run([exe, "--test", "--cache"], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert r2.returncode == 0, r2.stderr
+    assert r2.stdout == gold and ".cache_pair_all.dat is successfully loaded." in r2.stderr
+
+
 # ------------------------------------------------------------------------ full size (config C)
 def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
     """BASELINE config 3: FCC rho=1.0, 63 cells/side -> N=1,000,188.  Full oracle comparison
@@ -585,6 +637,7 @@ def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
     pn3 = torch.zeros_like(qd)
     ctx.force_loop(qd, pn3, half, loop=3, variant="n3", group=8)
     assert np.abs(pn3.cpu().numpy()[:, :3] - p_o).max() / scale < TOL_FP64
-    pmx = torch.zeros_like(qd)
-    ctx.force_loop(qd, pmx, full, loop=3, group=8, precision="mixed")
-    assert np.abs(pmx.cpu().numpy()[:, :3] - p_o).max() / scale < TOL_MIXED
+    for variant in ("subwarp", "cluster"):
+        pmx = torch.zeros_like(qd)
+        ctx.force_loop(qd, pmx, full, loop=3, group=8, precision="mixed", variant=variant)
+        assert np.abs(pmx.cpu().numpy()[:, :3] - p_o).max() / scale < TOL_MIXED

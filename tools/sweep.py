@@ -79,6 +79,7 @@ def main():
                 cases.append(("subwarp", g, 128, "fp64-int4-list"))
             for g in (4, 8, 16, 32):
                 cases.append(("subwarp", g, 128, "mixed"))
+            cases.append(("cluster", 0, 0, "mixed"))
             for variant, g, tb, prec in cases:
                 kw = dict(layout=layout, pn=npn, variant=variant, group=g, threads_per_block=tb,
                           precision=prec.split("-")[0], list_scalar=2 if prec.endswith("int4-list") else 0)
