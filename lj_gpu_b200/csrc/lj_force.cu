@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(1024)
 lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begin, int64_t row_end,
               int64_t plane, double c24, double c48, long long cl2_bits,
               const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
-              const void* __restrict__ pointer) {
+              const void* __restrict__ pointer, cudaTextureObject_t ltex = 0) {
   const int rows_per_block = blockDim.x / G;
   const int64_t i = row_begin + (int64_t)blockIdx.x * rows_per_block + threadIdx.x / G;
   const int lg = threadIdx.x % G;
@@ -44,7 +44,10 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
   double xi, yi, zi;
   load_pos<LAYOUT>(q, i, plane, xi, yi, zi);
   const int np = __ldg(nop + i);
-  const int32_t* __restrict__ row = list + row_offset<PTR64>(pointer, i);
+  const int64_t roff = row_offset<PTR64>(pointer, i);
+  const int32_t* __restrict__ row = list + roff;
+  // MODE 5 (experiment): list words through the TEX pipe instead of the LSU pipe
+  auto ldl = [&](int kk) -> int { return MODE == 5 ? tex1Dfetch<int>(ltex, (int)(roff + kk)) : __ldg(row + kk); };
 
   double fx = 0.0, fy = 0.0, fz = 0.0;
   int k = lg;
@@ -56,7 +59,7 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
   const bool any_full = k + (kUnroll - 1) * G < np;
   if (any_full) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) jn[u] = __ldg(row + k + u * G);
+    for (int u = 0; u < kUnroll; u++) jn[u] = ldl(k + u * G);
   }
   for (; k + (kUnroll - 1) * G < np; k += kUnroll * G) {
     int j[kUnroll];
@@ -64,7 +67,7 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
     for (int u = 0; u < kUnroll; u++) j[u] = jn[u];
     if (k + kUnroll * G + (kUnroll - 1) * G < np) {
 #pragma unroll
-      for (int u = 0; u < kUnroll; u++) jn[u] = __ldg(row + k + kUnroll * G + u * G);
+      for (int u = 0; u < kUnroll; u++) jn[u] = ldl(k + kUnroll * G + u * G);
     }
 #if LJ_LIST_PREFETCH_TRIPS > 0
     // pull the list line that is LJ_LIST_PREFETCH_TRIPS trips ahead towards L2/L1 (no register,
@@ -87,7 +90,15 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
     }
     double xj[kUnroll], yj[kUnroll], zj[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) load_pos<LAYOUT>(q, j[u], plane, xj[u], yj[u], zj[u]);
+    for (int u = 0; u < kUnroll; u++) {
+      if (MODE == 6) {  // experiment: positions through the TEX pipe (two 16-byte fetches)
+        const int4 a4 = tex1Dfetch<int4>(ltex, 2 * j[u]), b4 = tex1Dfetch<int4>(ltex, 2 * j[u] + 1);
+        xj[u] = __hiloint2double(a4.y, a4.x); yj[u] = __hiloint2double(a4.w, a4.z);
+        zj[u] = __hiloint2double(b4.y, b4.x);
+      } else {
+        load_pos<LAYOUT>(q, j[u], plane, xj[u], yj[u], zj[u]);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < kUnroll; u++) {
       if (MODE == 1 || MODE == 4) { fx += xj[u]; fy += yj[u]; fz += zj[u]; }
@@ -95,7 +106,7 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
     }
   }
   for (; k < np; k += G) {
-    int j = __ldg(row + k);
+    int j = ldl(k);
     if (MODE == 2) j &= 1023;
     double xj, yj, zj;
     load_pos<LAYOUT>(q, j, plane, xj, yj, zj);
@@ -302,6 +313,44 @@ void launch_csr(const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c
     lj_gather_csr<G, LAYOUT, PTR64, 3><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                                c48, cl2_bits, a->list,
                                                                a->number_of_partners, a->pointer);
+  else if (a->variant == 104 && G == 8 && LAYOUT == LJ_AOS_D4 && a->list_entries > 0 && a->list_entries < (1LL << 27)) {
+    static cudaTextureObject_t tex = 0;
+    static const void* tex_ptr = nullptr;
+    if (tex_ptr != a->list) {
+      if (tex) cudaDestroyTextureObject(tex);
+      cudaResourceDesc rd{};
+      rd.resType = cudaResourceTypeLinear;
+      rd.res.linear.devPtr = const_cast<int32_t*>(a->list);
+      rd.res.linear.desc = cudaCreateChannelDesc<int>();
+      rd.res.linear.sizeInBytes = (size_t)a->list_entries * 4;
+      cudaTextureDesc td{};
+      td.readMode = cudaReadModeElementType;
+      cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+      tex_ptr = a->list;
+    }
+    lj_gather_csr<G, LAYOUT, PTR64, 5><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
+                                                               c48, cl2_bits, a->list,
+                                                               a->number_of_partners, a->pointer, tex);
+  }
+  else if (a->variant == 105 && G == 8 && LAYOUT == LJ_AOS_D4 && a->pn < (1LL << 26)) {
+    static cudaTextureObject_t qtex = 0;
+    static const void* qtex_ptr = nullptr;
+    if (qtex_ptr != a->q) {
+      if (qtex) cudaDestroyTextureObject(qtex);
+      cudaResourceDesc rd{};
+      rd.resType = cudaResourceTypeLinear;
+      rd.res.linear.devPtr = const_cast<void*>(a->q);
+      rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+      rd.res.linear.sizeInBytes = (size_t)a->pn * 32;
+      cudaTextureDesc td{};
+      td.readMode = cudaReadModeElementType;
+      cudaCreateTextureObject(&qtex, &rd, &td, nullptr);
+      qtex_ptr = a->q;
+    }
+    lj_gather_csr<G, LAYOUT, PTR64, 6><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
+                                                               c48, cl2_bits, a->list,
+                                                               a->number_of_partners, a->pointer, qtex);
+  }
   else if (a->variant == 103 && G == 8 && LAYOUT == LJ_AOS_D4)
     lj_gather_csr<G, LAYOUT, PTR64, 4><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                                c48, cl2_bits, a->list,
