@@ -287,6 +287,20 @@ typedef struct lj_measure_args {
 
 LJ_API int lj_measure(lj_ctx* ctx, lj_measure_args* args);
 
+/* ---------------------------------------------------------------- MD step helpers ----- */
+/* The caller the hot path is meant for (NOT in the reference, whose q is static): the
+ * force call is the kick p += F dt of a symplectic Euler step, these add the drift, the
+ * skin-based rebuild trigger and energies for conservation checks. */
+LJ_API int lj_drift(lj_ctx* ctx, void* q, const void* p, int64_t pn, int32_t layout,
+                    int64_t plane_stride, double dt, void* stream);           /* q += p dt */
+/* max_i |q_i - q_ref,i|^2 (synchronises); rebuild the list when it exceeds ((search-cutoff)/2)^2 */
+LJ_API int lj_max_displacement2(lj_ctx* ctx, const void* q, const void* q_ref, int64_t pn,
+                                int32_t layout, int64_t plane_stride, double* out_host, void* stream);
+/* kinetic = sum p^2/2, potential = sum over listed pairs with r2 <= cl2 of 4(r^-12 - r^-6)
+ * (halved for a full list; pass variant = LJ_VARIANT_NEWTON3 for a half list).  Synchronises. */
+LJ_API int lj_energy(lj_ctx* ctx, const lj_force_args* args, double* kinetic_out,
+                     double* potential_out, void* stream);
+
 /* ---------------------------------------------------------------- multi-GPU helpers --- */
 /* z-slab decomposition support (no reference counterpart: the reference is single-GPU).
  * Peer access by CUDA IPC: export a handle for a device allocation, open a peer's. */

@@ -100,6 +100,9 @@ PROTOTYPES = {
     "lj_pairdat_write": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "lj_pairdat_read": (C.c_int, [C.c_char_p, _i64, _i64, _i64, C.POINTER(_i64), _vp, _vp, _vp, _i64]),
     "lj_measure": (C.c_int, [_vp, C.POINTER(LjMeasureArgs)]),
+    "lj_drift": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _dbl, _vp]),
+    "lj_max_displacement2": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, C.POINTER(_dbl), _vp]),
+    "lj_energy": (C.c_int, [_vp, C.POINTER(LjForceArgs), C.POINTER(_dbl), C.POINTER(_dbl), _vp]),
     "lj_ipc_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "lj_ipc_free": (C.c_int, [_vp, _vp]),
     "lj_ipc_export": (C.c_int, [_vp, _vp, C.c_char_p]),

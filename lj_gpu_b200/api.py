@@ -342,6 +342,49 @@ class LJContext:
         self._check(self.lib.lj_force_loop(self.h, C.byref(a), loop, int(use_graph),
                                            self._stream(stream)))
 
+    # ------------------------------------------------------------------ MD step
+    def drift(self, q, p, dt: float = DT, layout=None, pn=None, stream=None):
+        """q += p*dt (unit mass): the drift of a symplectic Euler step whose kick is force_step."""
+        lay = self._layout_of(q, layout)
+        n, stride = self._pn_stride(q, lay)
+        self._check(self.lib.lj_drift(self.h, q.data_ptr(), p.data_ptr(), n if pn is None else pn, lay,
+                                      stride, dt, self._stream(stream)))
+
+    def max_displacement2(self, q, q_ref, layout=None, pn=None, stream=None) -> float:
+        lay = self._layout_of(q, layout)
+        n, stride = self._pn_stride(q, lay)
+        out = C.c_double(0.0)
+        self._check(self.lib.lj_max_displacement2(self.h, q.data_ptr(), q_ref.data_ptr(),
+                                                  n if pn is None else pn, lay, stride, C.byref(out),
+                                                  self._stream(stream)))
+        return out.value
+
+    def energy(self, q, p, pl: PairList, stream=None, **kw):
+        """-> (kinetic, potential) of the listed pairs within the cutoff."""
+        a = self.force_args(q, p, pl, **kw)
+        ke, pe = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.lib.lj_energy(self.h, C.byref(a), C.byref(ke), C.byref(pe), self._stream(stream)))
+        return ke.value, pe.value
+
+    def md_run(self, q, p, pl: PairList, steps: int, dt: float = DT, search_len: float = SEARCH_LENGTH,
+               cutoff: float = CUTOFF_LENGTH, check_every: int = 1, **fkw):
+        """`steps` symplectic-Euler steps (kick = force_step, drift) with a skin-triggered list
+        rebuild: the list is rebuilt when a particle has moved more than (search - cutoff)/2 since
+        the last build.  Returns the number of rebuilds."""
+        q_ref = q.clone()
+        limit2 = (0.5 * (search_len - cutoff)) ** 2
+        rebuilds = 0
+        for s in range(steps):
+            self.force_step(q, p, pl, dt=dt, cl2=cutoff * cutoff, **fkw)
+            self.drift(q, p, dt=dt, layout=fkw.get("layout"), pn=fkw.get("pn"))
+            if (s + 1) % check_every == 0 and \
+                    self.max_displacement2(q, q_ref, layout=fkw.get("layout"), pn=fkw.get("pn")) > limit2:
+                self.rebuild(q, pl, search_len=search_len, layout=fkw.get("layout"), pn=fkw.get("pn"))
+                pl.number_of_pairs, pl.max_partners = self.list_result()  # raises on capacity overflow
+                q_ref.copy_(q)
+                rebuilds += 1
+        return rebuilds
+
     # ------------------------------------------------------------------ measure()
     def measure(self, q_host: np.ndarray, p_host: np.ndarray, layout=None, loop: int = LOOP,
                 rebuild_every: int = 0, half: bool = False, variant="auto", group: int = 0,
