@@ -19,6 +19,8 @@
 // Robustness: nothing is assumed about pointer[].  Each row checks that its range lies inside
 // the staged segment and otherwise reads its indices from global memory, so arbitrary
 // (non-monotone, padded) CSR lists stay correct, only slower.
+#include <cstdlib>
+
 #include "lj_common.cuh"
 #include "lj_tile.cuh"
 
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_begin, int64_t row_end,
                int64_t plane, double c24, double c48, long long cl2_bits,
                const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
-               const void* __restrict__ pointer, int64_t list_entries) {
+               const void* __restrict__ pointer, int64_t list_entries, int contig) {
   constexpr int R = kTileRows;
   constexpr int RG = R * G / kConsumerThreads;  // rows per group and tile
   constexpr int B = RG >= 4 ? 4 : RG;           // rows reduced together
@@ -87,12 +89,18 @@ lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
 
   const int64_t rows = row_end - row_begin;
   const int64_t ntiles = (rows + R - 1) / R;
+  // tile schedule of this CTA: grid-strided, or one CONTIGUOUS range of tiles (consecutive tiles
+  // are spatial neighbours, so the q[j] working set slides through L1 instead of being refetched)
+  const int64_t per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t_first = contig ? blockIdx.x * per_cta : blockIdx.x;
+  const int64_t t_step = contig ? 1 : gridDim.x;
+  const int64_t t_last = contig ? (t_first + per_cta < ntiles ? t_first + per_cta : ntiles) : ntiles;
 
   if (warp == kConsumerWarps) {
     // ------------------------------ producer warp: one elected lane drives the TMA -------
     if (lane == 0) {
       int n = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, n++) {
+      for (int64_t t = t_first; t < t_last; t += t_step, n++) {
         const int b = n & 1;
         if (n >= 2) mbar_wait(&empty_bar[b], ((n >> 1) - 1) & 1);
         const int64_t first = row_begin + t * R;
@@ -123,7 +131,7 @@ lj_gather_tile(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
   const int group = threadIdx.x / G;  // 0 .. 256/G-1
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - lg));
   int n = 0;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, n++) {
+  for (int64_t t = t_first; t < t_last; t += t_step, n++) {
     const int b = n & 1;
     const int64_t gfirst = row_begin + t * R + (int64_t)group * RG;  // this group's first row
     // metadata of the group's first row, fetched before waiting for the list
@@ -202,7 +210,8 @@ int launch_tile(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, dou
   if (grid > ntiles) grid = ntiles;
   kern<<<(unsigned)grid, kTileThreads, smem, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24, c48,
                                                     cl2_bits, a->list, a->number_of_partners,
-                                                    a->pointer, a->list_entries);
+                                                    a->pointer, a->list_entries,
+                                                    getenv("LJ_TILE_CONTIG") ? 1 : 0);  // contiguous measured slower (0.50 vs 0.45 ms): load imbalance
   LJ_LAUNCHED(ctx);
   return LJ_OK;
 }
