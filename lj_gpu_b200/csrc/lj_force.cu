@@ -18,6 +18,9 @@
 namespace {
 
 constexpr int kUnroll = 4;
+#ifndef LJ_LIST_NO_ALLOCATE
+#define LJ_LIST_NO_ALLOCATE 0
+#endif
 #ifndef LJ_LIST_PREFETCH_TRIPS
 #define LJ_LIST_PREFETCH_TRIPS 0
 #endif
@@ -47,7 +50,16 @@ lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begi
   const int64_t roff = row_offset<PTR64>(pointer, i);
   const int32_t* __restrict__ row = list + roff;
   // MODE 5 (experiment): list words through the TEX pipe instead of the LSU pipe
-  auto ldl = [&](int kk) -> int { return MODE == 5 ? tex1Dfetch<int>(ltex, (int)(roff + kk)) : __ldg(row + kk); };
+  auto ldl = [&](int kk) -> int {
+    if (MODE == 5) return tex1Dfetch<int>(ltex, (int)(roff + kk));
+#if LJ_LIST_NO_ALLOCATE
+    int v;  // the list is used once: do not let it displace q lines from L1
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(row + kk));
+    return v;
+#else
+    return __ldg(row + kk);
+#endif
+  };
 
   double fx = 0.0, fy = 0.0, fz = 0.0;
   int k = lg;

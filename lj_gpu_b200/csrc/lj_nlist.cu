@@ -758,6 +758,7 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
       LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_cnt, sizeof(uint32_t) * (nc + 1), ctx->pool, st));
       LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_ptr, sizeof(long long) * (nc + 1), ctx->pool, st));
       ctx->cl_nc_cap = nc + 1;
+      ctx->graph_loop = -1;  // a cached CUDA graph may hold the old pointers: force a recapture
     }
     const bool emit = !a->half && (a->flags & LJ_LIST_CLUSTERS);
     LJ_CUDA(ctx, cudaMemsetAsync(ctx->cl_cnt + nc, 0, sizeof(uint32_t), st));
@@ -805,6 +806,7 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
       if (ctx->cl_list) LJ_CUDA(ctx, cudaFreeAsync(ctx->cl_list, st));
       ctx->cl_list = nullptr;
       ctx->cl_cap = need + need / 32 + 4096;
+      ctx->graph_loop = -1;  // see above
       LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_list, sizeof(uint32_t) * ctx->cl_cap, ctx->pool, st));
     }
     if (a->pointer64)
