@@ -48,7 +48,8 @@ typedef enum lj_layout {
   LJ_AOS_D4 = 1, /* {x,y,z,w} doubles, 32 B stride, 32 B aligned; .w ignored on read and
                     preserved on the write of p                                          */
   LJ_SOA_D = 2,  /* planes x[], y[], z[] of doubles: base + c*plane_stride + i            */
-  LJ_AOS_F4 = 3  /* {x,y,z,w} floats, 16 B stride (FP32 kernels only)                     */
+  LJ_AOS_F4 = 3  /* {x,y,z,w} floats, 16 B stride: list build, and force with LJ_PREC_MIXED
+                    (FP32 pair math, p accumulated in float, one rounding per step)      */
 } lj_layout;
 
 /* Neighbour-list storage.  CSR = sorted_list + number_of_partners + pointer (no sentinel,

@@ -26,7 +26,7 @@ SEARCH_LENGTH = 3.3
 CL2 = CUTOFF_LENGTH * CUTOFF_LENGTH
 LOOP = 100
 
-LAYOUTS = {"aos3": LJ_AOS_D3, "aos4": LJ_AOS_D4, "soa": LJ_SOA_D}
+LAYOUTS = {"aos3": LJ_AOS_D3, "aos4": LJ_AOS_D4, "soa": LJ_SOA_D, "f4": capi.LJ_AOS_F4}
 VARIANTS = {"auto": LJ_VARIANT_AUTO, "subwarp": LJ_VARIANT_SUBWARP, "warp": LJ_VARIANT_SUBWARP,
             "thread": LJ_VARIANT_SUBWARP, "tile": LJ_VARIANT_TILE_TMA, "n3": LJ_VARIANT_NEWTON3,
             "cluster": capi.LJ_VARIANT_CLUSTER}
@@ -185,7 +185,8 @@ class LJContext:
         if q.dim() == 2 and q.shape[1] == 3:
             return LJ_AOS_D3
         if q.dim() == 2 and q.shape[1] == 4:
-            return LJ_AOS_D4
+            import torch
+            return capi.LJ_AOS_F4 if q.dtype == torch.float32 else LJ_AOS_D4
         raise ValueError("cannot infer layout; pass layout='aos3'|'aos4'|'soa'")
 
     @staticmethod

@@ -172,6 +172,9 @@ __device__ __forceinline__ void load_pos(const void* __restrict__ q, int64_t i, 
   } else if (LAYOUT == LJ_AOS_D3) {
     const double* b = reinterpret_cast<const double*>(q) + 3 * i;
     x = __ldg(b); y = __ldg(b + 1); z = __ldg(b + 2);
+  } else if (LAYOUT == LJ_AOS_F4) {  // float4 positions (cuda/force_cuda.cu:25): widened exactly
+    const float4 v = __ldg(reinterpret_cast<const float4*>(q) + i);
+    x = (double)v.x; y = (double)v.y; z = (double)v.z;
   } else {
     const double* b = reinterpret_cast<const double*>(q) + i;
     x = __ldg(b); y = __ldg(b + plane); z = __ldg(b + 2 * plane);
@@ -191,6 +194,11 @@ __device__ __forceinline__ void add_mom(void* __restrict__ p, int64_t i, int64_t
   } else if (LAYOUT == LJ_AOS_D3) {
     double* b = reinterpret_cast<double*>(p) + 3 * i;
     b[0] += fx; b[1] += fy; b[2] += fz;
+  } else if (LAYOUT == LJ_AOS_F4) {  // float4 momenta: one rounding per step, .w kept
+    float4* b = reinterpret_cast<float4*>(p) + i;
+    float4 v = *b;
+    v.x = (float)((double)v.x + fx); v.y = (float)((double)v.y + fy); v.z = (float)((double)v.z + fz);
+    *b = v;
   } else {
     double* b = reinterpret_cast<double*>(p) + i;
     b[0] += fx; b[plane] += fy; b[2 * plane] += fz;

@@ -428,8 +428,12 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
              "lj_force_step: unknown list layout");
   LJ_REQUIRE(ctx, a->list_layout == LJ_LIST_ELL || a->pointer != nullptr,
              "lj_force_step: CSR list needs pointer[]");
-  LJ_REQUIRE(ctx, a->layout == LJ_AOS_D3 || a->layout == LJ_AOS_D4 || a->layout == LJ_SOA_D,
-             "lj_force_step: layout must be AOS_D3, AOS_D4 or SOA_D");
+  LJ_REQUIRE(ctx, a->layout == LJ_AOS_D3 || a->layout == LJ_AOS_D4 || a->layout == LJ_SOA_D ||
+                      (a->layout == LJ_AOS_F4 && a->precision == LJ_PREC_MIXED),
+             "lj_force_step: layout must be AOS_D3, AOS_D4, SOA_D, or AOS_F4 with LJ_PREC_MIXED");
+  if (a->layout == LJ_AOS_F4)
+    LJ_REQUIRE(ctx, ((uintptr_t)a->q % 16 == 0) && ((uintptr_t)a->p % 16 == 0),
+               "lj_force_step: float4 arrays must be 16-byte aligned");
   if (a->layout == LJ_AOS_D4)
     LJ_REQUIRE(ctx, ((uintptr_t)a->q % 32 == 0) && ((uintptr_t)a->p % 32 == 0),
                "lj_force_step: double4 arrays must be 32-byte aligned");

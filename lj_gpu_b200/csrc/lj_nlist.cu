@@ -688,6 +688,7 @@ int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t p
   switch (layout) {
     case LJ_AOS_D3: k_bbox<LJ_AOS_D3><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
     case LJ_AOS_D4: k_bbox<LJ_AOS_D4><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
+    case LJ_AOS_F4: k_bbox<LJ_AOS_F4><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
     default: k_bbox<LJ_SOA_D><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
   }
   LJ_LAUNCHED(ctx);
@@ -887,7 +888,11 @@ extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number
       rc = build_list_impl<LJ_AOS_D4>(ctx, a, st);
       break;
     case LJ_SOA_D: rc = build_list_impl<LJ_SOA_D>(ctx, a, st); break;
-    default: return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_build_list", "layout must be AOS_D3, AOS_D4 or SOA_D");
+    case LJ_AOS_F4:
+      LJ_REQUIRE(ctx, (uintptr_t)a->q % 16 == 0, "lj_build_list: float4 array must be 16-byte aligned");
+      rc = build_list_impl<LJ_AOS_F4>(ctx, a, st);
+      break;
+    default: return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_build_list", "unknown layout");
   }
   if (rc) return rc;
   if (a->flags & LJ_LIST_SORT_ROWS) {

@@ -385,6 +385,32 @@ def test_force_mixed(ctx, torch, sysA, sysB, which, layout, group):
     assert e > 1e-14  # it really is the FP32 path
 
 
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_float4_layout_mixed(ctx, torch, sysA, sysB, oracle, which):
+    """The reference's q_f4 / p_f4 buffers (cuda/force_cuda.cu:25, never timed there): float4 in,
+    float4 out, FP32 pair math.  Checker = the FP64 oracle on the SAME float-valued positions."""
+    s = sysA if which == "A" else sysB
+    qf = np.zeros((s.pn, 4), np.float32); qf[:, :3] = s.q.astype(np.float32); qf[:, 3] = 3.5
+    q64 = np.ascontiguousarray(qf[:, :3].astype(np.float64))
+    nop_o, ptr_o, lst_o = oracle.makepair(q64, full=True)
+    p_o = np.zeros_like(q64)
+    oracle.force_gather(q64, p_o, nop_o, ptr_o, lst_o, steps=100)
+    qd = torch.from_numpy(qf).cuda()
+    pd = torch.zeros_like(qd); pd[:, 3] = -2.0
+    pl = ctx.makepair(qd, clusters=True)                      # list build straight from float4
+    nop, ptr, lst = list_to_host(pl)
+    assert np.array_equal(nop, nop_o) and np.array_equal(s.lo.sort_rows(nop, ptr, lst), lst_o)
+    for variant in ("auto", "cluster"):
+        pd[:, :3] = 0
+        ctx.force_loop(qd, pd, pl, loop=100, precision="mixed", variant=variant, group=0)
+        got = pd.cpu().numpy()
+        assert np.abs(got[:, :3] - p_o).max() / np.abs(p_o).max() < TOL_MIXED
+        assert np.all(got[:, 3] == -2.0)
+    from lj_gpu_b200 import LJError
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl, precision="fp64")           # float4 is a mixed-precision layout
+
+
 def test_row_order_is_irrelevant_and_gather_is_reproducible(ctx, torch, sysA):
     s = sysA
     qd, _ = s.device_arrays(torch, "aos4")
