@@ -194,7 +194,10 @@ def run_cuda(args):
     qd = torch.from_numpy(q4).cuda()
     pd = torch.zeros_like(qd)
     use_cl = args.variant == "cluster" and args.prec == "fp64"
-    pl = ctx.makepair(qd, pointer64=False, clusters=use_cl)
+    # "auto" on a list the library builds itself: the build also emits the cell-tile mirror and the
+    # FP64 step runs on it (k_tile_permute + lj_celltile_force, two launches per step)
+    use_tiles = args.variant in ("auto", "celltile") and args.prec == "fp64"
+    pl = ctx.makepair(qd, pointer64=False, clusters=use_cl, tiles=use_tiles)
     P = pl.number_of_pairs
     fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
                threads_per_block=args.threads_per_block)
@@ -204,7 +207,7 @@ def run_cuda(args):
         s = n0
         while s < n0 + n:
             if s % REBUILD_EVERY == 0:
-                ctx.rebuild(qd, pl, clusters=use_cl)
+                ctx.rebuild(qd, pl, clusters=use_cl, tiles=use_tiles)
             m = min(REBUILD_EVERY - s % REBUILD_EVERY, n0 + n - s)
             ctx.force_loop(qd, pd, pl, loop=m, **fkw)
             s += m
@@ -238,7 +241,7 @@ def run_cuda(args):
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record(stream)
     for _ in range(5):
-        ctx.rebuild(qd, pl, clusters=use_cl)
+        ctx.rebuild(qd, pl, clusters=use_cl, tiles=use_tiles)
     b1.record(stream)
     torch.cuda.synchronize()
     ms_build = b0.elapsed_time(b1) / 5
@@ -313,7 +316,9 @@ def run_cuda(args):
                         "every 20) -> D2H p", "p_checksum": checksum},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "force step (lj_gather_*)", "algorithmic_bytes_per_launch": bytes_force,
+                     "kernel": ("force step (k_tile_permute + lj_celltile_force)" if use_tiles
+                                else "force step (lj_gather_*)"),
+                     "algorithmic_bytes_per_launch": bytes_force,
                      "ms_per_launch": ms_force, "pairs_per_s_force_only": P / (ms_force * 1e-3),
                      "list_build_ms": ms_build,
                      "amortised_step_ms": ms_force + ms_build / REBUILD_EVERY},

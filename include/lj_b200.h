@@ -66,8 +66,12 @@ typedef enum lj_variant {
                                bulk copy, `group` lanes per i (CSR only)                     */
   LJ_VARIANT_NEWTON3 = 3,   /* half list, reaction scattered with FP64 atomics
                                (the *_with_aar kernels, kernel.cuh:238-469)                  */
-  LJ_VARIANT_CLUSTER = 4    /* cluster pair list built by lj_build_list(LJ_LIST_CLUSTERS) for
+  LJ_VARIANT_CLUSTER = 4,   /* cluster pair list built by lj_build_list(LJ_LIST_CLUSTERS) for
                                exactly these list arrays; error if there is none             */
+  LJ_VARIANT_CELLTILE = 5   /* cell-tile mirror built by lj_build_list(LJ_LIST_TILES) for exactly
+                               these list arrays: q[j] of a tile's neighbourhood staged in shared
+                               memory by TMA, 16-bit local indices; error if there is none.
+                               AUTO picks it whenever the mirror exists (FP64)                */
 } lj_variant;
 
 typedef enum lj_precision {
@@ -173,7 +177,13 @@ enum {
   LJ_LIST_CLUSTERS = 2,
   /* use the one-search-per-particle kernel instead of the default cluster-organised search
    * (identical output; kept for A/B measurements) */
-  LJ_LIST_PER_PARTICLE_SEARCH = 4
+  LJ_LIST_PER_PARTICLE_SEARCH = 4,
+  /* also build the library-owned CELL-TILE MIRROR of the list: the same rows in cell order with
+   * 16-bit indices into the shared-memory region of their tile (LJ_VARIANT_CELLTILE / AUTO).
+   * Full lists, FP64 layouts; two small host read-backs per build.  Dropped like the cluster list;
+   * silently absent when a tile's neighbourhood would not fit in shared memory (very dense
+   * systems), in which case AUTO stays on the per-row kernels. */
+  LJ_LIST_TILES = 8
 };
 
 typedef struct lj_list_args {

@@ -18,10 +18,12 @@ LJ_OK, LJ_ERR_CUDA, LJ_ERR_BAD_ARG, LJ_ERR_CAPACITY, LJ_ERR_OVERFLOW32, LJ_ERR_N
     LJ_ERR_INVALID_LIST = range(7)
 LJ_AOS_D3, LJ_AOS_D4, LJ_SOA_D, LJ_AOS_F4 = range(4)
 LJ_LIST_CSR, LJ_LIST_ELL = 0, 1
-LJ_VARIANT_AUTO, LJ_VARIANT_SUBWARP, LJ_VARIANT_TILE_TMA, LJ_VARIANT_NEWTON3, LJ_VARIANT_CLUSTER = range(5)
+LJ_VARIANT_AUTO, LJ_VARIANT_SUBWARP, LJ_VARIANT_TILE_TMA, LJ_VARIANT_NEWTON3, LJ_VARIANT_CLUSTER, \
+    LJ_VARIANT_CELLTILE = range(6)
 LJ_PREC_FP64, LJ_PREC_MIXED = 0, 1
 LJ_LIST_SORT_ROWS = 1
 LJ_LIST_CLUSTERS = 2
+LJ_LIST_TILES = 8
 LJ_LIST_PER_PARTICLE_SEARCH = 4
 
 

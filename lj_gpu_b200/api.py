@@ -29,7 +29,7 @@ LOOP = 100
 LAYOUTS = {"aos3": LJ_AOS_D3, "aos4": LJ_AOS_D4, "soa": LJ_SOA_D, "f4": capi.LJ_AOS_F4}
 VARIANTS = {"auto": LJ_VARIANT_AUTO, "subwarp": LJ_VARIANT_SUBWARP, "warp": LJ_VARIANT_SUBWARP,
             "thread": LJ_VARIANT_SUBWARP, "tile": LJ_VARIANT_TILE_TMA, "n3": LJ_VARIANT_NEWTON3,
-            "cluster": capi.LJ_VARIANT_CLUSTER}
+            "cluster": capi.LJ_VARIANT_CLUSTER, "celltile": capi.LJ_VARIANT_CELLTILE}
 
 
 class LJError(RuntimeError):
@@ -199,10 +199,11 @@ class LJContext:
     def makepair(self, q, search_len: float = SEARCH_LENGTH, half: bool = False, layout=None,
                  pointer64: bool = False, sort_rows: bool = False, capacity: int | None = None,
                  rows=None, pn=None, out: PairList | None = None, clusters: bool = False,
-                 per_particle: bool = False, stream=None) -> PairList:
+                 per_particle: bool = False, tiles: bool = False, stream=None) -> PairList:
         """makepair() (cuda/force_cuda.cu:122-163) on the GPU.  Returns device arrays.
         clusters=True also builds the library-owned cluster pair list (LJ_LIST_CLUSTERS) that the
-        "auto"/"cluster" force variants use for exactly these arrays."""
+        "auto"/"cluster" force variants use for exactly these arrays; tiles=True the cell-tile mirror
+        (LJ_LIST_TILES) of the "auto"/"celltile" variants."""
         import torch
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
@@ -222,7 +223,7 @@ class LJContext:
         a.number_of_partners, a.pointer = nop.data_ptr(), ptr.data_ptr()
         a.pointer64 = int(pointer64)
         a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0) | \
-            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0)
+            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0) | (capi.LJ_LIST_TILES if tiles else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         total = C.c_int64(0)
@@ -241,7 +242,7 @@ class LJContext:
 
     def rebuild(self, q, pl: PairList, search_len: float = SEARCH_LENGTH, layout=None,
                 sort_rows: bool = False, rows=None, pn=None, clusters: bool = False,
-                per_particle: bool = False, stream=None):
+                per_particle: bool = False, tiles: bool = False, stream=None):
         """Asynchronous rebuild into existing arrays (no host sync, no reallocation)."""
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
@@ -254,7 +255,7 @@ class LJContext:
         a.sorted_list, a.capacity = pl.sorted_list.data_ptr(), pl.sorted_list.numel()
         a.pointer64 = int(pl.pointer64)
         a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0) | \
-            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0)
+            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0) | (capi.LJ_LIST_TILES if tiles else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         self._check(self.lib.lj_build_list(self.h, C.byref(a), None, self._stream(stream)))

@@ -26,6 +26,20 @@ struct lj_grid_params {  // cell grid derived ON THE DEVICE from the bounding bo
   int ncell;
 };
 
+// Geometry of the cell-tile mirror (lj_celltile.cuh): tiles of `tc` consecutive x-cells of one
+// (y,z) pencil of the cell grid.  Written on the device by the list build, copied to the host.
+struct lj_tile_geom {
+  int tc;          // cells per tile along x
+  int ntx;         // tiles per pencil
+  int nx, ny, nz;  // cell grid
+  int ntiles;      // ntx * ny * nz
+  int max_rows;    // largest number of rows (particles) in one tile
+  int max_yrow;    // longest y-row (five pencils), particles; cap_y = max_yrow + 8
+  int max_units;   // largest list segment of one tile, in units of 8 entries
+  int pad;
+  unsigned long long total_units;  // whole mirror list, units of 8 entries
+};
+
 struct lj_ctx {
   int device = 0;
   int sm_count = 148;
@@ -70,6 +84,28 @@ struct lj_ctx {
   const void* cl_id_ptr = nullptr;
   int64_t cl_pn = 0, cl_r0 = 0, cl_r1 = 0, cl_entries = 0;
 
+  // cell-tile mirror: library-owned copy of the CSR list most recently built with LJ_LIST_TILES,
+  // rows in cell order, entries = 16-bit indices into the tile's staged region (lj_celltile.cuh)
+  lj_tile_geom* tl_geom = nullptr;       // device
+  lj_tile_geom* tl_geom_host = nullptr;  // pinned
+  int32_t* tl_order = nullptr;           // [pn]   original index of sorted slot s
+  int32_t* tl_cnt = nullptr;             // [pn]   entries of row s
+  uint32_t* tl_units = nullptr;          // [pn+1] padded row length, units of 8 entries
+  uint32_t* tl_off = nullptr;            // [pn+1] exclusive scan of tl_units
+  double* tl_qs = nullptr;               // [pn+2][3] positions in cell order, refreshed every step
+  uint32_t* tl_cell_start = nullptr;     // [ncell+1] private copy of the cell offsets
+  uint16_t* tl_list = nullptr;
+  uint2* tl_tab = nullptr;               // [ntiles][6] y-row table (lj_celltile.cuh)
+  uint4* tl_ttab = nullptr;              // [ntiles][2] tile table
+  int4* tl_meta = nullptr;               // [pn] {entries, first unit, original index, 0} of row s
+  int64_t tl_pn_cap = 0, tl_cells_cap = 0, tl_list_cap = 0, tl_tab_cap = 0;  // particles, cells, units, tiles
+  bool tl_valid = false;
+  const void* tl_id_list = nullptr;
+  const void* tl_id_nop = nullptr;
+  const void* tl_id_ptr = nullptr;
+  int64_t tl_pn = 0, tl_r0 = 0, tl_r1 = 0;
+  lj_tile_geom tl_g{};                   // host copy of the geometry of the valid mirror
+
   // mixed-precision scratch: origin-shifted float4 positions
   float4* q32 = nullptr;
   int64_t q32_len = 0;
@@ -111,6 +147,21 @@ int lj_scratch_reserve(lj_ctx* ctx, int64_t pn, cudaStream_t st);
 int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st);
 int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t plane,
                    lj_list_totals* reset_totals, cudaStream_t st);
+// cell-tile mirror (lj_nlist.cu builds it, lj_force_celltile.cu consumes it)
+int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st);
+bool lj_celltile_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1);
+bool lj_celltile_worthwhile(const lj_ctx* ctx);
+int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
+                             long long cl2_bits, cudaStream_t st);
+// shared memory of the force kernel: a ring of y-row slots (cap_y packed double3 records each) and
+// a ring of list slots (a tile's list segment + 16 B of metadata per row)
+constexpr size_t kTileSmemBudget = 227 * 1024 - 8 * 1024;  // minus the kernel's static shared memory
+static inline int lj_celltile_cap_y(const lj_tile_geom& g) { return (g.max_yrow + 8 + 1) & ~1; }
+static inline size_t lj_celltile_yslot_bytes(const lj_tile_geom& g) { return (size_t)lj_celltile_cap_y(g) * 24; }
+static inline size_t lj_celltile_lslot_bytes(const lj_tile_geom& g) {
+  return (size_t)g.max_units * 16 + (size_t)g.max_rows * 16;
+}
+constexpr int kTileMinYSlots = 7, kTileMinLSlots = 2;  // five rows in use + two in flight; two lists
 
 // ------------------------------------------------------------------------------------
 // Device helpers

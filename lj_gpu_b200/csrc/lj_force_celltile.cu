@@ -1,0 +1,444 @@
+// lj_force_celltile.cu -- FP64 force kernel on the cell-tile mirror (sm_100a).
+//
+// Why: the per-row gather kernels are bound by the L1/LSU data pipe.  A 32-lane LDG.E.256 gather
+// costs ~2 SM-cycles per distinct 128-byte line it touches (8-32 lines), the 4-byte list words are
+// a second LSU stream, and both wait on L2/DRAM latency.  This kernel takes the gather off the
+// global path altogether (geometry: lj_celltile.cuh):
+//
+//   * persistent CTAs, one per SM.  A CTA walks COLUMNS of tiles (fixed x-range and z, y
+//     ascending).  The neighbours of a tile are the 25 pencils (y-2..y+2) x (z-2..z+2); the five
+//     pencils of one y form a y-row, and consecutive tiles share four of their five y-rows.  A
+//     producer warp keeps a ring of y-rows in shared memory and stages ONE new y-row per tile
+//     (five TMA bulk copies, cp.async.bulk -> UBLKCP) plus the tile's list segment and row
+//     metadata, each completion counted in bytes on an mbarrier: 16 KB per tile instead of the
+//     60 KB of a whole region (the L2 -> SM path is the scarce resource: ~43 B/cycle/SM);
+//   * the mirror list holds 16-bit region-local indices (2 B per pair from HBM instead of 4),
+//     rows padded to 8 entries with an index that points at a far-away dummy point, so the inner
+//     loop has no bounds logic;
+//   * per pair-iteration a warp issues one LDS.U16 and three LDS.64 on packed double3 records at
+//     ~30-cycle latency, instead of one list LDG and one 32-line gather at L2 latency.
+//
+// Sixteen consumer warps: eight lanes per row, four rows (a quad) per warp in lock step with
+// warp-uniform trip counts, quads dealt round-robin across tiles, shuffle reduction, one
+// RED.ADD.F64 per component and row (exactly one add per step: deterministic).  Results are
+// bit-identical to the per-row kernel with group = 8 on the same list order.  Positions are
+// re-permuted into cell order at the start of every step (k_tile_permute, ~10 us at N = 1M), so
+// moving particles are handled exactly like in the per-row kernels: the list decides membership,
+// the current q decides the force.
+#include <cstdlib>
+#include <vector>
+
+#include "lj_celltile.cuh"
+#include "lj_tile.cuh"
+
+namespace {
+
+#ifndef LJ_CT_CONSUMERS
+#define LJ_CT_CONSUMERS 16
+#endif
+constexpr int kCtConsumers = LJ_CT_CONSUMERS;        // consumer warps
+constexpr int kCtThreads = (kCtConsumers + 1) * 32;  // + one producer warp
+constexpr int kCtMaxStages = 8;
+#ifndef LJ_CT_UNROLL
+#define LJ_CT_UNROLL 4
+#endif
+constexpr int kCtUnroll = LJ_CT_UNROLL;
+
+struct __align__(16) tile_hdr { int ns, self0; uint32_t u0; int yslot0; };
+
+template <int LAYOUT>
+__device__ __forceinline__ void red_mom(void* __restrict__ p, int64_t i, int64_t plane, double fx,
+                                        double fy, double fz) {
+  double* b;
+  int64_t s;
+  if (LAYOUT == LJ_AOS_D4) { b = reinterpret_cast<double*>(p) + 4 * i; s = 1; }
+  else if (LAYOUT == LJ_AOS_D3) { b = reinterpret_cast<double*>(p) + 3 * i; s = 1; }
+  else { b = reinterpret_cast<double*>(p) + i; s = plane; }
+  atomicAdd(b, fx);
+  atomicAdd(b + s, fy);
+  atomicAdd(b + 2 * s, fz);
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+constexpr int kCtMaxY = 16, kCtMaxL = 8;
+constexpr int kCtMaxSeg = 32;  // tiles per unit (column segment) at most
+
+struct ct_params {
+  const double* qs; void* p; int64_t plane;
+  double c24, c48; long long cl2_bits;
+  const uint2* ytab; const uint4* ttab; const int4* meta; const uint16_t* list;
+  int ntx, ny, ncols;    // tiles per pencil, cells in y, columns = ntx * nz
+  int seg_len, nseg;     // a unit = one column x [seg*seg_len, min(ny, (seg+1)*seg_len))
+  int cap_y, cap_units, cap_rows;
+  int ry, rl;            // ring sizes: y-row slots, tile slots (list + metadata + barriers)
+  int lslot_bytes;
+  int* unit_counter;     // zeroed by k_tile_permute before every launch: units are dealt dynamically
+  long long* dbg;        // diagnostics (LJ_TILE_DBG): per consumer warp {wait, work, quads, total} cycles
+  int mode;              // diagnostics (LJ_TILE_MODE): 0 normal, 1 no pair math, 3 staging only
+};
+
+// One `full` and one `empty` mbarrier per TILE slot.  Everything a tile waits for -- its newest
+// y-row (all five for the first tile of a column segment), its list segment and its row metadata --
+// completes on the tile's full barrier, so a consumer warp pays one wait, one 16-byte header read
+// and one arrive per tile (most warps have no quad in a given tile: that path must be short).  The
+// y-row ring is managed by the producer alone: a y-row's slot is free once the tile that had it as
+// its oldest row has been released.
+template <int LAYOUT>
+__global__ void __launch_bounds__(kCtThreads, 1)
+lj_celltile_force(const ct_params P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t tfull[kCtMaxL], tempty[kCtMaxL];
+  __shared__ tile_hdr hdr[kCtMaxL];
+  __shared__ int yrel[kCtMaxY];  // producer: tile sequence number whose release frees the y slot
+  // the producer's view of the y-row / tile tables of the current and the next unit (bulk-copied one
+  // unit ahead: a table entry fetched with a plain load costs a DRAM round trip per tile)
+  __shared__ __align__(16) uint2 ytab_s[2][(kCtMaxSeg + 4) * kTileYTab];
+  __shared__ __align__(16) uint4 ttab_s[2][kCtMaxSeg * kTileTTab];
+  __shared__ __align__(8) uint64_t tabbar[2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ry = P.ry, rl = P.rl, cap_y = P.cap_y;
+  unsigned char* const ybase = smem_raw;
+  unsigned char* const lbase = smem_raw + (size_t)ry * cap_y * 24;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kCtConsumers); }
+    mbar_init(&tabbar[0], 1); mbar_init(&tabbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < ry) {  // the dummy record of every y slot: its last one, no copy ever reaches it
+    double* d = reinterpret_cast<double*>(ybase) + ((size_t)threadIdx.x * cap_y + cap_y - 1) * 3;
+    d[0] = kTileFar; d[1] = kTileFar; d[2] = kTileFar;
+    yrel[threadIdx.x] = -1;
+  }
+  __syncthreads();
+  const int nunits = P.ncols * P.nseg;
+
+  if (warp == kCtConsumers) {
+    // ------------------------------------------------------------------ producer warp ---
+    int yslot = 0;                       // next y-row slot (ring of ry)
+    int tseq = 0, tslot = 0;             // tile being assembled: sequence number, slot (ring of rl)
+    int done = 0, dslot = 0, dphase = 0; // tiles known to be released: [0, done)
+    auto ensure_done = [&](int q) {      // block until tile q has been released by every consumer
+      while (done <= q) {
+        mbar_wait(&tempty[dslot], dphase);
+        done++;
+        if (++dslot == rl) { dslot = 0; dphase ^= 1; }
+      }
+    };
+    // table rows of unit u -> staging buffer b: y-rows max(y0-2,0) .. min(y1+1,ny-1), tiles y0 .. y1-1
+    auto stage_tables = [&](int u, int b) {
+      const int col = u % P.ncols, seg = u / P.ncols;
+      const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
+      const int ylo = max(y0 - 2, 0), yhi = min(y1 + 1, P.ny - 1);
+      if (lane == 0) {
+        const uint32_t yb = (uint32_t)(yhi - ylo + 1) * kTileYTab * 8u, tb = (uint32_t)(y1 - y0) * kTileTTab * 16u;
+        mbar_arrive_expect_tx(&tabbar[b], yb + tb);
+        bulk_g2s(&ytab_s[b][0], P.ytab + ((size_t)col * P.ny + ylo) * kTileYTab, yb, &tabbar[b]);
+        bulk_g2s(&ttab_s[b][0], P.ttab + ((size_t)col * P.ny + y0) * kTileTTab, tb, &tabbar[b]);
+      }
+    };
+    // units are dealt dynamically (tiles differ in size by 2x, a static deal leaves SMs idle at the
+    // end); the next unit is claimed one unit ahead so that its tables can be staged early
+    auto claim = [&]() {
+      int v = 0;
+      if (lane == 0) v = atomicAdd(P.unit_counter, 1);
+      return __shfl_sync(0xffffffffu, v, 0);
+    };
+    int nu = 0;  // units done by this CTA
+    int u = claim();
+    if (u < nunits) stage_tables(u, 0);
+    for (; u < nunits; nu++) {
+      const int u_next = claim();
+      const int seg = u / P.ncols;
+      const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
+      const int ntile = y1 - y0;
+      const int tb = nu & 1;
+      __syncwarp();  // every lane is done with the other buffer (the previous unit's tables)
+      if (u_next < nunits) stage_tables(u_next, tb ^ 1);
+      mbar_wait(&tabbar[tb], (nu >> 1) & 1);
+      const int ylo = max(y0 - 2, 0);
+      auto load_y = [&](int Y) {  // lane dz < 5: {st, pb}; lane 5: {0, length}
+        uint2 e = make_uint2(0u, 0u);
+        if (lane < kTileYTab && Y >= 0 && Y < P.ny) e = ytab_s[tb][(Y - ylo) * kTileYTab + lane];
+        return e;
+      };
+      auto load_t = [&](int cy) {  // lanes 0, 1: the two uint4 of the tile
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < kTileTTab && cy >= y0 && cy < y1) e = ttab_s[tb][(cy - y0) * kTileTTab + lane];
+        return e;
+      };
+      uint2 ey_next = load_y(y0 - 2);
+      uint4 et_next = load_t(y0);
+      const int tbase = tseq;
+      int first_yslot = yslot;  // slot of the oldest y-row of the tile being assembled
+      for (int i = 0; i < ntile + 4; i++) {
+        const int Y = y0 - 2 + i;
+        const uint2 ey = ey_next;
+        ey_next = load_y(Y + 1);  // in flight while this iteration waits and issues
+        // the tile this y-row completes on: tile 0 for the first five rows, then one row per tile.
+        // Its slot (barrier, list, header) must be free before the first contribution.
+        if (i == 0 || i > 4) { if (tseq >= rl) ensure_done(tseq - rl); }
+        // ---- y-row Y -> y slot
+        {
+          const int rel = yrel[yslot];
+          if (rel >= 0) ensure_done(rel);
+          const uint32_t pb_next = __shfl_down_sync(0xffffffffu, ey.y, 1);
+          const uint32_t len = lane < kTileYPencils ? pb_next - ey.y : 0u;
+          uint32_t ylen = __shfl_sync(0xffffffffu, ey.y, 5);
+          if (P.mode & 16) ylen = 0;  // diagnostics: no y-row copies
+          if ((int)ylen > cap_y - 8) __trap();
+          if (lane == 0) {
+            yrel[yslot] = tbase + min(i, ntile - 1);  // the tile that has it as its oldest row
+            if (ylen) mbar_expect_tx(&tfull[tslot], ylen * 24u);
+          }
+          __syncwarp();
+          if (len && ylen)
+            bulk_g2s(ybase + ((size_t)yslot * cap_y + ey.y) * 24, P.qs + (size_t)ey.x * 3, len * 24u, &tfull[tslot]);
+          if (++yslot == ry) yslot = 0;
+        }
+        // ---- tile cy = Y - 2: list segment, metadata, header; then the barrier's one arrival
+        if (i >= 4) {
+          const int cy = Y - 2;
+          const uint4 et = et_next;
+          et_next = load_t(cy + 1);
+          const uint32_t s0 = __shfl_sync(0xffffffffu, et.x, 0), ns = __shfl_sync(0xffffffffu, et.y, 0);
+          const uint32_t u0 = __shfl_sync(0xffffffffu, et.z, 0), units = __shfl_sync(0xffffffffu, et.w, 0);
+          const uint32_t self0 = __shfl_sync(0xffffffffu, et.x, 1);
+          const uint32_t units_c = (P.mode & 32) ? 0u : units, ns_c = (P.mode & 64) ? 0u : ns;  // diagnostics
+          if ((int)units > P.cap_units || (int)ns > P.cap_rows) __trap();
+          unsigned char* dst = lbase + (size_t)tslot * P.lslot_bytes;
+          if (lane == 0) {
+            hdr[tslot].ns = (int)ns; hdr[tslot].self0 = (int)self0 + 2 * cap_y; hdr[tslot].u0 = u0;
+            hdr[tslot].yslot0 = first_yslot;
+            mbar_arrive_expect_tx(&tfull[tslot], units_c * 16u + ns_c * 16u);
+          }
+          __syncwarp();
+          if (lane == 0 && units_c) bulk_g2s(dst, P.list + (size_t)u0 * 8, units * 16u, &tfull[tslot]);
+          if (lane == 1 && ns_c) bulk_g2s(dst + (size_t)P.cap_units * 16, P.meta + s0, ns * 16u, &tfull[tslot]);
+          tseq++;
+          if (++tslot == rl) tslot = 0;
+          if (++first_yslot == ry) first_yslot = 0;
+        }
+      }
+      u = u_next;
+    }
+    // end marker for the consumers: a tile header with ns < 0
+    if (tseq >= rl) ensure_done(tseq - rl);
+    if (lane == 0) {
+      hdr[tslot].ns = -1;
+      mbar_arrive(&tfull[tslot]);
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps ---
+  const int lg = lane & 7, gi = lane >> 3;
+  const uint32_t ring = (uint32_t)ry * (uint32_t)cap_y;
+  const uint32_t ybase_s = smem_u32(ybase);
+  const uint32_t dummy = (uint32_t)cap_y - 1u;
+  int tslot = 0, tphase = 0;
+  long long t_wait = 0, t_work = 0, n_quads = 0;
+  const long long t_begin = P.dbg ? clock64() : 0;
+  int first = warp;  // quads are dealt round-robin over the warps ACROSS tiles: tiles hold fewer
+                     // quads than there are warps, a per-tile deal would leave the high warps idle
+  for (;;) {
+    {
+      long long tw0 = 0;
+      if (P.dbg) tw0 = clock64();
+      mbar_wait(&tfull[tslot], tphase);
+      long long tw1 = 0;
+      if (P.dbg) { tw1 = clock64(); t_wait += tw1 - tw0; }
+      const int4 h = *reinterpret_cast<const int4*>(&hdr[tslot]);  // ns, self0, u0, yslot0
+      const int ns = h.x;
+      if (ns < 0) break;  // end marker
+      const int nquads = (ns + 3) >> 2;
+      int quad = first;
+      const bool had_quad = quad < nquads;
+      first = (first + kCtConsumers - nquads % kCtConsumers) % kCtConsumers;
+      if (quad < nquads && (P.mode & 15) != 3) {
+        const int self0 = h.y;
+        const uint32_t u0 = (uint32_t)h.z;
+        const unsigned char* lptr = lbase + (size_t)tslot * P.lslot_bytes;
+        const uint16_t* __restrict__ lst = reinterpret_cast<const uint16_t*>(lptr);
+        const int4* __restrict__ meta = reinterpret_cast<const int4*>(lptr + (size_t)P.cap_units * 16);
+        // region-local index L -> ring record: (slot of the tile's first y-row) * cap_y + L, wrapped
+        const uint32_t off0 = (uint32_t)h.w * (uint32_t)cap_y;
+        const uint32_t off0w = off0 - ring;
+        auto fetch = [&](uint32_t L, double& x, double& y, double& z) {
+          const uint32_t a = ybase_s + min(L + off0, L + off0w) * 24u;  // unsigned min = wrap
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
+          asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(y) : "r"(a));
+          asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(z) : "r"(a));
+        };
+        for (; quad < nquads; quad += kCtConsumers) {
+          const int r = quad * 4 + gi;
+          const bool valid = r < ns;
+          int4 m = make_int4(0, (int)u0, 0, 0);
+          if (valid) m = meta[r];
+          const int np = m.x;
+          const int trips = (np + 7) >> 3;
+          const int tmin = __reduce_min_sync(0xffffffffu, trips);
+          const int tmax = __reduce_max_sync(0xffffffffu, trips);
+          const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lg;
+          double xi, yi, zi;
+          fetch(valid ? (uint32_t)(self0 + r) : dummy, xi, yi, zi);
+          double fx = 0.0, fy = 0.0, fz = 0.0;
+          int k = 0;
+          for (; k + kCtUnroll <= tmin; k += kCtUnroll) {
+            uint32_t en[kCtUnroll];
+#pragma unroll
+            for (int v = 0; v < kCtUnroll; v++) en[v] = e[(k + v) * 8];
+            double xj[kCtUnroll], yj[kCtUnroll], zj[kCtUnroll];
+#pragma unroll
+            for (int v = 0; v < kCtUnroll; v++) fetch(en[v], xj[v], yj[v], zj[v]);
+            if ((P.mode & 15) == 1) {
+#pragma unroll
+              for (int v = 0; v < kCtUnroll; v++) { fx += xj[v]; fy += yj[v]; fz += zj[v]; }
+              continue;
+            }
+#pragma unroll
+            for (int v = 0; v < kCtUnroll; v++)
+              lj_pair(xj[v] - xi, yj[v] - yi, zj[v] - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
+          }
+          for (; k < tmax; k += 2) {  // warp-uniform; rows that are already done look at the dummy point
+            const uint32_t e0 = k < trips ? (uint32_t)e[k * 8] : dummy;
+            const uint32_t e1 = k + 1 < trips ? (uint32_t)e[(k + 1) * 8] : dummy;
+            double x0, y0_, z0, x1, y1_, z1;
+            fetch(e0, x0, y0_, z0);
+            fetch(e1, x1, y1_, z1);
+            lj_pair(x0 - xi, y0_ - yi, z0 - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
+            lj_pair(x1 - xi, y1_ - yi, z1 - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
+          }
+          fx = group_sum<8>(fx);
+          fy = group_sum<8>(fy);
+          fz = group_sum<8>(fz);
+          // RED (no return value): the warp does not wait for p at the end of every quad.  Exactly
+          // one add per component, row and step, so the result is deterministic.
+          if (lg == 0 && np > 0) red_mom<LAYOUT>(P.p, m.z, P.plane, fx, fy, fz);
+          n_quads++;
+        }
+      }
+      __syncwarp();
+      if (P.dbg && had_quad) t_work += clock64() - tw1;
+      if (lane == 0) mbar_arrive(&tempty[tslot]);  // this warp is through with the tile
+      if (++tslot == rl) { tslot = 0; tphase ^= 1; }
+    }
+  }
+  if (P.dbg && lane == 0) {
+    long long* d = P.dbg + ((size_t)blockIdx.x * kCtConsumers + warp) * 4;
+    d[0] = t_wait; d[1] = t_work; d[2] = n_quads; d[3] = clock64() - t_begin;
+  }
+}
+
+template <int LAYOUT>
+int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
+                    cudaStream_t st) {
+  const lj_tile_geom& g = ctx->tl_g;
+  const size_t ys = lj_celltile_yslot_bytes(g), ls = lj_celltile_lslot_bytes(g);
+  // ring sizes.  A tile holds five y-rows and one list slot; at a unit boundary the last tile of the
+  // old unit and the first tile of the new one hold ten y-rows between them, so fewer than ten
+  // y slots drain the pipeline at every boundary.  Prefer >= 10 y slots, then balance look-ahead.
+  int ry = 0, rl = 0, best = -1;
+  for (int l = kCtMaxL; l >= kTileMinLSlots; l--) {
+    if ((size_t)l * ls + kTileMinYSlots * ys > kTileSmemBudget) continue;
+    int y = (int)((kTileSmemBudget - (size_t)l * ls) / ys);
+    if (y > kCtMaxY) y = kCtMaxY;
+    int score = (y - 5 < l - 1) ? y - 5 : l - 1;
+    if (y >= 10 && l >= 3) score += 100;
+    if (score > best) { best = score; ry = y; rl = l; }
+  }
+  LJ_REQUIRE(ctx, best >= 0, "lj_force_step: cell-tile geometry does not fit in shared memory");
+  static const int seg_env = [] { const char* e = getenv("LJ_TILE_SEG"); return e ? atoi(e) : 0; }();
+  const int ncols = g.ntx * g.nz;
+  int nseg = (16 * ctx->sm_count + ncols - 1) / ncols;  // >= 16 units per CTA: the dynamic deal ends evenly
+  if (nseg > g.ny / 6) nseg = g.ny / 6;                 // but every unit re-stages four y-rows: keep them long
+  if (nseg < 1) nseg = 1;
+  int seg_len = seg_env > 0 ? seg_env : (g.ny + nseg - 1) / nseg;
+  if (seg_len > g.ny) seg_len = g.ny;
+  if (seg_len > kCtMaxSeg) seg_len = kCtMaxSeg;
+  nseg = (g.ny + seg_len - 1) / seg_len;
+
+  ct_params P;
+  P.qs = ctx->tl_qs; P.p = a->p; P.plane = a->plane_stride;
+  P.c24 = c24; P.c48 = c48; P.cl2_bits = cl2_bits;
+  P.ytab = ctx->tl_tab; P.ttab = ctx->tl_ttab; P.meta = ctx->tl_meta; P.list = ctx->tl_list;
+  P.ntx = g.ntx; P.ny = g.ny; P.ncols = ncols; P.seg_len = seg_len; P.nseg = nseg;
+  P.cap_y = lj_celltile_cap_y(g); P.cap_units = g.max_units; P.cap_rows = g.max_rows;
+  P.ry = ry; P.rl = rl; P.lslot_bytes = (int)ls;
+  static const int mode_env = [] { const char* e = getenv("LJ_TILE_MODE"); return e ? atoi(e) : 0; }();
+  P.mode = mode_env;
+  P.unit_counter = &ctx->tl_geom->pad;
+  P.dbg = nullptr;
+  static long long* dbg_buf = nullptr;
+  if (getenv("LJ_TILE_DBG")) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * kCtConsumers * 1024);
+    P.dbg = dbg_buf;
+  }
+  const size_t smem = (size_t)ry * ys + (size_t)rl * ls;
+  auto kern = lj_celltile_force<LAYOUT>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    LJ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int nunits = ncols * nseg;
+  const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
+  if (getenv("LJ_TILE_DEBUG"))
+    fprintf(stderr, "[lj] cell-tile force: %d units (%d columns x %d segments of %d), y ring %d x %zu B, list ring "
+            "%d x %zu B, smem %zu B\n", nunits, ncols, nseg, seg_len, ry, ys, rl, ls, smem);
+  kern<<<(unsigned)grid, kCtThreads, smem, st>>>(P);
+  LJ_LAUNCHED(ctx);
+  if (P.dbg) {  // diagnostics only: synchronises
+    static int dumps = 0;
+    cudaStreamSynchronize(st);
+    if (dumps++ == 3) {
+      std::vector<long long> h((size_t)4 * kCtConsumers * grid);
+      cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      double w = 0, k = 0, q = 0, t = 0, tmax = 0, tmin = 1e30, qmax = 0, qmin = 1e30;
+      for (int b = 0; b < grid; b++) {
+        double qb = 0, tb = 0;
+        for (int c = 0; c < kCtConsumers; c++) {
+          const long long* d = &h[((size_t)b * kCtConsumers + c) * 4];
+          w += d[0]; k += d[1]; q += d[2]; t += d[3]; qb += d[2]; if (d[3] > tb) tb = d[3];
+        }
+        if (tb > tmax) tmax = tb; if (tb < tmin) tmin = tb; if (qb > qmax) qmax = qb; if (qb < qmin) qmin = qb;
+      }
+      const double n = (double)grid * kCtConsumers;
+      fprintf(stderr, "[lj] celltile dbg: per warp avg wait %.0f, work %.0f, total %.0f cycles, quads %.1f (%.0f cycles/quad); "
+              "CTA total min %.0f max %.0f, quads per CTA min %.0f max %.0f\n", w / n, k / n, t / n, q / n, k / q, tmin, tmax, qmin, qmax);
+    }
+  }
+  return LJ_OK;
+}
+
+}  // namespace
+
+// AUTO takes the cell-tile kernel only where it wins: the persistent CTAs need a few dozen tiles each
+// to amortise their pipeline fill (measured: slower than the per-row kernel at N = 23k, faster at 1M)
+bool lj_celltile_worthwhile(const lj_ctx* ctx) { return ctx->tl_g.ntiles >= 32 * ctx->sm_count; }
+
+// true when the mirror describes exactly the list arrays and the row range of this call
+bool lj_celltile_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1) {
+  if (!ctx->tl_valid || a->list_layout != LJ_LIST_CSR || a->precision != LJ_PREC_FP64) return false;
+  if (a->layout != LJ_AOS_D3 && a->layout != LJ_AOS_D4 && a->layout != LJ_SOA_D) return false;
+  if (a->list != ctx->tl_id_list || a->number_of_partners != ctx->tl_id_nop ||
+      a->pointer != ctx->tl_id_ptr || a->pn != ctx->tl_pn)
+    return false;
+  return r0 == ctx->tl_r0 && r1 == ctx->tl_r1;
+}
+
+int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
+                             long long cl2_bits, cudaStream_t st) {
+  int rc = lj_celltile_permute(ctx, a, st);
+  if (rc) return rc;
+  switch (a->layout) {
+    case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_SOA_D: return launch_celltile<LJ_SOA_D>(ctx, a, c24, c48, cl2_bits, st);
+  }
+  return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
+}

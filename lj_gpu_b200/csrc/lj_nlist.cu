@@ -12,6 +12,9 @@
 // expression r2 = fma(dz,dz,fma(dy,dy,dx*dx)) < search^2 (same chain as oracle/lj_oracle.c);
 // an FP32 test on origin-shifted coordinates only pre-classifies candidates that are farther
 // than a rigorous error margin from the threshold.
+#include <cstdlib>
+
+#include "lj_celltile.cuh"
 #include "lj_common.cuh"
 
 namespace {
@@ -645,6 +648,210 @@ k_validate(const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
   }
 }
 
+
+// ------------------------------------------------------------------ cell-tile mirror ---
+// LJ_LIST_TILES: besides the reference's CSR arrays the build emits the same list a second time,
+// organised for the shared-memory force kernel (lj_force_celltile.cu): rows in cell order, each
+// padded to a multiple of 8 entries, entries = 16-bit indices into the tile's staged region
+// (geometry: lj_celltile.cuh).  Membership is decided by the same tests as k_search, so row s of
+// the mirror is row order[s] of the CSR list as a set; the row lengths are taken from
+// number_of_partners and cross-checked.
+__global__ void k_tile_prepare(const grid_ext* __restrict__ ge, int64_t pn, int target_rows,
+                               lj_tile_geom* __restrict__ tg) {
+  const lj_grid_params g = ge->g;
+  const double occ = fmax((double)pn / (double)g.ncell, 1.0e-3);  // mean particles per cell
+  int tc0 = (int)((double)target_rows / occ + 0.5);
+  tc0 = max(1, min(tc0, g.nx));
+  const int ntx = (g.nx + tc0 - 1) / tc0;
+  tg->tc = (g.nx + ntx - 1) / ntx;  // even split of the pencil
+  tg->ntx = (g.nx + tg->tc - 1) / tg->tc;
+  tg->nx = g.nx; tg->ny = g.ny; tg->nz = g.nz;
+  tg->ntiles = tg->ntx * g.ny * g.nz;
+  tg->max_rows = 0; tg->max_yrow = 0; tg->max_units = 0; tg->pad = 0;
+  tg->total_units = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_rows(int64_t pn, const float4* __restrict__ sorted_pos32, const int32_t* __restrict__ nop,
+            int32_t* __restrict__ order, int32_t* __restrict__ cnt, uint32_t* __restrict__ units) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > pn) return;
+  if (s == pn) { units[s] = 0u; return; }  // sentinel: the scan then yields off[pn] = total
+  const int i = __float_as_int(sorted_pos32[s].w);
+  const int c = nop[i];
+  order[s] = i;
+  cnt[s] = c;
+  units[s] = (uint32_t)(c + 7) >> 3;
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_meta(int64_t pn, const int32_t* __restrict__ order, const int32_t* __restrict__ cnt,
+            const uint32_t* __restrict__ off, int4* __restrict__ meta) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < pn) meta[s] = make_int4(cnt[s], (int)off[s], order[s], 0);
+}
+
+// One thread per (tx, Y = cy, cz).  Y-row table: the five pencil ranges {start, local base} of y-row
+// (tx, Y, cz) + {0, length}.  Tile table: {first row, rows, first list unit, list units} and the
+// region-local index of the tile's first row (it lives in the centre pencil: dy = 2, dz = 2).
+__global__ void __launch_bounds__(128)
+k_tile_table(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ off,
+             lj_tile_geom* __restrict__ tg, uint2* __restrict__ ytab, uint4* __restrict__ ttab) {
+  const lj_tile_geom g = *tg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.ntiles) return;
+  // tiles are numbered column by column: t = ((cz * ntx + tx) * ny + cy)
+  const int cy = t % g.ny, tx = (t / g.ny) % g.ntx, cz = t / (g.ny * g.ntx);
+  int xa, xb, rxa, rxb;
+  tile_x_extent(tx * g.tc, g.tc, g.nx, xa, xb, rxa, rxb);
+  uint32_t base = 0, st2 = 0, pb2 = 0;
+  for (int dz = 0; dz < kTileYPencils; dz++) {
+    uint32_t st, len;
+    tile_pencil_range(cell_start, g.nx, g.ny, g.nz, cy, cz, rxa, rxb, dz, st, len);
+    ytab[(size_t)t * kTileYTab + dz] = make_uint2(st, base);
+    if (dz == 2) { st2 = st; pb2 = base; }
+    base += len;
+  }
+  ytab[(size_t)t * kTileYTab + 5] = make_uint2(0u, base);
+  const int rowc = (cz * g.ny + cy) * g.nx;
+  const uint32_t s0 = cell_start[rowc + xa], s1 = cell_start[rowc + xb + 1];
+  ttab[(size_t)t * kTileTTab] = make_uint4(s0, s1 - s0, off[s0], off[s1] - off[s0]);
+  ttab[(size_t)t * kTileTTab + 1] = make_uint4(pb2 + (s0 - st2), 0u, 0u, 0u);  // + 2 * cap_y at run time
+  atomicMax(&tg->max_rows, (int)(s1 - s0));
+  atomicMax(&tg->max_yrow, (int)base);
+  atomicMax(&tg->max_units, (int)(off[s1] - off[s0]));
+}
+
+// FILL pass of the mirror: k_search in cell order, writing region-local 16-bit indices.  With
+// PUBLIC it is the FILL pass of the reference-format list as well (each hit is stored twice: j
+// into sorted_list, the local index into the mirror), which replaces the cluster FILL pass.
+template <bool PUBLIC, bool PTR64>
+__global__ void __launch_bounds__(256)
+k_tile_fill(int64_t pn, const grid_ext* __restrict__ ge, const lj_tile_geom* __restrict__ tgp,
+            const int32_t* __restrict__ cell_of, const uint32_t* __restrict__ cell_start,
+            const double4* __restrict__ sorted_pos, const float4* __restrict__ sorted_pos32, double sl2,
+            const int32_t* __restrict__ tl_cnt, const uint32_t* __restrict__ tl_off,
+            const uint2* __restrict__ tab, uint16_t* __restrict__ tl_list, lj_list_totals* __restrict__ tot,
+            const void* __restrict__ pointer, int32_t* __restrict__ list, int64_t capacity, int fake) {
+  constexpr int GL = kSearchLanes;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;  // slot in cell order
+  const int lane = threadIdx.x & 31;
+  const int lg = lane % GL;
+  const unsigned gbits = ((1u << GL) - 1u) << (lane - lg);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  bool active = s < pn;
+  float4 me32 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int want = 0;
+  if (active) { me32 = sorted_pos32[s]; want = tl_cnt[s]; }
+  const int i = __float_as_int(me32.w);
+  active = active && want > 0;  // empty rows (also: rows outside the build's row range)
+  const lj_grid_params g = ge->g;
+  const int tc = tgp->tc, ntx = tgp->ntx;
+  const float margin = ge->margin, sl2f = ge->sl2f, edge = ge->edge, pad = ge->pad;
+  const float lo_f = sl2f - margin, hi_f = sl2f + margin;
+  const int c = active ? cell_of[i] : 0;
+  const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+  // y-row table of my column (tx, cz), row index Y in [0, ny)
+  const uint2* __restrict__ mytab = tab + (size_t)((cz * ntx + cx / tc) * g.ny) * kTileYTab;
+  const uint32_t cap_y = (uint32_t)((tgp->max_yrow + 8 + 1) & ~1);
+  const size_t base = active ? (size_t)tl_off[s] * 8 : 0;
+  int64_t pbase = 0;
+  bool pub = PUBLIC && active;
+  if (pub) {
+    pbase = row_offset<PTR64>(pointer, i);
+    if (pbase + want > capacity) {
+      if (lg == 0) atomicOr(&tot->overflow, 1);
+      pub = false;
+    }
+  }
+
+  const float kInf = __int_as_float(0x7f800000);
+  float gx2[5], gy2[5], gz2[5];
+#pragma unroll
+  for (int o = 0; o < 5; o++) {
+    const int x = cx + o - 2, y = cy + o - 2, z = cz + o - 2;
+    const float ax = fmaxf(fmaxf(x * edge - me32.x, me32.x - (x + 1) * edge) - pad, 0.f);
+    const float ay = fmaxf(fmaxf(y * edge - me32.y, me32.y - (y + 1) * edge) - pad, 0.f);
+    const float az = fmaxf(fmaxf(z * edge - me32.z, me32.z - (z + 1) * edge) - pad, 0.f);
+    gx2[o] = (active && x >= 0 && x < g.nx) ? ax * ax : kInf;
+    gy2[o] = (active && y >= 0 && y < g.ny) ? ay * ay : kInf;
+    gz2[o] = (active && z >= 0 && z < g.nz) ? az * az : kInf;
+  }
+  int count = 0;
+  double4 me = make_double4(0, 0, 0, 0);
+  bool have_me = false;
+
+#pragma unroll
+  for (int dz = 0; dz < 5; dz++) {
+#pragma unroll
+    for (int dy = 0; dy < 5; dy++) {
+      const float rem = hi_f - gz2[dz] - gy2[dy];
+      const bool run = gx2[2] < rem;
+      if (!__any_sync(0xffffffffu, run)) continue;
+      uint32_t m = 0, m_end = 0, delta = 0;
+      if (run) {
+        const int xa = cx - ((gx2[0] < rem) ? 2 : (gx2[1] < rem) ? 1 : 0);
+        const int xb = cx + ((gx2[4] < rem) ? 2 : (gx2[3] < rem) ? 1 : 0);
+        const int rowc = ((cz + dz - 2) * g.ny + (cy + dy - 2)) * g.nx;
+        m = cell_start[rowc + xa] + lg;
+        m_end = cell_start[rowc + xb + 1];
+        const uint2 e = mytab[(cy + dy - 2) * kTileYTab + dz];
+        delta = (uint32_t)dy * cap_y + e.y - e.x;  // region-local index = sorted index + delta (mod 2^32)
+      }
+      while (__any_sync(0xffffffffu, m < m_end)) {
+        bool hit = false;
+        int j = 0;
+        if (m < m_end) {
+          const float4 c32 = sorted_pos32[m];
+          j = __float_as_int(c32.w);
+          const float dx = me32.x - c32.x, dy_ = me32.y - c32.y, dz_ = me32.z - c32.z;
+          const float r2f = fmaf(dz_, dz_, fmaf(dy_, dy_, dx * dx));
+          if (r2f < hi_f) {
+            if (r2f < lo_f && r2f > margin) {
+              hit = true;
+            } else {
+              if (!have_me) { me = sorted_pos[s]; have_me = true; }
+              const double4 cj = sorted_pos[m];
+              const double ddx = me.x - cj.x, ddy = me.y - cj.y, ddz = me.z - cj.z;
+              hit = (j != i) && (fma(ddz, ddz, fma(ddy, ddy, ddx * ddx)) < sl2);
+            }
+          }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit) & gbits;
+        const int pos = count + __popc(ballot & lt_mask);
+        if (hit && pos < want) {
+          // fake (LJ_TILE_FAKE, timing experiment only): a bank-conflict-free index pattern
+          tl_list[base + pos] = fake ? (uint16_t)((pos & 7) + ((s & 1) << 3) + (((pos >> 3) & 3) << 4))
+                                     : (uint16_t)(m + delta);
+          if (pub) list[pbase + pos] = j;
+        }
+        count += __popc(ballot);
+        m += GL;
+      }
+    }
+  }
+  if (active) {
+    if (count != want) {  // cannot happen unless the CSR arrays were not built from these positions
+      if (lg == 0) atomicOr(&tot->overflow, 8);
+    }
+    const uint16_t dummy = (uint16_t)(cap_y - 1);  // last record of the dy = 0 ring slot: far-away point
+    const int padded = ((want + 7) >> 3) << 3;
+    for (int k = min(count, want) + lg; k < padded; k += GL) tl_list[base + k] = dummy;
+  }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+k_tile_permute(const void* __restrict__ q, int64_t plane, const int32_t* __restrict__ order,
+               int64_t pn, double* __restrict__ qs, int* __restrict__ unit_counter) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) *unit_counter = 0;  // the force kernel that follows deals its work units from here
+  if (s >= pn) return;
+  double x, y, z;
+  load_pos<LAYOUT>(q, order[s], plane, x, y, z);
+  qs[3 * s] = x; qs[3 * s + 1] = y; qs[3 * s + 2] = z;
+}
+
 int64_t blocks_for(int64_t n, int tb) { return (n + tb - 1) / tb; }
 
 }  // namespace
@@ -697,7 +904,12 @@ int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t p
 
 // --------------------------------------------------------------------------- build -----
 template <int LAYOUT>
-static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) {
+static int cluster_fill(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool emit);
+
+// *deferred (in: the caller would like to run the FILL pass itself; out: it has to): the COUNT pass
+// and the scans are done, sorted_list is still unwritten.
+template <int LAYOUT>
+static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool* deferred) {
   const int64_t pn = a->pn;
   int rc = lj_scratch_reserve(ctx, pn, st);
   if (rc) return rc;
@@ -742,6 +954,7 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
   }
   const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
   const uint32_t* nop_u = reinterpret_cast<const uint32_t*>(a->number_of_partners);
+  ctx->tl_valid = false;  // the cell-sort scratch and any mirror derived from it are rebuilt below
   // any list these arrays were mirrored by is stale from here on
   if (ctx->cl_valid && (ctx->cl_id_list == a->sorted_list || ctx->cl_id_nop == a->number_of_partners ||
                         ctx->cl_id_ptr == a->pointer))
@@ -810,17 +1023,10 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
       ctx->graph_loop = -1;  // see above
       LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->cl_list, sizeof(uint32_t) * ctx->cl_cap, ctx->pool, st));
     }
-    if (a->pointer64)
-      k_search_cluster<true, true, LAYOUT><<<cblocks, 256, 0, st>>>(
-          a->q, a->plane_stride, pn, ge, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2, a->half, r0,
-          r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity,
-          emit ? ctx->cl_cnt : nullptr, ctx->cl_ptr, ctx->cl_list, ctx->cl_cap, ctx->totals);
-    else
-      k_search_cluster<true, false, LAYOUT><<<cblocks, 256, 0, st>>>(
-          a->q, a->plane_stride, pn, ge, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2, a->half, r0,
-          r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity,
-          emit ? ctx->cl_cnt : nullptr, ctx->cl_ptr, ctx->cl_list, ctx->cl_cap, ctx->totals);
-    LJ_LAUNCHED(ctx);
+    if (*deferred && !emit) return LJ_OK;  // the cell-tile fill pass writes sorted_list as well
+    *deferred = false;
+    rc = cluster_fill<LAYOUT>(ctx, a, st, emit);
+    if (rc) return rc;
     if (emit) {
       ctx->cl_valid = true;
       ctx->cl_id_list = a->sorted_list; ctx->cl_id_nop = a->number_of_partners; ctx->cl_id_ptr = a->pointer;
@@ -829,6 +1035,7 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
     return LJ_OK;
   }
 
+  *deferred = false;
   const unsigned search_blocks = (unsigned)blocks_for(pn * kSearchLanes, 256);
   k_search<false, false><<<search_blocks, 256, 0, st>>>(
       pn, ge, ctx->cell_of, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2,
@@ -861,6 +1068,160 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) 
   return LJ_OK;
 }
 
+
+template <int LAYOUT>
+static int cluster_fill(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool emit) {
+  const int64_t pn = a->pn;
+  int64_t r0 = a->row_begin, r1 = a->row_end;
+  if (r0 == 0 && r1 == 0) r1 = pn;
+  grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
+  float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
+  const double sl2 = a->search_len * a->search_len;
+  const int64_t nc = (r1 - r0 + 3) / 4;
+  const unsigned cblocks = (unsigned)blocks_for(nc * kSearchLanes, 256);
+  if (a->pointer64)
+    k_search_cluster<true, true, LAYOUT><<<cblocks, 256, 0, st>>>(
+        a->q, a->plane_stride, pn, ge, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2, a->half, r0,
+        r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity,
+        emit ? ctx->cl_cnt : nullptr, ctx->cl_ptr, ctx->cl_list, ctx->cl_cap, ctx->totals);
+  else
+    k_search_cluster<true, false, LAYOUT><<<cblocks, 256, 0, st>>>(
+        a->q, a->plane_stride, pn, ge, ctx->cell_start, ctx->sorted_pos, sorted_pos32, sl2, a->half, r0,
+        r1, a->number_of_partners, a->pointer, a->sorted_list, a->capacity,
+        emit ? ctx->cl_cnt : nullptr, ctx->cl_ptr, ctx->cl_list, ctx->cl_cap, ctx->totals);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+// ------------------------------------------------------------------ cell-tile mirror: host
+// Runs right after build_list_impl on the same stream: the cell-sort scratch (cell_of, cell_start,
+// sorted_pos*) still describes a->q.  Two small read-backs: the tile count (sizes the per-tile
+// table and the list) and the per-tile maxima (size the force kernel's shared memory).
+static int tile_alloc(lj_ctx* ctx, void** ptr, size_t bytes, cudaStream_t st) {
+  if (*ptr) LJ_CUDA(ctx, cudaFreeAsync(*ptr, st));
+  *ptr = nullptr;
+  LJ_CUDA(ctx, cudaMallocAsync(ptr, bytes, ctx->pool, st));
+  ctx->graph_loop = -1;  // a cached CUDA graph may hold the old pointer
+  return LJ_OK;
+}
+
+static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool fill_public,
+                             bool* filled_public) {
+  *filled_public = false;
+  const int64_t pn = a->pn;
+  int64_t r0 = a->row_begin, r1 = a->row_end;
+  if (r0 == 0 && r1 == 0) r1 = pn;
+  grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
+  float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
+  int rc;
+  if (!ctx->tl_geom) {
+    LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->tl_geom, sizeof(lj_tile_geom), ctx->pool, st));
+    LJ_CUDA(ctx, cudaHostAlloc((void**)&ctx->tl_geom_host, sizeof(lj_tile_geom), cudaHostAllocDefault));
+  }
+  if (pn > ctx->tl_pn_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_order, sizeof(int32_t) * pn, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cnt, sizeof(int32_t) * pn, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_units, sizeof(uint32_t) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_off, sizeof(uint32_t) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_meta, sizeof(int4) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_qs, 24 * (size_t)(pn + 2), st))) return rc;
+    LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_qs, 0, 24 * (size_t)(pn + 2), st));
+    ctx->tl_pn_cap = pn;
+  }
+  static const int target_rows = [] {
+    const char* e = getenv("LJ_TILE_ROWS");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 40;
+  }();
+  k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
+  LJ_LAUNCHED(ctx);
+  k_tile_rows<<<(unsigned)blocks_for(pn + 1, 256), 256, 0, st>>>(pn, sorted_pos32, a->number_of_partners,
+                                                                  ctx->tl_order, ctx->tl_cnt, ctx->tl_units);
+  LJ_LAUNCHED(ctx);
+  const unsigned tiles = (unsigned)blocks_for(pn + 1, kScanTile);
+  k_scan_reduce<<<tiles, kScanThreads, 0, st>>>(ctx->tl_units, pn + 1, nullptr, ctx->scan_tmp);
+  LJ_LAUNCHED(ctx);
+  k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, tiles, &ctx->tl_geom->total_units);
+  LJ_LAUNCHED(ctx);
+  k_scan_down<uint32_t><<<tiles, kScanThreads, 0, st>>>(ctx->tl_units, pn + 1, nullptr, ctx->scan_tmp,
+                                                         ctx->tl_off);
+  LJ_LAUNCHED(ctx);
+  k_tile_meta<<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(pn, ctx->tl_order, ctx->tl_cnt, ctx->tl_off, ctx->tl_meta);
+  LJ_LAUNCHED(ctx);
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_geom_host, ctx->tl_geom, sizeof(lj_tile_geom), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->totals_host->overflow) { *filled_public = true; return LJ_OK; }  // reported by lj_list_result; nothing to fill
+  lj_tile_geom g = *ctx->tl_geom_host;
+  if (g.total_units >= 0xffffffffull) return LJ_OK;  // 32-bit unit offsets: no mirror, per-row kernels serve
+  const int64_t ncell1 = (int64_t)g.nx * g.ny * g.nz + 1;
+  if (ncell1 > ctx->tl_cells_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cell_start, sizeof(uint32_t) * ncell1, st))) return rc;
+    ctx->tl_cells_cap = ncell1;
+  }
+  if (g.ntiles > ctx->tl_tab_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_tab, sizeof(uint2) * kTileYTab * (size_t)g.ntiles, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_ttab, sizeof(uint4) * kTileTTab * (size_t)g.ntiles, st))) return rc;
+    ctx->tl_tab_cap = g.ntiles;
+  }
+  if ((int64_t)g.total_units + 2 > ctx->tl_list_cap) {
+    const int64_t cap = (int64_t)g.total_units + (int64_t)g.total_units / 32 + 1024;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_list, 16 * (size_t)cap, st))) return rc;
+    ctx->tl_list_cap = cap;
+  }
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_cell_start, ctx->cell_start, sizeof(uint32_t) * ncell1,
+                               cudaMemcpyDeviceToDevice, st));
+  k_tile_table<<<(unsigned)blocks_for(g.ntiles, 128), 128, 0, st>>>(ctx->tl_cell_start, ctx->tl_off,
+                                                                     ctx->tl_geom, ctx->tl_tab, ctx->tl_ttab);
+  LJ_LAUNCHED(ctx);
+  const unsigned fblocks = (unsigned)blocks_for(pn * kSearchLanes, 256);
+#define LJ_TILE_FILL(PUB, P64)                                                                        \
+  k_tile_fill<PUB, P64><<<fblocks, 256, 0, st>>>(                                                     \
+      pn, ge, ctx->tl_geom, ctx->cell_of, ctx->tl_cell_start, ctx->sorted_pos, sorted_pos32,          \
+      a->search_len * a->search_len, ctx->tl_cnt, ctx->tl_off, ctx->tl_tab, ctx->tl_list, ctx->totals, \
+      a->pointer, a->sorted_list, a->capacity, getenv("LJ_TILE_FAKE") ? 1 : 0)
+  if (!fill_public) LJ_TILE_FILL(false, false);
+  else if (a->pointer64) LJ_TILE_FILL(true, true);
+  else LJ_TILE_FILL(true, false);
+#undef LJ_TILE_FILL
+  LJ_LAUNCHED(ctx);
+  *filled_public = fill_public;
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_geom_host, ctx->tl_geom, sizeof(lj_tile_geom), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->totals_host->overflow & 8)
+    return lj_set_error(ctx, LJ_ERR_INVALID_LIST, "lj_build_list", "cell-tile mirror disagrees with the CSR list");
+  if (ctx->totals_host->overflow) return LJ_OK;  // capacity problems are reported by lj_list_result
+  g = *ctx->tl_geom_host;
+  if (getenv("LJ_TILE_DEBUG"))
+    fprintf(stderr, "[lj] cell-tile mirror: grid %dx%dx%d, %d cells per tile, %d tiles, max rows %d, y-row %d, "
+            "list units %d, y slot %zu B, list slot %zu B, %llu units total\n", g.nx, g.ny, g.nz, g.tc,
+            g.ntiles, g.max_rows, g.max_yrow, g.max_units, lj_celltile_yslot_bytes(g),
+            lj_celltile_lslot_bytes(g), g.total_units);
+  // too dense for 16-bit indices or for the shared-memory rings: no mirror, the per-row kernels serve
+  if (5 * lj_celltile_cap_y(g) >= 65536 ||
+      kTileMinYSlots * lj_celltile_yslot_bytes(g) + kTileMinLSlots * lj_celltile_lslot_bytes(g) > kTileSmemBudget)
+    return LJ_OK;
+  ctx->tl_g = g;
+  ctx->tl_valid = true;
+  ctx->tl_id_list = a->sorted_list; ctx->tl_id_nop = a->number_of_partners; ctx->tl_id_ptr = a->pointer;
+  ctx->tl_pn = pn; ctx->tl_r0 = r0; ctx->tl_r1 = r1;
+  ctx->graph_loop = -1;  // the geometry is baked into the launch parameters
+  return LJ_OK;
+}
+
+// positions of this step in cell order (the force kernel's TMA source)
+int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
+  const unsigned blocks = (unsigned)blocks_for(a->pn, 256);
+  switch (a->layout) {
+    case LJ_AOS_D3: k_tile_permute<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;
+    case LJ_AOS_D4: k_tile_permute<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;
+    default: k_tile_permute<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;
+  }
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
 int lj_sort_rows_launch(lj_ctx* ctx, int32_t* list, const int32_t* nop, const void* pointer,
                         int pointer64, int64_t pn, int64_t capacity, cudaStream_t st);
 
@@ -881,20 +1242,35 @@ extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number
   if (a->layout == LJ_SOA_D)
     LJ_REQUIRE(ctx, a->plane_stride >= a->pn, "lj_build_list: SoA plane_stride < particle_number");
   int rc;
+  const bool tiles = (a->flags & LJ_LIST_TILES) && !a->half && a->layout != LJ_AOS_F4;
+  bool deferred = tiles;  // let the cell-tile fill pass write sorted_list too, if the engine allows
   switch (a->layout) {
-    case LJ_AOS_D3: rc = build_list_impl<LJ_AOS_D3>(ctx, a, st); break;
+    case LJ_AOS_D3: rc = build_list_impl<LJ_AOS_D3>(ctx, a, st, &deferred); break;
     case LJ_AOS_D4:
       LJ_REQUIRE(ctx, (uintptr_t)a->q % 32 == 0, "lj_build_list: double4 array must be 32-byte aligned");
-      rc = build_list_impl<LJ_AOS_D4>(ctx, a, st);
+      rc = build_list_impl<LJ_AOS_D4>(ctx, a, st, &deferred);
       break;
-    case LJ_SOA_D: rc = build_list_impl<LJ_SOA_D>(ctx, a, st); break;
+    case LJ_SOA_D: rc = build_list_impl<LJ_SOA_D>(ctx, a, st, &deferred); break;
     case LJ_AOS_F4:
       LJ_REQUIRE(ctx, (uintptr_t)a->q % 16 == 0, "lj_build_list: float4 array must be 16-byte aligned");
-      rc = build_list_impl<LJ_AOS_F4>(ctx, a, st);
+      rc = build_list_impl<LJ_AOS_F4>(ctx, a, st, &deferred);
       break;
     default: return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_build_list", "unknown layout");
   }
   if (rc) return rc;
+  if (tiles) {
+    bool filled = false;
+    rc = build_tile_mirror(ctx, a, st, deferred, &filled);
+    if (rc) return rc;
+    if (deferred && !filled) {  // no mirror after all: the regular FILL pass
+      switch (a->layout) {
+        case LJ_AOS_D3: rc = cluster_fill<LJ_AOS_D3>(ctx, a, st, false); break;
+        case LJ_AOS_D4: rc = cluster_fill<LJ_AOS_D4>(ctx, a, st, false); break;
+        default: rc = cluster_fill<LJ_SOA_D>(ctx, a, st, false); break;
+      }
+      if (rc) return rc;
+    }
+  }
   if (a->flags & LJ_LIST_SORT_ROWS) {
     rc = lj_sort_rows_launch(ctx, a->sorted_list, a->number_of_partners, a->pointer, a->pointer64,
                              a->pn, a->capacity, st);
@@ -958,6 +1334,7 @@ extern "C" int lj_shuffle_rows(lj_ctx* ctx, int32_t* sorted_list, const int32_t*
   // the cluster mirror stays correct as a SET, but drop it so that a shuffled list really is
   // consumed in its shuffled order
   if (ctx->cl_id_list == sorted_list) ctx->cl_valid = false;
+  if (ctx->tl_id_list == sorted_list) ctx->tl_valid = false;
   cudaStream_t st = lj_stream(ctx, stream);
   const unsigned blocks = (unsigned)blocks_for(pn, 256);
   if (pointer64) k_shuffle_rows<true><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, seed);

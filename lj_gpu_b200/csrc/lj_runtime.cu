@@ -93,11 +93,13 @@ int lj_ctx_destroy(lj_ctx* ctx) {
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   void* frees[] = {ctx->bbox, ctx->grid, ctx->totals, ctx->cell_of, ctx->cell_slot, ctx->cell_count,
                    ctx->cell_start, ctx->sorted_pos, ctx->sorted_tmp, ctx->scan_tmp, ctx->q32,
-                   ctx->cl_list, ctx->cl_ptr, ctx->cl_cnt};
+                   ctx->cl_list, ctx->cl_ptr, ctx->cl_cnt, ctx->tl_geom, ctx->tl_order, ctx->tl_cnt,
+                   ctx->tl_units, ctx->tl_off, ctx->tl_qs, ctx->tl_cell_start, ctx->tl_list, ctx->tl_tab, ctx->tl_ttab, ctx->tl_meta};
   for (void* f : frees)
     if (f) cudaFreeAsync(f, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->totals_host) cudaFreeHost(ctx->totals_host);
+  if (ctx->tl_geom_host) cudaFreeHost(ctx->tl_geom_host);
   for (int k = 0; k < 2; k++) {
     if (ctx->ring[k]) cudaFreeHost(ctx->ring[k]);
     if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
@@ -126,6 +128,7 @@ int lj_sync(lj_ctx* ctx, void* stream) {
 int lj_list_invalidate(lj_ctx* ctx) {
   if (!ctx) return LJ_ERR_BAD_ARG;
   ctx->cl_valid = false;
+  ctx->tl_valid = false;
   return LJ_OK;
 }
 
@@ -308,6 +311,15 @@ int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int use_grap
       warm.row_begin = args->row_begin;
       warm.row_end = args->row_begin + 32 < args->row_end ? args->row_begin + 32 : args->row_end;
     }
+    {  // the cell-tile kernel only runs on the row range of its mirror: warm it with a full, neutral step
+      int64_t r0 = args->row_begin, r1 = args->row_end;
+      if (r0 == 0 && r1 == 0) r1 = args->pn;
+      if ((args->variant == LJ_VARIANT_CELLTILE || args->variant == LJ_VARIANT_AUTO) &&
+          lj_celltile_usable(ctx, args, r0, r1)) {
+        warm.row_begin = args->row_begin;
+        warm.row_end = args->row_end;
+      }
+    }
     int rc = lj_force_launch(ctx, &warm, st);
     if (rc) return rc;
     LJ_CUDA(ctx, cudaStreamSynchronize(st));
@@ -377,6 +389,11 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
     la.flags = m->list_flags;
     if (!m->half && m->variant == LJ_VARIANT_CLUSTER)
       la.flags |= LJ_LIST_CLUSTERS;
+    // the cell-tile mirror serves FP64 steps on lists the library builds itself; below a few
+    // hundred thousand particles the per-row kernels are faster and the mirror is not built
+    if (!m->half && own_list && m->precision == LJ_PREC_FP64 && m->layout != LJ_AOS_F4 &&
+        (m->variant == LJ_VARIANT_CELLTILE || (m->variant == LJ_VARIANT_AUTO && pn >= 300000)))
+      la.flags |= LJ_LIST_TILES;
     if (own_list) {
       // first build sizes the list: count pass only needs capacity 0 to learn the total
       la.sorted_list = nullptr; la.capacity = 0;

@@ -667,3 +667,133 @@ def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
         pmx = torch.zeros_like(qd)
         ctx.force_loop(qd, pmx, full, loop=3, group=8, precision="mixed", variant=variant)
         assert np.abs(pmx.cpu().numpy()[:, :3] - p_o).max() / scale < TOL_MIXED
+
+
+# ------------------------------------------------------------------------ cell-tile mirror
+def _rows_as_sets(nop, ptr, lst, pn):
+    rows = np.repeat(np.arange(pn, dtype=np.int64), nop[:pn])
+    order = np.lexsort((lst, rows))
+    return rows[order] * pn + lst[order]
+
+
+@pytest.mark.parametrize("layout", ["aos4", "aos3", "soa"])
+def test_celltile_force_and_list_match_oracle(ctx, torch, sysS, layout):
+    """lj_build_list(LJ_LIST_TILES) + LJ_VARIANT_CELLTILE: the list the tile fill pass writes is the
+    oracle's list, the shared-memory force kernel reproduces the oracle's momenta, and (same list
+    order, same lane mapping) its result is bit-identical to the per-row kernel with group = 8."""
+    s = sysS
+    qd, pd = s.device_arrays(torch, layout)
+    npn = s.pn if layout == "soa" else None
+    pl = ctx.makepair(qd, layout=layout, pn=npn, tiles=True)
+    nop, ptr, lst = list_to_host(pl)
+    assert pl.number_of_pairs == len(s.full[2])
+    assert np.array_equal(nop[:s.pn], s.full[0]) and np.array_equal(ptr[:s.pn], s.full[1])
+    assert np.array_equal(_rows_as_sets(nop, ptr, lst, s.pn), _rows_as_sets(s.full[0], s.full[1], s.full[2], s.pn))
+    launches = ctx.launches
+    ctx.force_loop(qd, pd, pl, loop=s.steps, layout=layout, pn=npn, variant="celltile")
+    assert ctx.launches - launches == 2 * s.steps          # position permute + force kernel
+    assert s.err(pd, layout) < TOL_FP64
+    pr = torch.zeros_like(pd)
+    if layout == "aos4":
+        pr[:, 3] = 77.5
+        assert float(pd[:, 3].min()) == 77.5 == float(pd[:, 3].max())   # .w of p survives
+    ctx.force_loop(qd, pr, pl, loop=s.steps, layout=layout, pn=npn, variant="subwarp", group=8)
+    assert torch.equal(pd, pr)
+
+
+def test_celltile_random_cloud_and_clusters_of_particles(ctx, torch, oracle):
+    """No lattice: a uniform random cloud with a denser blob and an empty region (tiles with very
+    different row counts, empty cells, empty tiles), particle order without spatial coherence."""
+    from lj_gpu_b200 import LJError
+    rng = np.random.default_rng(12)
+    a = rng.uniform(0.0, 18.0, size=(2600, 3))
+    a = a[~((a[:, 0] > 6) & (a[:, 0] < 11) & (a[:, 1] < 9))]          # a hole
+    blob = rng.normal(loc=(14.0, 14.0, 4.0), scale=1.6, size=(220, 3))
+    q = np.ascontiguousarray(np.concatenate([a, blob]))
+    rng.shuffle(q)
+    pn = len(q)
+    nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
+    qd = torch.from_numpy(q).cuda()
+    pl = ctx.makepair(qd, layout="aos3", tiles=True)
+    nop, ptr, lst = list_to_host(pl)
+    assert np.array_equal(nop[:pn], nop_o)
+    assert np.array_equal(_rows_as_sets(nop, ptr, lst, pn), _rows_as_sets(nop_o, ptr_o, lst_o, pn))
+    # forces: the two GPU kernels bit for bit on this list (close random pairs make huge but finite
+    # numbers; both kernels evaluate the same expression in the same order)
+    p1 = torch.zeros_like(qd); p2 = torch.zeros_like(qd)
+    ctx.force_step(qd, p1, pl, layout="aos3", variant="celltile", dt=1e-9)
+    ctx.force_step(qd, p2, pl, layout="aos3", variant="subwarp", group=8, dt=1e-9)
+    assert torch.equal(p1, p2)
+    # far too dense for the shared-memory rings (rows of > 1000 partners): the build still delivers
+    # the list, there is silently no mirror, AUTO runs the per-row kernel
+    blob = rng.normal(loc=(9.0, 9.0, 9.0), scale=0.8, size=(900, 3))
+    q = np.ascontiguousarray(np.concatenate([a, blob]))
+    nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
+    qd = torch.from_numpy(q).cuda()
+    pl = ctx.makepair(qd, layout="aos3", tiles=True)
+    nop, ptr, lst = list_to_host(pl)
+    assert np.array_equal(_rows_as_sets(nop, ptr, lst, len(q)), _rows_as_sets(nop_o, ptr_o, lst_o, len(q)))
+    p1 = torch.zeros_like(qd)
+    with pytest.raises(LJError):
+        ctx.force_step(qd, p1, pl, layout="aos3", variant="celltile", dt=1e-9)
+    ctx.force_step(qd, p1, pl, layout="aos3", dt=1e-9)
+
+
+def test_celltile_moving_particles_rebuild_and_row_ranges(ctx, torch, sysS):
+    """The mirror is a LIST: it stays valid while particles move (positions are re-permuted every
+    step), it is rebuilt with the list, and it serves exactly the row range it was built for."""
+    from lj_gpu_b200 import LJError
+    s = sysS
+    qd, pd = s.device_arrays(torch, "aos4")
+    qr, pr = qd.clone(), pd.clone()
+    pl = ctx.makepair(qd, tiles=True)
+    plr = ctx.makepair(qr)
+    pl = ctx.makepair(qd, tiles=True)                    # the plain build above dropped the mirror
+    for step in range(12):                                # kick + drift, list reused (skin 0.3)
+        ctx.force_step(qd, pd, pl, variant="celltile")
+        ctx.drift(qd, pd)
+        ctx.force_step(qr, pr, plr, variant="subwarp", group=8)
+        ctx.drift(qr, pr)
+        if step == 5:                                     # rebuild both lists in place mid-run
+            ctx.rebuild(qr, plr)
+            ctx.rebuild(qd, pl, tiles=True)
+    assert torch.equal(qd, qr) and torch.equal(pd, pr)
+    # a rebuild without the flag leaves no mirror: explicit request fails, AUTO falls back
+    ctx.rebuild(qd, pl)
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl, variant="celltile")
+    ctx.force_step(qd, pd, pl)
+    # partial row range at build time (ghost particles are candidates only)
+    qd, pd = s.device_arrays(torch, "aos4")
+    own = s.pn // 3 + 1
+    plo = ctx.makepair(qd, tiles=True, rows=(0, own))
+    ctx.force_loop(qd, pd, plo, loop=s.steps, variant="celltile", rows=(0, own))
+    ph = pd.cpu().numpy()[:, :3]
+    assert np.abs(ph[:own] - s.p[:own]).max() / s.scale < TOL_FP64 and np.all(ph[own:] == 0)
+    with pytest.raises(LJError):                          # another row range: no mirror for it
+        ctx.force_step(qd, pd, plo, variant="celltile", rows=(0, own - 1))
+    ctx.force_step(qd, pd, plo, rows=(0, own - 1))       # AUTO: per-row kernel
+    # half lists and float4 positions have no mirror; the flag is ignored, the build still works
+    plh = ctx.makepair(qd, half=True, tiles=True)
+    assert plh.number_of_pairs == len(s.half[2])
+
+
+def test_celltile_large_system_matches_per_row_kernel(ctx, torch):
+    """N = 108k (rho = 1.0, L = 48): thousands of tiles, every SM walks several column segments."""
+    from lj_gpu_b200 import init_fcc
+    q = init_fcc(1.0, 48.0)
+    pn = len(q)
+    q4 = np.zeros((pn, 4)); q4[:, :3] = q
+    qd = torch.from_numpy(q4).cuda()
+    pl = ctx.makepair(qd, tiles=True)
+    p1 = torch.zeros_like(qd); p2 = torch.zeros_like(qd)
+    ctx.force_loop(qd, p1, pl, loop=3, variant="celltile")
+    ctx.force_loop(qd, p2, pl, loop=3, variant="subwarp", group=8)
+    assert torch.equal(p1, p2)
+    plain = ctx.makepair(qd)                              # cluster-engine fill: same list as a set
+    assert plain.number_of_pairs == pl.number_of_pairs
+    assert torch.equal(plain.number_of_partners, pl.number_of_partners)
+    rows = torch.repeat_interleave(torch.arange(pn, device="cuda"), plain.number_of_partners[:pn].long())
+    ka = torch.sort(rows * pn + plain.sorted_list[:plain.number_of_pairs].long()).values
+    kb = torch.sort(rows * pn + pl.sorted_list[:pl.number_of_pairs].long()).values
+    assert torch.equal(ka, kb)

@@ -24,9 +24,10 @@ else:
     qh = np.ascontiguousarray(q.T)
 npn = pn if a.layout == "soa" else None
 qd = torch.from_numpy(qh).cuda(); pd = torch.zeros_like(qd)
-pl = ctx.makepair(qd, layout=a.layout, pn=npn, sort_rows=a.sort_rows, clusters=(a.variant == "cluster"))
+tiles = a.variant in ("celltile", "auto")
+pl = ctx.makepair(qd, layout=a.layout, pn=npn, sort_rows=a.sort_rows, clusters=(a.variant == "cluster"), tiles=tiles)
 for _ in range(a.rebuild):
-    ctx.rebuild(qd, pl, layout=a.layout, pn=npn, sort_rows=a.sort_rows, clusters=(a.variant == "cluster"))
+    ctx.rebuild(qd, pl, layout=a.layout, pn=npn, sort_rows=a.sort_rows, clusters=(a.variant == "cluster"), tiles=tiles)
 for _ in range(a.steps):
     ctx.force_step(qd, pd, pl, layout=a.layout, pn=npn, variant=a.variant, group=a.group, precision=a.prec, threads_per_block=a.tb)
 torch.cuda.synchronize()
