@@ -9,5 +9,6 @@ python bench.py --steps 200 --warmup 20 > gpurun_out/bench_final.json 2> gpurun_
 kill $SMI
 cat gpurun_out/bench_final.json
 $NCU --metrics gpu__time_duration.sum -s 60 -c 400 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 200 --warmup 20 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
-$NCU --set full --import-source on -k regex:lj_gather_csr -s 2 -c 1 -f -o gpurun_out/prof_final_gather python tools/prof_target.py --variant auto --steps 4 > gpurun_out/p1.log 2>&1; echo "full rc=$?"
-$NCU --set full --import-source on -k regex:k_search_cluster -s 2 -c 2 -f -o gpurun_out/prof_final_search python tools/prof_target.py --steps 0 --rebuild 1 > gpurun_out/p2.log 2>&1; echo "full rc=$?"
+$NCU --set full --import-source on -k regex:lj_celltile_force -s 2 -c 1 -f -o gpurun_out/prof_final_celltile python tools/prof_target.py --variant auto --steps 4 > gpurun_out/p1.log 2>&1; echo "full rc=$?"
+$NCU --set full --import-source on -k regex:lj_gather_csr -s 2 -c 1 -f -o gpurun_out/prof_final_gather python tools/prof_target.py --variant subwarp --group 8 --steps 4 > gpurun_out/p3.log 2>&1; echo "full rc=$?"
+$NCU --set full --import-source on -k "regex:k_search_cluster|k_tile_fill" -s 2 -c 2 -f -o gpurun_out/prof_final_search python tools/prof_target.py --variant auto --steps 0 --rebuild 1 > gpurun_out/p2.log 2>&1; echo "full rc=$?"
