@@ -139,7 +139,8 @@ def exchange_halo(q_local, plan, dist, async_op: bool = False):
 # GPU execution (one process per GPU, torchrun)
 # ------------------------------------------------------------------------------------------
 class DecomposedSystem:
-    def __init__(self, density: float, L: float, halo_mode: str = "nccl", search_len: float = 3.3):
+    def __init__(self, density: float, L: float, halo_mode: str = "nccl", search_len: float = 3.3,
+                 tiles: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -167,7 +168,11 @@ class DecomposedSystem:
         self.p = torch.zeros_like(self.q)
         self.compute = torch.cuda.current_stream()
         self.comm = torch.cuda.Stream()
-        self.pl = self.ctx.makepair(self.q, rows=(0, self.slab.n_own), search_len=search_len)
+        # tiles: also build the cell-tile mirror for the owned rows; the halo-then-force schedule
+        # (one launch over rows [0, n_own)) then runs the shared-memory kernel, the overlapped
+        # schedule (row sub-ranges) the per-row kernel
+        self.tiles = tiles
+        self.pl = self.ctx.makepair(self.q, rows=(0, self.slab.n_own), search_len=search_len, tiles=tiles)
         self.search_len = search_len
         self.pairs_local = self.pl.number_of_pairs
         self.peer_ptr = {}
@@ -231,7 +236,8 @@ class DecomposedSystem:
             ctx.force_step(self.q, self.p, self.pl, rows=(0, s.n_own), **fkw)
 
     def rebuild(self):
-        self.ctx.rebuild(self.q, self.pl, search_len=self.search_len, rows=(0, self.slab.n_own))
+        self.ctx.rebuild(self.q, self.pl, search_len=self.search_len, rows=(0, self.slab.n_own),
+                         tiles=self.tiles)
 
     def run(self, steps: int, rebuild_every: int, first_step: int = 0, overlap: bool = True, **fkw):
         for k in range(first_step, first_step + steps):
@@ -266,7 +272,8 @@ def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_p
         n = int(os.environ["LJ_BENCH_CELLS"])
     L = (n + 0.05) * s
     halo_mode = os.environ.get("LJ_HALO", "p2p")
-    system = DecomposedSystem(density, L, halo_mode=halo_mode)
+    tiles = args.variant in ("auto", "celltile") and args.prec == "fp64"
+    system = DecomposedSystem(density, L, halo_mode=halo_mode, tiles=tiles)
     halo_mode = system.halo_mode
     fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
                threads_per_block=args.threads_per_block)

@@ -18,11 +18,15 @@ def _worker(rank, world, port, mode, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from lj_gpu_b200 import decomp
-    system = decomp.DecomposedSystem(DENSITY, L, halo_mode=mode)
+    tiles = mode.endswith("-tiles")   # cell-tile mirror per slab, halo-then-force schedule
+    system = decomp.DecomposedSystem(DENSITY, L, halo_mode=mode.split("-")[0], tiles=tiles)
     # ghosts start as garbage: they must come from the exchange
     system.q[system.slab.n_own:] = 1e6
     torch.cuda.synchronize(); dist.barrier()
-    system.run(STEPS, rebuild_every=10, first_step=1, variant="tile", group=8)
+    if tiles:
+        system.run(STEPS, rebuild_every=10, first_step=1, overlap=False, variant="celltile")
+    else:
+        system.run(STEPS, rebuild_every=10, first_step=1, variant="tile", group=8)
     torch.cuda.synchronize()
     p = system.gather_p()
     if rank == 0:
@@ -31,7 +35,7 @@ def _worker(rank, world, port, mode, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "p2p-tiles"])
 def test_two_gpu_decomposition_matches_single_gpu(mode, tmp_path):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
