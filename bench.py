@@ -196,7 +196,7 @@ def run_cuda(args):
     use_cl = args.variant == "cluster" and args.prec == "fp64"
     # "auto" on a list the library builds itself: the build also emits the cell-tile mirror and the
     # FP64 step runs on it (k_tile_permute + lj_celltile_force, two launches per step)
-    use_tiles = args.variant in ("auto", "celltile") and args.prec == "fp64"
+    use_tiles = args.variant in ("auto", "celltile")
     pl = ctx.makepair(qd, pointer64=False, clusters=use_cl, tiles=use_tiles)
     P = pl.number_of_pairs
     fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
@@ -237,6 +237,30 @@ def run_cuda(args):
     f1.record(stream)
     torch.cuda.synchronize()
     ms_force = f0.elapsed_time(f1) / nf
+    # ---- side measurement: the same force step in the mixed-precision mode north_star allows
+    #      (FP32 pair arithmetic on fixed-point positions, FP64 momenta; parity bound 1e-5), on the
+    #      same list, with its deviation from the FP64 kernel after 20 steps
+    mixed = None
+    if args.prec == "fp64":
+        try:
+            mkw = dict(fkw); mkw["precision"] = "mixed"
+            pm, pf = torch.zeros_like(qd), torch.zeros_like(qd)
+            ctx.force_loop(qd, pm, pl, loop=20, **mkw)
+            ctx.force_loop(qd, pf, pl, loop=20, **fkw)
+            torch.cuda.synchronize()
+            dev = ((pm - pf)[:, :3].abs().max() / pf[:, :3].abs().max()).item()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record(stream)
+            ctx.force_loop(qd, pm, pl, loop=nf, **mkw)
+            m1.record(stream)
+            torch.cuda.synchronize()
+            ms_mixed = m0.elapsed_time(m1) / nf
+            mixed = {"ms_per_launch": ms_mixed, "pairs_per_s_force_only": P / (ms_mixed * 1e-3),
+                     "max_rel_deviation_from_fp64_after_20_steps": dev, "bound_stated": 1e-5,
+                     "kernel": "k_tile_permute_fx + lj_celltile_force<mixed>" if use_tiles else "lj_gather_mixed"}
+            del pm, pf
+        except Exception as e:  # noqa: BLE001 -- the side measurement must not take the headline down
+            mixed = {"error": str(e)}
     # ---- one list rebuild alone
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record(stream)
@@ -316,13 +340,18 @@ def run_cuda(args):
                         "every 20) -> D2H p", "p_checksum": checksum},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ("force step (k_tile_permute + lj_celltile_force)" if use_tiles
+                     "kernel": ("force step (k_tile_permute + lj_celltile_force, %s)" % args.prec if use_tiles
                                 else "force step (lj_gather_*)"),
                      "algorithmic_bytes_per_launch": bytes_force,
                      "ms_per_launch": ms_force, "pairs_per_s_force_only": P / (ms_force * 1e-3),
                      "list_build_ms": ms_build,
                      "amortised_step_ms": ms_force + ms_build / REBUILD_EVERY},
     }
+    if mixed is not None and "ms_per_launch" in mixed:
+        # same algorithmic bytes: the caller's arrays are the same FP64 q/p and int32 list
+        mixed["roofline_frac"] = bytes_force / (mixed["ms_per_launch"] * 1e-3) / 1e9 / peak
+        mixed["amortised_step_ms"] = mixed["ms_per_launch"] + ms_build / REBUILD_EVERY
+    out["mixed_precision"] = mixed
     out["reference_config"] = ref_cfg
     if not args.no_cpu:
         r = cpu_reference_sample(20)

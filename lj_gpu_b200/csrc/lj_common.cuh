@@ -93,6 +93,8 @@ struct lj_ctx {
   uint32_t* tl_units = nullptr;          // [pn+1] padded row length, units of 8 entries
   uint32_t* tl_off = nullptr;            // [pn+1] exclusive scan of tl_units
   double* tl_qs = nullptr;               // [pn+2][3] positions in cell order, refreshed every step
+  int4* tl_qfx = nullptr;                // [pn+2] the same in 32-bit fixed point + original index (mixed precision)
+  int64_t tl_qfx_cap = 0;
   uint32_t* tl_cell_start = nullptr;     // [ncell+1] private copy of the cell offsets
   uint16_t* tl_list = nullptr;
   uint2* tl_tab = nullptr;               // [ntiles][6] y-row table (lj_celltile.cuh)
@@ -162,6 +164,26 @@ static inline size_t lj_celltile_lslot_bytes(const lj_tile_geom& g) {
   return (size_t)g.max_units * 16 + (size_t)g.max_rows * 16;
 }
 constexpr int kTileMinYSlots = 7, kTileMinLSlots = 2;  // five rows in use + two in flight; two lists
+
+// Fixed-point frame of the mixed-precision cell-tile kernel.  Coordinates are stored modulo 2^32
+// counts of `unit`, a power of two chosen from the cutoff alone so that every difference the force
+// needs is below 2^24 counts (its int -> float conversion is exact): cutoff 3.0 -> unit = 2^-22.
+// No bounding box, nothing to clamp, and the precision does not depend on the size of the system.
+// margin bounds |r2_f32 - r2_f64| near the cutoff: two half-count roundings per component
+// (delta) and the FP32 roundings of the three-term sum; doubled.
+struct lj_fx_frame { double scale, unit; float margin; };
+static inline lj_fx_frame lj_fx_frame_for(double cl2) {
+  const double c = sqrt(cl2);
+  int e = 0;
+  frexp(c, &e);  // c < 2^e
+  lj_fx_frame f;
+  f.unit = ldexp(1.0, e - 24);
+  f.scale = ldexp(1.0, 24 - e);
+  const double u = 5.9604644775390625e-8, dmax = 1.01 * c;
+  const double delta = f.unit + u * dmax;
+  f.margin = (float)(2.0 * (3.0 * (2.0 * dmax * delta + delta * delta) + 6.0 * u * dmax * dmax));
+  return f;
+}
 
 // ------------------------------------------------------------------------------------
 // Device helpers

@@ -476,12 +476,12 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
     if (a->precision == LJ_PREC_MIXED) return lj_force_mixed_launch(ctx, a, r0, r1, g, tb, st);
     return lj_force_cluster_launch(ctx, a, r0, r1, c24, c48, cl2_bits, st);
   }
-  // The cell-tile mirror (lj_build_list with LJ_LIST_TILES) serves FP64 calls on exactly the
+  // The cell-tile mirror (lj_build_list with LJ_LIST_TILES) serves FP64 and mixed calls on exactly the
   // arrays and row range it was built for; AUTO prefers it.
   if (a->variant == LJ_VARIANT_CELLTILE)
     LJ_REQUIRE(ctx, lj_celltile_usable(ctx, a, r0, r1),
                "lj_force_step: no cell-tile mirror for these arrays (build with LJ_LIST_TILES; CSR, "
-               "FP64, same row range)");
+               "double positions, same row range)");
   if ((a->variant == LJ_VARIANT_CELLTILE || (a->variant == LJ_VARIANT_AUTO && lj_celltile_worthwhile(ctx))) &&
       lj_celltile_usable(ctx, a, r0, r1))
     return lj_force_celltile_launch(ctx, a, c24, c48, cl2_bits, st);

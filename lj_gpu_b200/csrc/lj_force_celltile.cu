@@ -26,6 +26,7 @@
 // moving particles are handled exactly like in the per-row kernels: the list decides membership,
 // the current q decides the force.
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "lj_celltile.cuh"
@@ -36,13 +37,19 @@ namespace {
 #ifndef LJ_CT_CONSUMERS
 #define LJ_CT_CONSUMERS 16
 #endif
-constexpr int kCtConsumers = LJ_CT_CONSUMERS;        // consumer warps
-constexpr int kCtThreads = (kCtConsumers + 1) * 32;  // + one producer warp
-constexpr int kCtMaxStages = 8;
+constexpr int kCtConsumers = LJ_CT_CONSUMERS;  // consumer warps of the FP64 kernel (+ one producer warp)
+#ifndef LJ_CT_CONSUMERS_MX
+#define LJ_CT_CONSUMERS_MX 16
+#endif
+constexpr int kCtConsumersMx = LJ_CT_CONSUMERS_MX;  // default for the mixed-precision kernel
 #ifndef LJ_CT_UNROLL
 #define LJ_CT_UNROLL 4
 #endif
 constexpr int kCtUnroll = LJ_CT_UNROLL;
+#ifndef LJ_CT_UNROLL_MX
+#define LJ_CT_UNROLL_MX 4
+#endif
+constexpr int kCtUnrollMx = LJ_CT_UNROLL_MX;
 
 struct __align__(16) tile_hdr { int ns, self0; uint32_t u0; int yslot0; };
 
@@ -68,8 +75,16 @@ constexpr int kCtMaxY = 16, kCtMaxL = 8;
 constexpr int kCtMaxSeg = 32;  // tiles per unit (column segment) at most
 
 struct ct_params {
-  const double* qs; void* p; int64_t plane;
+  const unsigned char* qs;  // positions in cell order: packed double3 (FP64) or int4 fixed point (mixed)
+  void* p; int64_t plane;
   double c24, c48; long long cl2_bits;
+  // mixed precision only
+  const void* q;            // the caller's FP64 positions: exact cutoff decision of borderline pairs
+  const lj_grid_params* grid;
+  double cl2, fx_scale;     // counts per length (a power of two)
+  float c24u, c48u;         // 24 dt unit, 48 dt unit (the differences stay in counts)
+  float unit2, cl2f, lo_c;  // unit^2; the cutoff^2; r2 <= lo_c = cl2f - margin: inside for sure
+  float band;               // |r2 - cl2f| <= band: too close to call in FP32 (slightly above margin)
   const uint2* ytab; const uint4* ttab; const int4* meta; const uint16_t* list;
   int ntx, ny, ncols;    // tiles per pencil, cells in y, columns = ntx * nz
   int seg_len, nseg;     // a unit = one column x [seg*seg_len, min(ny, (seg+1)*seg_len))
@@ -87,9 +102,15 @@ struct ct_params {
 // and one arrive per tile (most warps have no quad in a given tile: that path must be short).  The
 // y-row ring is managed by the producer alone: a y-row's slot is free once the tile that had it as
 // its oldest row has been released.
-template <int LAYOUT>
-__global__ void __launch_bounds__(kCtThreads, 1)
+//
+// MX = mixed precision: the ring holds 16-byte fixed-point records {x, y, z, original index}
+// (one LDS.128 per pair instead of three LDS.64 on 24-byte records), differences are exact integer
+// subtractions, the pair arithmetic is FP32 and the per-row sums are reduced and added to p in
+// FP64 -- see the consumer loop.  Producer, rings and barriers are the same for both precisions.
+template <int LAYOUT, bool MX, int NCONS>
+__global__ void __launch_bounds__((NCONS + 1) * 32, 1)
 lj_celltile_force(const ct_params P) {
+  constexpr uint32_t RB = MX ? 16u : 24u;  // bytes per staged position record
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t tfull[kCtMaxL], tempty[kCtMaxL];
   __shared__ tile_hdr hdr[kCtMaxL];
@@ -99,25 +120,29 @@ lj_celltile_force(const ct_params P) {
   __shared__ __align__(16) uint2 ytab_s[2][(kCtMaxSeg + 4) * kTileYTab];
   __shared__ __align__(16) uint4 ttab_s[2][kCtMaxSeg * kTileTTab];
   __shared__ __align__(8) uint64_t tabbar[2];
+  __shared__ float kconst[8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ry = P.ry, rl = P.rl, cap_y = P.cap_y;
   unsigned char* const ybase = smem_raw;
-  unsigned char* const lbase = smem_raw + (size_t)ry * cap_y * 24;
+  unsigned char* const lbase = smem_raw + (size_t)ry * cap_y * RB;
   if (threadIdx.x == 0) {
-    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kCtConsumers); }
+    kconst[0] = P.unit2; kconst[1] = P.c24u; kconst[2] = P.c48u; kconst[3] = P.lo_c; kconst[4] = P.cl2f;
+    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NCONS); }
     mbar_init(&tabbar[0], 1); mbar_init(&tabbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < ry) {  // the dummy record of every y slot: its last one, no copy ever reaches it
-    double* d = reinterpret_cast<double*>(ybase) + ((size_t)threadIdx.x * cap_y + cap_y - 1) * 3;
-    d[0] = kTileFar; d[1] = kTileFar; d[2] = kTileFar;
+    if (!MX) {
+      double* d = reinterpret_cast<double*>(ybase) + ((size_t)threadIdx.x * cap_y + cap_y - 1) * 3;
+      d[0] = kTileFar; d[1] = kTileFar; d[2] = kTileFar;
+    }  // MX: fixed-point coordinates wrap, "far" depends on the unit -- the producer writes it
     yrel[threadIdx.x] = -1;
   }
   __syncthreads();
   const int nunits = P.ncols * P.nseg;
 
-  if (warp == kCtConsumers) {
+  if (warp == NCONS) {
     // ------------------------------------------------------------------ producer warp ---
     int yslot = 0;                       // next y-row slot (ring of ry)
     int tseq = 0, tslot = 0;             // tile being assembled: sequence number, slot (ring of rl)
@@ -157,6 +182,15 @@ lj_celltile_force(const ct_params P) {
       const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
       const int ntile = y1 - y0;
       const int tb = nu & 1;
+      // MX: the dummy record rows are padded with.  Fixed-point coordinates live modulo 2^32
+      // counts, so no point is far from everything; half a period away in z from this unit's
+      // cell layer is far from every row of the unit (all in z-cell cz, give or take the skin).
+      int dummy_z = 0;
+      if (MX) {
+        const int cz = (u % P.ncols) / P.ntx;
+        const double zc = P.grid->oz + ((double)cz + 0.5) / P.grid->inv_cell;
+        dummy_z = (int)((uint32_t)__double2ll_rn(zc * P.fx_scale) + 0x80000000u);
+      }
       __syncwarp();  // every lane is done with the other buffer (the previous unit's tables)
       if (u_next < nunits) stage_tables(u_next, tb ^ 1);
       mbar_wait(&tabbar[tb], (nu >> 1) & 1);
@@ -193,11 +227,13 @@ lj_celltile_force(const ct_params P) {
           if ((int)ylen > cap_y - 8) __trap();
           if (lane == 0) {
             yrel[yslot] = tbase + min(i, ntile - 1);  // the tile that has it as its oldest row
-            if (ylen) mbar_expect_tx(&tfull[tslot], ylen * 24u);
+            if (ylen) mbar_expect_tx(&tfull[tslot], ylen * RB);
+            if (MX)  // made visible to the consumers by this lane's arrive on the tile's full barrier
+              *reinterpret_cast<int4*>(ybase + ((size_t)yslot * cap_y + cap_y - 1) * RB) = make_int4(0, 0, dummy_z, 0);
           }
           __syncwarp();
           if (len && ylen)
-            bulk_g2s(ybase + ((size_t)yslot * cap_y + ey.y) * 24, P.qs + (size_t)ey.x * 3, len * 24u, &tfull[tslot]);
+            bulk_g2s(ybase + ((size_t)yslot * cap_y + ey.y) * RB, P.qs + (size_t)ey.x * RB, len * RB, &tfull[tslot]);
           if (++yslot == ry) yslot = 0;
         }
         // ---- tile cy = Y - 2: list segment, metadata, header; then the barrier's one arrival
@@ -236,6 +272,18 @@ lj_celltile_force(const ct_params P) {
   }
 
   // -------------------------------------------------------------------- consumer warps ---
+  // MX: the pair-loop constants, read back through a volatile shared-memory load so that they
+  // live in registers.  Left as kernel parameters, ptxas re-reads the constant bank inside the
+  // pair loop (9 of 116 instructions per four pairs).
+  float unit2 = 0.f, c24u = 0.f, c48u = 0.f, lo_c = 0.f, cl2f = 0.f;
+  if (MX) {
+    const uint32_t ka = smem_u32(kconst);
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(unit2) : "r"(ka));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+4];" : "=f"(c24u) : "r"(ka));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+8];" : "=f"(c48u) : "r"(ka));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+12];" : "=f"(lo_c) : "r"(ka));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+16];" : "=f"(cl2f) : "r"(ka));
+  }
   const int lg = lane & 7, gi = lane >> 3;
   const uint32_t ring = (uint32_t)ry * (uint32_t)cap_y;
   const uint32_t ybase_s = smem_u32(ybase);
@@ -258,7 +306,7 @@ lj_celltile_force(const ct_params P) {
       const int nquads = (ns + 3) >> 2;
       int quad = first;
       const bool had_quad = quad < nquads;
-      first = (first + kCtConsumers - nquads % kCtConsumers) % kCtConsumers;
+      first = (first + NCONS - nquads % NCONS) % NCONS;
       if (quad < nquads && (P.mode & 15) != 3) {
         const int self0 = h.y;
         const uint32_t u0 = (uint32_t)h.z;
@@ -268,13 +316,115 @@ lj_celltile_force(const ct_params P) {
         // region-local index L -> ring record: (slot of the tile's first y-row) * cap_y + L, wrapped
         const uint32_t off0 = (uint32_t)h.w * (uint32_t)cap_y;
         const uint32_t off0w = off0 - ring;
+        if constexpr (MX) {
+          // ---------------------------------------------------------- mixed precision ---
+          // Same quads, same lock-step trips; per pair one LDS.U16 (index) and one LDS.128 (record).
+          // A quarter-warp = the eight lanes of one row = one shared-memory wavefront when the
+          // eight records are distinct modulo 8, which runs of consecutive indices are.
+          // Two copies of the loop: most tiles have their five y-rows in consecutive ring slots
+          // (record address = one IMAD); the others wrap around the end of the ring (+ IMAD, UMIN).
+          const uint32_t c1 = ybase_s + off0 * 16u, c2 = ybase_s + off0w * 16u;
+          auto run = [&](auto wrap_tag) {
+            constexpr bool WRAP = decltype(wrap_tag)::value;
+            auto fetchx = [&](uint32_t L) {
+              uint32_t a = L * 16u + c1;
+              if (WRAP) a = min(a, L * 16u + c2);  // unsigned: the slot before the ring start is "huge"
+              int4 v;
+              asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+              return v;
+            };
+            for (; quad < nquads; quad += NCONS) {
+              const int r = quad * 4 + gi;
+              const bool valid = r < ns;
+              int4 m = make_int4(0, (int)u0, 0, 0);
+              if (valid) m = meta[r];
+              const int np = m.x;
+              const int trips = (np + 7) >> 3;
+              const int tmin = __reduce_min_sync(0xffffffffu, trips);
+              const int tmax = __reduce_max_sync(0xffffffffu, trips);
+              const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lg;
+              const int4 me = fetchx(valid ? (uint32_t)(self0 + r) : dummy);
+              float fx = 0.f, fy = 0.f, fz = 0.f;
+              float nearest = 3.0e38f;  // min |r2 - cl2| over the row's pairs of this lane
+              // r2 from exact differences in counts (modulo 2^32: correct for |d| < 2^31 counts)
+              auto dist = [&](const int4 pj, float& dx, float& dy, float& dz) {
+                dx = (float)(int)((uint32_t)pj.x - (uint32_t)me.x);
+                dy = (float)(int)((uint32_t)pj.y - (uint32_t)me.y);
+                dz = (float)(int)((uint32_t)pj.z - (uint32_t)me.z);
+                return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) * unit2;
+              };
+              auto force = [&](float r2) {  // df * unit: the differences stay in counts
+                float x;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(r2));
+                const float x2 = x * x;
+                return (x2 * x2) * fmaf(-c48u, x2 * x, c24u);
+              };
+              // Hot path: a pair counts iff r2 <= lo_c = cl2 - margin, i.e. it is inside the cutoff
+              // whatever the FP32 / fixed-point error.  Pairs in the band around the cutoff are left
+              // out here and only REMEMBERED (one FADD + FMNMX, no branch); rows that saw one are
+              // revisited below with the exact FP64 test.
+              auto pairx = [&](const int4 pj) {
+                float dx, dy, dz;
+                const float r2 = dist(pj, dx, dy, dz);
+                nearest = fminf(nearest, fabsf(r2 - cl2f));
+                const float df = r2 <= lo_c ? force(r2) : 0.f;
+                fx = fmaf(df, dx, fx);
+                fy = fmaf(df, dy, fy);
+                fz = fmaf(df, dz, fz);
+              };
+              int k = 0;
+              for (; k + kCtUnrollMx <= tmin; k += kCtUnrollMx) {
+                uint32_t en[kCtUnrollMx];
+#pragma unroll
+                for (int v = 0; v < kCtUnrollMx; v++) en[v] = e[(k + v) * 8];
+                int4 pj[kCtUnrollMx];
+#pragma unroll
+                for (int v = 0; v < kCtUnrollMx; v++) pj[v] = fetchx(en[v]);
+#pragma unroll
+                for (int v = 0; v < kCtUnrollMx; v++) pairx(pj[v]);
+              }
+              for (; k < tmax; k += 2) {  // warp-uniform; rows that are already done look at the dummy point
+                const uint32_t e0 = k < trips ? (uint32_t)e[k * 8] : dummy;
+                const uint32_t e1 = k + 1 < trips ? (uint32_t)e[(k + 1) * 8] : dummy;
+                const int4 p0 = fetchx(e0), p1 = fetchx(e1);
+                pairx(p0);
+                pairx(p1);
+              }
+              if (nearest <= P.band) {  // rare (about one row in 300 at rho = 1): the borderline pairs, exactly
+                for (int kk = 0; kk < trips; kk++) {
+                  const int4 pj = fetchx((uint32_t)e[kk * 8]);
+                  float dx, dy, dz;
+                  const float r2 = dist(pj, dx, dy, dz);
+                  if (r2 <= lo_c || !(fabsf(r2 - cl2f) <= P.band)) continue;
+                  double xi, yi, zi, xj, yj, zj;
+                  load_pos<LAYOUT>(P.q, m.z, P.plane, xi, yi, zi);
+                  load_pos<LAYOUT>(P.q, pj.w, P.plane, xj, yj, zj);
+                  const double ex = xj - xi, ey = yj - yi, ez = zj - zi;
+                  if (fma(ez, ez, fma(ey, ey, ex * ex)) <= P.cl2) {
+                    const float df = force(r2);
+                    fx = fmaf(df, dx, fx);
+                    fy = fmaf(df, dy, fy);
+                    fz = fmaf(df, dz, fz);
+                  }
+                }
+              }
+              // FP32 per-lane partial sums (about 17 pairs each), FP64 from here on
+              const double sx = group_sum<8>((double)fx);
+              const double sy = group_sum<8>((double)fy);
+              const double sz = group_sum<8>((double)fz);
+              if (lg == 0 && np > 0) red_mom<LAYOUT>(P.p, m.z, P.plane, sx, sy, sz);
+              n_quads++;
+            }
+          };
+          if (h.w + kTileYPencils > ry) run(std::true_type{}); else run(std::false_type{});
+        } else {
         auto fetch = [&](uint32_t L, double& x, double& y, double& z) {
           const uint32_t a = ybase_s + min(L + off0, L + off0w) * 24u;  // unsigned min = wrap
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
           asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(y) : "r"(a));
           asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(z) : "r"(a));
         };
-        for (; quad < nquads; quad += kCtConsumers) {
+        for (; quad < nquads; quad += NCONS) {
           const int r = quad * 4 + gi;
           const bool valid = r < ns;
           int4 m = make_int4(0, (int)u0, 0, 0);
@@ -321,6 +471,7 @@ lj_celltile_force(const ct_params P) {
           if (lg == 0 && np > 0) red_mom<LAYOUT>(P.p, m.z, P.plane, fx, fy, fz);
           n_quads++;
         }
+        }  // FP64
       }
       __syncwarp();
       if (P.dbg && had_quad) t_work += clock64() - tw1;
@@ -329,16 +480,16 @@ lj_celltile_force(const ct_params P) {
     }
   }
   if (P.dbg && lane == 0) {
-    long long* d = P.dbg + ((size_t)blockIdx.x * kCtConsumers + warp) * 4;
+    long long* d = P.dbg + ((size_t)blockIdx.x * NCONS + warp) * 4;
     d[0] = t_wait; d[1] = t_work; d[2] = n_quads; d[3] = clock64() - t_begin;
   }
 }
 
-template <int LAYOUT>
+template <int LAYOUT, bool MX, int NCONS>
 int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
                     cudaStream_t st) {
   const lj_tile_geom& g = ctx->tl_g;
-  const size_t ys = lj_celltile_yslot_bytes(g), ls = lj_celltile_lslot_bytes(g);
+  const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
   // ring sizes.  A tile holds five y-rows and one list slot; at a unit boundary the last tile of the
   // old unit and the first tile of the new one hold ten y-rows between them, so fewer than ten
   // y slots drain the pipeline at every boundary.  Prefer >= 10 y slots, then balance look-ahead.
@@ -363,8 +514,17 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   nseg = (g.ny + seg_len - 1) / seg_len;
 
   ct_params P;
-  P.qs = ctx->tl_qs; P.p = a->p; P.plane = a->plane_stride;
+  P.qs = MX ? reinterpret_cast<const unsigned char*>(ctx->tl_qfx) : reinterpret_cast<const unsigned char*>(ctx->tl_qs);
+  P.p = a->p; P.plane = a->plane_stride;
   P.c24 = c24; P.c48 = c48; P.cl2_bits = cl2_bits;
+  P.q = a->q; P.grid = ctx->grid; P.cl2 = a->cl2;
+  {
+    const lj_fx_frame f = lj_fx_frame_for(a->cl2);
+    P.fx_scale = f.scale;
+    P.c24u = (float)(c24 * f.unit); P.c48u = (float)(c48 * f.unit);
+    P.unit2 = (float)(f.unit * f.unit);  // a power of two: exact
+    P.cl2f = (float)a->cl2; P.lo_c = P.cl2f - f.margin; P.band = 1.01f * f.margin;
+  }
   P.ytab = ctx->tl_tab; P.ttab = ctx->tl_ttab; P.meta = ctx->tl_meta; P.list = ctx->tl_list;
   P.ntx = g.ntx; P.ny = g.ny; P.ncols = ncols; P.seg_len = seg_len; P.nseg = nseg;
   P.cap_y = lj_celltile_cap_y(g); P.cap_units = g.max_units; P.cap_rows = g.max_rows;
@@ -375,11 +535,11 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   P.dbg = nullptr;
   static long long* dbg_buf = nullptr;
   if (getenv("LJ_TILE_DBG")) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * kCtConsumers * 1024);
+    if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 32 * 1024);
     P.dbg = dbg_buf;
   }
   const size_t smem = (size_t)ry * ys + (size_t)rl * ls;
-  auto kern = lj_celltile_force<LAYOUT>;
+  auto kern = lj_celltile_force<LAYOUT, MX, NCONS>;
   static size_t configured = 0;
   if (smem > configured) {
     LJ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -390,24 +550,24 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   if (getenv("LJ_TILE_DEBUG"))
     fprintf(stderr, "[lj] cell-tile force: %d units (%d columns x %d segments of %d), y ring %d x %zu B, list ring "
             "%d x %zu B, smem %zu B\n", nunits, ncols, nseg, seg_len, ry, ys, rl, ls, smem);
-  kern<<<(unsigned)grid, kCtThreads, smem, st>>>(P);
+  kern<<<(unsigned)grid, (NCONS + 1) * 32, smem, st>>>(P);
   LJ_LAUNCHED(ctx);
   if (P.dbg) {  // diagnostics only: synchronises
     static int dumps = 0;
     cudaStreamSynchronize(st);
     if (dumps++ == 3) {
-      std::vector<long long> h((size_t)4 * kCtConsumers * grid);
+      std::vector<long long> h((size_t)4 * NCONS * grid);
       cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       double w = 0, k = 0, q = 0, t = 0, tmax = 0, tmin = 1e30, qmax = 0, qmin = 1e30;
       for (int b = 0; b < grid; b++) {
         double qb = 0, tb = 0;
-        for (int c = 0; c < kCtConsumers; c++) {
-          const long long* d = &h[((size_t)b * kCtConsumers + c) * 4];
+        for (int c = 0; c < NCONS; c++) {
+          const long long* d = &h[((size_t)b * NCONS + c) * 4];
           w += d[0]; k += d[1]; q += d[2]; t += d[3]; qb += d[2]; if (d[3] > tb) tb = d[3];
         }
         if (tb > tmax) tmax = tb; if (tb < tmin) tmin = tb; if (qb > qmax) qmax = qb; if (qb < qmin) qmin = qb;
       }
-      const double n = (double)grid * kCtConsumers;
+      const double n = (double)grid * NCONS;
       fprintf(stderr, "[lj] celltile dbg: per warp avg wait %.0f, work %.0f, total %.0f cycles, quads %.1f (%.0f cycles/quad); "
               "CTA total min %.0f max %.0f, quads per CTA min %.0f max %.0f\n", w / n, k / n, t / n, q / n, k / q, tmin, tmax, qmin, qmax);
     }
@@ -423,7 +583,8 @@ bool lj_celltile_worthwhile(const lj_ctx* ctx) { return ctx->tl_g.ntiles >= 32 *
 
 // true when the mirror describes exactly the list arrays and the row range of this call
 bool lj_celltile_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1) {
-  if (!ctx->tl_valid || a->list_layout != LJ_LIST_CSR || a->precision != LJ_PREC_FP64) return false;
+  if (!ctx->tl_valid || a->list_layout != LJ_LIST_CSR) return false;
+  if (a->precision != LJ_PREC_FP64 && a->precision != LJ_PREC_MIXED) return false;
   if (a->layout != LJ_AOS_D3 && a->layout != LJ_AOS_D4 && a->layout != LJ_SOA_D) return false;
   if (a->list != ctx->tl_id_list || a->number_of_partners != ctx->tl_id_nop ||
       a->pointer != ctx->tl_id_ptr || a->pn != ctx->tl_pn)
@@ -435,10 +596,28 @@ int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, do
                              long long cl2_bits, cudaStream_t st) {
   int rc = lj_celltile_permute(ctx, a, st);
   if (rc) return rc;
+  if (a->precision == LJ_PREC_MIXED) {
+    // consumer warps of the mixed kernel: FP32 needs fewer registers, so more warps fit (diagnostics)
+    static const int nc_env = [] { const char* e = getenv("LJ_TILE_CONSUMERS"); return e ? atoi(e) : 0; }();
+    const int nc = nc_env ? nc_env : kCtConsumersMx;
+#define LJ_CT_MX(L)                                                                        \
+    switch (nc) {                                                                          \
+      case 24: return launch_celltile<L, true, 24>(ctx, a, c24, c48, cl2_bits, st);        \
+      case 31: return launch_celltile<L, true, 31>(ctx, a, c24, c48, cl2_bits, st);        \
+      default: return launch_celltile<L, true, 16>(ctx, a, c24, c48, cl2_bits, st);        \
+    }
+    switch (a->layout) {
+      case LJ_AOS_D4: LJ_CT_MX(LJ_AOS_D4)
+      case LJ_AOS_D3: LJ_CT_MX(LJ_AOS_D3)
+      case LJ_SOA_D: LJ_CT_MX(LJ_SOA_D)
+    }
+#undef LJ_CT_MX
+    return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
+  }
   switch (a->layout) {
-    case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4>(ctx, a, c24, c48, cl2_bits, st);
-    case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3>(ctx, a, c24, c48, cl2_bits, st);
-    case LJ_SOA_D: return launch_celltile<LJ_SOA_D>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, kCtConsumers>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, kCtConsumers>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, kCtConsumers>(ctx, a, c24, c48, cl2_bits, st);
   }
   return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
 }

@@ -852,6 +852,22 @@ k_tile_permute(const void* __restrict__ q, int64_t plane, const int32_t* __restr
   qs[3 * s] = x; qs[3 * s + 1] = y; qs[3 * s + 2] = z;
 }
 
+// the same for the mixed-precision kernel: {x, y, z} in counts modulo 2^32 (lj_fx_frame), .w = the
+// original index (the kernel re-decides borderline cutoff cases from the caller's FP64 positions)
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+k_tile_permute_fx(const void* __restrict__ q, int64_t plane, const int32_t* __restrict__ order,
+                  int64_t pn, double scale, int4* __restrict__ qfx, int* __restrict__ unit_counter) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) *unit_counter = 0;
+  if (s >= pn) return;
+  const int o = order[s];
+  double x, y, z;
+  load_pos<LAYOUT>(q, o, plane, x, y, z);
+  qfx[s] = make_int4((int)(uint32_t)__double2ll_rn(x * scale), (int)(uint32_t)__double2ll_rn(y * scale),
+                     (int)(uint32_t)__double2ll_rn(z * scale), o);
+}
+
 int64_t blocks_for(int64_t n, int tb) { return (n + tb - 1) / tb; }
 
 }  // namespace
@@ -1213,6 +1229,24 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
 // positions of this step in cell order (the force kernel's TMA source)
 int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
   const unsigned blocks = (unsigned)blocks_for(a->pn, 256);
+  if (a->precision == LJ_PREC_MIXED) {
+    if (ctx->tl_qfx_cap < a->pn) {
+      if (ctx->tl_qfx) LJ_CUDA(ctx, cudaFreeAsync(ctx->tl_qfx, st));
+      ctx->tl_qfx = nullptr;
+      LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->tl_qfx, sizeof(int4) * (size_t)(a->pn + 2), ctx->pool, st));
+      LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_qfx, 0, sizeof(int4) * (size_t)(a->pn + 2), st));
+      ctx->tl_qfx_cap = a->pn;
+      ctx->graph_loop = -1;  // a cached CUDA graph may hold the old pointer
+    }
+    const double scale = lj_fx_frame_for(a->cl2).scale;
+    switch (a->layout) {
+      case LJ_AOS_D3: k_tile_permute_fx<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, &ctx->tl_geom->pad); break;
+      case LJ_AOS_D4: k_tile_permute_fx<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, &ctx->tl_geom->pad); break;
+      default: k_tile_permute_fx<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, &ctx->tl_geom->pad); break;
+    }
+    LJ_LAUNCHED(ctx);
+    return LJ_OK;
+  }
   switch (a->layout) {
     case LJ_AOS_D3: k_tile_permute<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;
     case LJ_AOS_D4: k_tile_permute<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;

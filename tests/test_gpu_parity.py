@@ -701,6 +701,55 @@ def test_celltile_force_and_list_match_oracle(ctx, torch, sysS, layout):
     assert torch.equal(pd, pr)
 
 
+@pytest.mark.parametrize("layout", ["aos4", "aos3", "soa"])
+def test_celltile_mixed_precision_matches_oracle(ctx, torch, sysS, layout):
+    """LJ_VARIANT_CELLTILE + LJ_PREC_MIXED: fixed-point records in shared memory, FP32 pair
+    arithmetic, FP64 momenta; within the stated 1e-5 of the oracle, .w of p untouched."""
+    s = sysS
+    qd, pd = s.device_arrays(torch, layout)
+    npn = s.pn if layout == "soa" else None
+    pl = ctx.makepair(qd, layout=layout, pn=npn, tiles=True)
+    launches = ctx.launches
+    ctx.force_loop(qd, pd, pl, loop=s.steps, layout=layout, pn=npn, variant="celltile", precision="mixed")
+    assert ctx.launches - launches == 2 * s.steps          # fixed-point permute + force kernel
+    err = s.err(pd, layout)
+    assert 0 < err < TOL_MIXED                              # FP32 arithmetic really ran
+    if layout == "aos4":
+        assert float(pd[:, 3].min()) == 77.5 == float(pd[:, 3].max())
+    # the CUDA-graph replay of the same loop gives the same bits
+    pg = torch.zeros_like(pd)
+    if layout == "aos4":
+        pg[:, 3] = 77.5
+    ctx.force_loop(qd, pg, pl, loop=s.steps, layout=layout, pn=npn, variant="celltile", precision="mixed",
+                   use_graph=True)
+    assert torch.equal(pg, pd)
+
+
+def test_celltile_mixed_precision_borderline_pairs_are_decided_in_fp64(ctx, torch, oracle, sysS):
+    """Pairs at r2 == CL2 (contributes, cuda/kernel.cuh:30) and a hair outside (does not): FP32
+    on fixed-point coordinates cannot tell them apart, the kernel re-decides them from the FP64
+    positions.  A misclassified pair would show as ~1e-3 relative, far above the 1e-5 bound."""
+    s = sysS
+    a = np.array([-7.0, -7.0, -7.0])
+    extra = np.stack([a, a + [3.0, 0.0, 0.0], a - [0.0, 3.0 + 4e-9, 0.0], a + [0.0, 0.0, 3.0 - 4e-9]])
+    q = np.ascontiguousarray(np.concatenate([s.q, extra]))
+    pn = len(q)
+    nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
+    p_o = np.zeros_like(q)
+    oracle.force_gather(q, p_o, nop_o, ptr_o, lst_o, steps=s.steps)
+    assert p_o[pn - 4, 0] != 0 and p_o[pn - 4, 1] == 0 and p_o[pn - 4, 2] != 0   # in, out, in
+    qd = torch.from_numpy(q).cuda()
+    pl = ctx.makepair(qd, layout="aos3", tiles=True)
+    for prec, tol in (("fp64", TOL_FP64), ("mixed", TOL_MIXED)):
+        pd = torch.zeros_like(qd)
+        ctx.force_loop(qd, pd, pl, loop=s.steps, layout="aos3", variant="celltile", precision=prec)
+        ph = pd.cpu().numpy()
+        assert np.abs(ph - p_o).max() / np.abs(p_o).max() < tol
+        # the four extra atoms only see each other: their momenta are small, check them on their own scale
+        assert np.abs(ph[pn - 4:] - p_o[pn - 4:]).max() / np.abs(p_o[pn - 4:]).max() < 100 * tol
+        assert ph[pn - 4, 1] == 0.0
+
+
 def test_celltile_random_cloud_and_clusters_of_particles(ctx, torch, oracle):
     """No lattice: a uniform random cloud with a denser blob and an empty region (tiles with very
     different row counts, empty cells, empty tiles), particle order without spatial coherence."""
@@ -790,6 +839,9 @@ def test_celltile_large_system_matches_per_row_kernel(ctx, torch):
     ctx.force_loop(qd, p1, pl, loop=3, variant="celltile")
     ctx.force_loop(qd, p2, pl, loop=3, variant="subwarp", group=8)
     assert torch.equal(p1, p2)
+    pm = torch.zeros_like(qd)                             # mixed precision on the same mirror
+    ctx.force_loop(qd, pm, pl, loop=3, variant="celltile", precision="mixed")
+    assert 0 < ((pm - p1).abs().max() / p1.abs().max()).item() < TOL_MIXED
     plain = ctx.makepair(qd)                              # cluster-engine fill: same list as a set
     assert plain.number_of_pairs == pl.number_of_pairs
     assert torch.equal(plain.number_of_partners, pl.number_of_partners)

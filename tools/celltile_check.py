@@ -65,6 +65,7 @@ def main():
         torch.cuda.synchronize()
         err = (p_new - p_ref).abs().max().item()
         scale = p_ref.abs().max().item()
+        p_ref_one = p_ref.clone()
         print("layout=%s N=%d P=%d  max|dp| = %.3e (scale %.3e, rel %.3e)" % (layout, pn, P, err, scale, err / scale), flush=True)
         ms_sub = timeit(lambda: ctx.force_step(qd, p_ref, pl, layout=layout, pn=npn, variant="subwarp", group=8), args.reps)
         ms_ct = timeit(lambda: ctx.force_step(qd, p_new, pl, layout=layout, pn=npn, variant="celltile"), args.reps)
@@ -73,6 +74,15 @@ def main():
         ms_b1 = timeit(lambda: ctx.rebuild(qd, pl, layout=layout, pn=npn, tiles=True), 5)
         print("  force: subwarp g8 %.4f ms, celltile %.4f ms (auto %.4f ms); build %.3f ms, +tiles %.3f ms"
               % (ms_sub, ms_ct, ms_auto, ms_b0, ms_b1), flush=True)
+        # mixed precision on the same mirror (fixed-point records, FP32 pair arithmetic)
+        p_mx = torch.zeros_like(qd)
+        ctx.force_step(qd, p_mx, pl, layout=layout, pn=npn, variant="celltile", precision="mixed")
+        torch.cuda.synchronize()
+        err = (p_mx - p_ref_one).abs().max().item()
+        print("  mixed celltile vs FP64: max|dp| = %.3e (rel %.3e of %.3e)" % (err, err / scale, scale), flush=True)
+        ms_mx = timeit(lambda: ctx.force_step(qd, p_mx, pl, layout=layout, pn=npn, variant="celltile", precision="mixed"), args.reps)
+        ms_mr = timeit(lambda: ctx.force_step(qd, p_mx, pl, layout=layout, pn=npn, variant="subwarp", group=4, precision="mixed"), args.reps)
+        print("  mixed: celltile %.4f ms (consumers=%s), per-row g4 %.4f ms" % (ms_mx, os.environ.get("LJ_TILE_CONSUMERS", "default"), ms_mr), flush=True)
 
 
 if __name__ == "__main__":
