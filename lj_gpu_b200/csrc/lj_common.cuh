@@ -92,7 +92,8 @@ struct lj_ctx {
   int32_t* tl_cnt = nullptr;             // [pn]   entries of row s
   uint32_t* tl_units = nullptr;          // [pn+1] padded row length, units of 8 entries
   uint32_t* tl_off = nullptr;            // [pn+1] exclusive scan of tl_units
-  double* tl_qs = nullptr;               // [pn+2][3] positions in cell order, refreshed every step
+  double* tl_qs = nullptr;               // positions in cell order, refreshed every step: [cap+2] {x,y} ...
+  double* tl_qz = nullptr;               // ... followed by [cap+2] z (inside the tl_qs allocation)
   int4* tl_qfx = nullptr;                // [pn+2] the same in 32-bit fixed point + original index (mixed precision)
   int64_t tl_qfx_cap = 0;
   uint32_t* tl_cell_start = nullptr;     // [ncell+1] private copy of the cell offsets

@@ -75,7 +75,8 @@ constexpr int kCtMaxY = 16, kCtMaxL = 8;
 constexpr int kCtMaxSeg = 32;  // tiles per unit (column segment) at most
 
 struct ct_params {
-  const unsigned char* qs;  // positions in cell order: packed double3 (FP64) or int4 fixed point (mixed)
+  const unsigned char* qs;  // positions in cell order: int4 fixed point (mixed) or the {x,y} plane (FP64)
+  const unsigned char* qz;  // FP64: the z plane
   void* p; int64_t plane;
   double c24, c48; long long cl2_bits;
   // mixed precision only
@@ -124,7 +125,12 @@ lj_celltile_force(const ct_params P) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ry = P.ry, rl = P.rl, cap_y = P.cap_y;
+  // FP64 ring: a plane of {x,y} pairs (16 B, one LDS.128) followed by a plane of z (8 B, LDS.64), both
+  // indexed by ring record.  Packed 24-byte records cost three LDS.64 whose half-warps (two rows
+  // of eight lanes at unrelated offsets) almost always collide: 16 shared-memory wavefronts per 32
+  // pairs measured, against 6 for conflict-free access; the planes need 4 + ~4.
   unsigned char* const ybase = smem_raw;
+  unsigned char* const zbase = smem_raw + (size_t)ry * cap_y * 16;  // FP64 only
   unsigned char* const lbase = smem_raw + (size_t)ry * cap_y * RB;
   if (threadIdx.x == 0) {
     kconst[0] = P.unit2; kconst[1] = P.c24u; kconst[2] = P.c48u; kconst[3] = P.lo_c; kconst[4] = P.cl2f;
@@ -134,8 +140,9 @@ lj_celltile_force(const ct_params P) {
   }
   if (threadIdx.x < ry) {  // the dummy record of every y slot: its last one, no copy ever reaches it
     if (!MX) {
-      double* d = reinterpret_cast<double*>(ybase) + ((size_t)threadIdx.x * cap_y + cap_y - 1) * 3;
-      d[0] = kTileFar; d[1] = kTileFar; d[2] = kTileFar;
+      const size_t R = (size_t)threadIdx.x * cap_y + cap_y - 1;
+      reinterpret_cast<double2*>(ybase)[R] = make_double2(kTileFar, kTileFar);
+      reinterpret_cast<double*>(zbase)[R] = kTileFar;
     }  // MX: fixed-point coordinates wrap, "far" depends on the unit -- the producer writes it
     yrel[threadIdx.x] = -1;
   }
@@ -232,8 +239,15 @@ lj_celltile_force(const ct_params P) {
               *reinterpret_cast<int4*>(ybase + ((size_t)yslot * cap_y + cap_y - 1) * RB) = make_int4(0, 0, dummy_z, 0);
           }
           __syncwarp();
-          if (len && ylen)
-            bulk_g2s(ybase + ((size_t)yslot * cap_y + ey.y) * RB, P.qs + (size_t)ey.x * RB, len * RB, &tfull[tslot]);
+          if (len && ylen) {
+            const size_t R = (size_t)yslot * cap_y + ey.y;
+            if (MX) {
+              bulk_g2s(ybase + R * 16, P.qs + (size_t)ey.x * 16, len * 16u, &tfull[tslot]);
+            } else {  // both ends of a pencil range are even: the 8-byte plane stays 16-byte aligned
+              bulk_g2s(ybase + R * 16, P.qs + (size_t)ey.x * 16, len * 16u, &tfull[tslot]);
+              bulk_g2s(zbase + R * 8, P.qz + (size_t)ey.x * 8, len * 8u, &tfull[tslot]);
+            }
+          }
           if (++yslot == ry) yslot = 0;
         }
         // ---- tile cy = Y - 2: list segment, metadata, header; then the barrier's one arrival
@@ -322,13 +336,14 @@ lj_celltile_force(const ct_params P) {
           // A quarter-warp = the eight lanes of one row = one shared-memory wavefront when the
           // eight records are distinct modulo 8, which runs of consecutive indices are.
           // Two copies of the loop: most tiles have their five y-rows in consecutive ring slots
-          // (record address = one IMAD); the others wrap around the end of the ring (+ IMAD, UMIN).
-          const uint32_t c1 = ybase_s + off0 * 16u, c2 = ybase_s + off0w * 16u;
+          // (record address = one IMAD); the others wrap around the end of the ring (+ ISETP, IADD).
+          const uint32_t c1 = ybase_s + off0 * 16u;
+          const uint32_t ring_end = ybase_s + ring * 16u, ring_bytes = ring * 16u;
           auto run = [&](auto wrap_tag) {
             constexpr bool WRAP = decltype(wrap_tag)::value;
             auto fetchx = [&](uint32_t L) {
               uint32_t a = L * 16u + c1;
-              if (WRAP) a = min(a, L * 16u + c2);  // unsigned: the slot before the ring start is "huge"
+              if (WRAP) { if (a >= ring_end) a -= ring_bytes; }  // past the last slot: back to slot 0
               int4 v;
               asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
               return v;
@@ -418,59 +433,62 @@ lj_celltile_force(const ct_params P) {
           };
           if (h.w + kTileYPencils > ry) run(std::true_type{}); else run(std::false_type{});
         } else {
-        auto fetch = [&](uint32_t L, double& x, double& y, double& z) {
-          const uint32_t a = ybase_s + min(L + off0, L + off0w) * 24u;  // unsigned min = wrap
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
-          asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(y) : "r"(a));
-          asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(z) : "r"(a));
-        };
-        for (; quad < nquads; quad += NCONS) {
-          const int r = quad * 4 + gi;
-          const bool valid = r < ns;
-          int4 m = make_int4(0, (int)u0, 0, 0);
-          if (valid) m = meta[r];
-          const int np = m.x;
-          const int trips = (np + 7) >> 3;
-          const int tmin = __reduce_min_sync(0xffffffffu, trips);
-          const int tmax = __reduce_max_sync(0xffffffffu, trips);
-          const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lg;
-          double xi, yi, zi;
-          fetch(valid ? (uint32_t)(self0 + r) : dummy, xi, yi, zi);
-          double fx = 0.0, fy = 0.0, fz = 0.0;
-          int k = 0;
-          for (; k + kCtUnroll <= tmin; k += kCtUnroll) {
-            uint32_t en[kCtUnroll];
+          // ------------------------------------------------------------------ FP64 ---
+          const uint32_t zbase_s = smem_u32(zbase);
+          const uint32_t c1 = ybase_s + off0 * 16u, c1z = zbase_s + off0 * 8u;
+          const uint32_t ring_end = ybase_s + ring * 16u, ring_xy = ring * 16u, ring_z = ring * 8u;
+          auto run = [&](auto wrap_tag) {
+            constexpr bool WRAP = decltype(wrap_tag)::value;
+            auto fetch = [&](uint32_t L, double& x, double& y, double& z) {
+              uint32_t a = L * 16u + c1, az = L * 8u + c1z;
+              if (WRAP) { if (a >= ring_end) { a -= ring_xy; az -= ring_z; } }  // past the last slot: back to slot 0
+              asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(z) : "r"(az));
+            };
+            for (; quad < nquads; quad += NCONS) {
+              const int r = quad * 4 + gi;
+              const bool valid = r < ns;
+              int4 m = make_int4(0, (int)u0, 0, 0);
+              if (valid) m = meta[r];
+              const int np = m.x;
+              const int trips = (np + 7) >> 3;
+              const int tmin = __reduce_min_sync(0xffffffffu, trips);
+              const int tmax = __reduce_max_sync(0xffffffffu, trips);
+              const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lg;
+              double xi, yi, zi;
+              fetch(valid ? (uint32_t)(self0 + r) : dummy, xi, yi, zi);
+              double fx = 0.0, fy = 0.0, fz = 0.0;
+              int k = 0;
+              for (; k + kCtUnroll <= tmin; k += kCtUnroll) {
+                uint32_t en[kCtUnroll];
 #pragma unroll
-            for (int v = 0; v < kCtUnroll; v++) en[v] = e[(k + v) * 8];
-            double xj[kCtUnroll], yj[kCtUnroll], zj[kCtUnroll];
+                for (int v = 0; v < kCtUnroll; v++) en[v] = e[(k + v) * 8];
+                double xj[kCtUnroll], yj[kCtUnroll], zj[kCtUnroll];
 #pragma unroll
-            for (int v = 0; v < kCtUnroll; v++) fetch(en[v], xj[v], yj[v], zj[v]);
-            if ((P.mode & 15) == 1) {
+                for (int v = 0; v < kCtUnroll; v++) fetch(en[v], xj[v], yj[v], zj[v]);
 #pragma unroll
-              for (int v = 0; v < kCtUnroll; v++) { fx += xj[v]; fy += yj[v]; fz += zj[v]; }
-              continue;
+                for (int v = 0; v < kCtUnroll; v++)
+                  lj_pair(xj[v] - xi, yj[v] - yi, zj[v] - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
+              }
+              for (; k < tmax; k += 2) {  // warp-uniform; rows that are already done look at the dummy point
+                const uint32_t e0 = k < trips ? (uint32_t)e[k * 8] : dummy;
+                const uint32_t e1 = k + 1 < trips ? (uint32_t)e[(k + 1) * 8] : dummy;
+                double x0, y0_, z0, x1, y1_, z1;
+                fetch(e0, x0, y0_, z0);
+                fetch(e1, x1, y1_, z1);
+                lj_pair(x0 - xi, y0_ - yi, z0 - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
+                lj_pair(x1 - xi, y1_ - yi, z1 - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
+              }
+              fx = group_sum<8>(fx);
+              fy = group_sum<8>(fy);
+              fz = group_sum<8>(fz);
+              // RED (no return value): the warp does not wait for p at the end of every quad.  Exactly
+              // one add per component, row and step, so the result is deterministic.
+              if (lg == 0 && np > 0) red_mom<LAYOUT>(P.p, m.z, P.plane, fx, fy, fz);
+              n_quads++;
             }
-#pragma unroll
-            for (int v = 0; v < kCtUnroll; v++)
-              lj_pair(xj[v] - xi, yj[v] - yi, zj[v] - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
-          }
-          for (; k < tmax; k += 2) {  // warp-uniform; rows that are already done look at the dummy point
-            const uint32_t e0 = k < trips ? (uint32_t)e[k * 8] : dummy;
-            const uint32_t e1 = k + 1 < trips ? (uint32_t)e[(k + 1) * 8] : dummy;
-            double x0, y0_, z0, x1, y1_, z1;
-            fetch(e0, x0, y0_, z0);
-            fetch(e1, x1, y1_, z1);
-            lj_pair(x0 - xi, y0_ - yi, z0 - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
-            lj_pair(x1 - xi, y1_ - yi, z1 - zi, P.c24, P.c48, P.cl2_bits, fx, fy, fz);
-          }
-          fx = group_sum<8>(fx);
-          fy = group_sum<8>(fy);
-          fz = group_sum<8>(fz);
-          // RED (no return value): the warp does not wait for p at the end of every quad.  Exactly
-          // one add per component, row and step, so the result is deterministic.
-          if (lg == 0 && np > 0) red_mom<LAYOUT>(P.p, m.z, P.plane, fx, fy, fz);
-          n_quads++;
-        }
+          };
+          if (h.w + kTileYPencils > ry) run(std::true_type{}); else run(std::false_type{});
         }  // FP64
       }
       __syncwarp();
@@ -503,6 +521,12 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
     if (score > best) { best = score; ry = y; rl = l; }
   }
   LJ_REQUIRE(ctx, best >= 0, "lj_force_step: cell-tile geometry does not fit in shared memory");
+  {  // diagnostics: cap the ring sizes
+    static const int ry_env = [] { const char* e = getenv("LJ_TILE_RY"); return e ? atoi(e) : 0; }();
+    static const int rl_env = [] { const char* e = getenv("LJ_TILE_RL"); return e ? atoi(e) : 0; }();
+    if (ry_env >= kTileMinYSlots && ry_env < ry) ry = ry_env;
+    if (rl_env >= kTileMinLSlots && rl_env < rl) rl = rl_env;
+  }
   static const int seg_env = [] { const char* e = getenv("LJ_TILE_SEG"); return e ? atoi(e) : 0; }();
   const int ncols = g.ntx * g.nz;
   int nseg = (16 * ctx->sm_count + ncols - 1) / ncols;  // >= 16 units per CTA: the dynamic deal ends evenly
@@ -515,6 +539,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
 
   ct_params P;
   P.qs = MX ? reinterpret_cast<const unsigned char*>(ctx->tl_qfx) : reinterpret_cast<const unsigned char*>(ctx->tl_qs);
+  P.qz = reinterpret_cast<const unsigned char*>(ctx->tl_qz);
   P.p = a->p; P.plane = a->plane_stride;
   P.c24 = c24; P.c48 = c48; P.cl2_bits = cl2_bits;
   P.q = a->q; P.grid = ctx->grid; P.cl2 = a->cl2;

@@ -843,13 +843,14 @@ k_tile_fill(int64_t pn, const grid_ext* __restrict__ ge, const lj_tile_geom* __r
 template <int LAYOUT>
 __global__ void __launch_bounds__(256)
 k_tile_permute(const void* __restrict__ q, int64_t plane, const int32_t* __restrict__ order,
-               int64_t pn, double* __restrict__ qs, int* __restrict__ unit_counter) {
+               int64_t pn, double2* __restrict__ qxy, double* __restrict__ qz, int* __restrict__ unit_counter) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s == 0) *unit_counter = 0;  // the force kernel that follows deals its work units from here
   if (s >= pn) return;
   double x, y, z;
   load_pos<LAYOUT>(q, order[s], plane, x, y, z);
-  qs[3 * s] = x; qs[3 * s + 1] = y; qs[3 * s + 2] = z;
+  qxy[s] = make_double2(x, y);  // two planes: the force kernel reads {x,y} with LDS.128, z with LDS.64
+  qz[s] = z;
 }
 
 // the same for the mixed-precision kernel: {x, y, z} in counts modulo 2^32 (lj_fx_frame), .w = the
@@ -1142,6 +1143,7 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
     if ((rc = tile_alloc(ctx, (void**)&ctx->tl_meta, sizeof(int4) * (pn + 1), st))) return rc;
     if ((rc = tile_alloc(ctx, (void**)&ctx->tl_qs, 24 * (size_t)(pn + 2), st))) return rc;
     LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_qs, 0, 24 * (size_t)(pn + 2), st));
+    ctx->tl_qz = ctx->tl_qs + 2 * (size_t)(pn + 2);
     ctx->tl_pn_cap = pn;
   }
   static const int target_rows = [] {
@@ -1248,9 +1250,9 @@ int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
     return LJ_OK;
   }
   switch (a->layout) {
-    case LJ_AOS_D3: k_tile_permute<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;
-    case LJ_AOS_D4: k_tile_permute<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;
-    default: k_tile_permute<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, ctx->tl_qs, &ctx->tl_geom->pad); break;
+    case LJ_AOS_D3: k_tile_permute<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, &ctx->tl_geom->pad); break;
+    case LJ_AOS_D4: k_tile_permute<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, &ctx->tl_geom->pad); break;
+    default: k_tile_permute<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, &ctx->tl_geom->pad); break;
   }
   LJ_LAUNCHED(ctx);
   return LJ_OK;
