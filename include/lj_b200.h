@@ -71,7 +71,7 @@ typedef enum lj_variant {
   LJ_VARIANT_CELLTILE = 5   /* cell-tile mirror built by lj_build_list(LJ_LIST_TILES) for exactly
                                these list arrays: q[j] of a tile's neighbourhood staged in shared
                                memory by TMA, 16-bit local indices; error if there is none.
-                               AUTO picks it whenever the mirror exists (FP64)                */
+                               AUTO picks it whenever the mirror exists (FP64 and mixed)      */
 } lj_variant;
 
 typedef enum lj_precision {
@@ -183,7 +183,11 @@ enum {
    * Full lists, FP64 layouts; two small host read-backs per build.  Dropped like the cluster list;
    * silently absent when a tile's neighbourhood would not fit in shared memory (very dense
    * systems), in which case AUTO stays on the per-row kernels. */
-  LJ_LIST_TILES = 8
+  LJ_LIST_TILES = 8,
+  /* With LJ_LIST_TILES: size the tiles of the mirror for the mixed-precision force kernel
+   * (LJ_PREC_MIXED: 16-byte position records leave shared memory for ~56-row tiles, measured 8 %
+   * faster than the 40-row tiles the FP64 kernel prefers).  Either kernel runs on either mirror. */
+  LJ_LIST_TILES_WIDE = 16
 };
 
 typedef struct lj_list_args {

@@ -24,6 +24,7 @@ LJ_PREC_FP64, LJ_PREC_MIXED = 0, 1
 LJ_LIST_SORT_ROWS = 1
 LJ_LIST_CLUSTERS = 2
 LJ_LIST_TILES = 8
+LJ_LIST_TILES_WIDE = 16
 LJ_LIST_PER_PARTICLE_SEARCH = 4
 
 

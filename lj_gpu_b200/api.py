@@ -203,7 +203,8 @@ class LJContext:
         """makepair() (cuda/force_cuda.cu:122-163) on the GPU.  Returns device arrays.
         clusters=True also builds the library-owned cluster pair list (LJ_LIST_CLUSTERS) that the
         "auto"/"cluster" force variants use for exactly these arrays; tiles=True the cell-tile mirror
-        (LJ_LIST_TILES) of the "auto"/"celltile" variants."""
+        (LJ_LIST_TILES) of the "auto"/"celltile" variants; tiles="wide" sizes its tiles for the
+        mixed-precision kernel (LJ_LIST_TILES_WIDE)."""
         import torch
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
@@ -223,7 +224,7 @@ class LJContext:
         a.number_of_partners, a.pointer = nop.data_ptr(), ptr.data_ptr()
         a.pointer64 = int(pointer64)
         a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0) | \
-            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0) | (capi.LJ_LIST_TILES if tiles else 0)
+            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0) | (capi.LJ_LIST_TILES if tiles else 0) | (capi.LJ_LIST_TILES_WIDE if tiles == "wide" else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         total = C.c_int64(0)
@@ -255,7 +256,7 @@ class LJContext:
         a.sorted_list, a.capacity = pl.sorted_list.data_ptr(), pl.sorted_list.numel()
         a.pointer64 = int(pl.pointer64)
         a.flags = (capi.LJ_LIST_SORT_ROWS if sort_rows else 0) | (capi.LJ_LIST_CLUSTERS if clusters else 0) | \
-            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0) | (capi.LJ_LIST_TILES if tiles else 0)
+            (capi.LJ_LIST_PER_PARTICLE_SEARCH if per_particle else 0) | (capi.LJ_LIST_TILES if tiles else 0) | (capi.LJ_LIST_TILES_WIDE if tiles == "wide" else 0)
         if rows is not None:
             a.row_begin, a.row_end = rows
         self._check(self.lib.lj_build_list(self.h, C.byref(a), None, self._stream(stream)))

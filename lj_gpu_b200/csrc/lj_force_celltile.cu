@@ -50,6 +50,10 @@ constexpr int kCtUnroll = LJ_CT_UNROLL;
 #define LJ_CT_UNROLL_MX 4
 #endif
 constexpr int kCtUnrollMx = LJ_CT_UNROLL_MX;
+#ifndef LJ_CT_LANES_MX
+#define LJ_CT_LANES_MX 8
+#endif
+constexpr int kCtLanesMx = LJ_CT_LANES_MX;  // lanes per row in the mixed kernel: 8 or 4
 
 struct __align__(16) tile_hdr { int ns, self0; uint32_t u0; int yslot0; };
 
@@ -108,8 +112,12 @@ struct ct_params {
 // (one LDS.128 per pair instead of three LDS.64 on 24-byte records), differences are exact integer
 // subtractions, the pair arithmetic is FP32 and the per-row sums are reduced and added to p in
 // FP64 -- see the consumer loop.  Producer, rings and barriers are the same for both precisions.
-template <int LAYOUT, bool MX, int NCONS>
-__global__ void __launch_bounds__((NCONS + 1) * 32, 1)
+// NB = CTAs per SM.  The producer warp needs ~1600 cycles of dependent instructions per tile
+// (measured: 0.14 ms per step with every copy and all pair work switched off), which is half of
+// what 16 consumer warps need to work a tile off -- any hiccup and they wait (22 % of their time).
+// Two CTAs of 8 consumer warps per SM are two independent pipelines at half the tile rate each.
+template <int LAYOUT, bool MX, int NCONS, int NB>
+__global__ void __launch_bounds__((NCONS + 2) * 32, NB)
 lj_celltile_force(const ct_params P) {
   constexpr uint32_t RB = MX ? 16u : 24u;  // bytes per staged position record
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -120,7 +128,9 @@ lj_celltile_force(const ct_params P) {
   // unit ahead: a table entry fetched with a plain load costs a DRAM round trip per tile)
   __shared__ __align__(16) uint2 ytab_s[2][(kCtMaxSeg + 4) * kTileYTab];
   __shared__ __align__(16) uint4 ttab_s[2][kCtMaxSeg * kTileTTab];
-  __shared__ __align__(8) uint64_t tabbar[2];
+  __shared__ __align__(8) uint64_t tabbar[2][2];     // [warp Y | warp L][staging buffer]
+  __shared__ __align__(8) uint64_t mfull[2], mempty[2];  // unit mailbox, warp Y -> warp L
+  __shared__ int umail[2];
   __shared__ float kconst[8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,8 +144,11 @@ lj_celltile_force(const ct_params P) {
   unsigned char* const lbase = smem_raw + (size_t)ry * cap_y * RB;
   if (threadIdx.x == 0) {
     kconst[0] = P.unit2; kconst[1] = P.c24u; kconst[2] = P.c48u; kconst[3] = P.lo_c; kconst[4] = P.cl2f;
-    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NCONS); }
-    mbar_init(&tabbar[0], 1); mbar_init(&tabbar[1], 1);
+    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 2); mbar_init(&tempty[b], NCONS); }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&tabbar[0][b], 1); mbar_init(&tabbar[1][b], 1);
+      mbar_init(&mfull[b], 1); mbar_init(&mempty[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < ry) {  // the dummy record of every y slot: its last one, no copy ever reaches it
@@ -149,82 +162,105 @@ lj_celltile_force(const ct_params P) {
   __syncthreads();
   const int nunits = P.ncols * P.nseg;
 
-  if (warp == NCONS) {
-    // ------------------------------------------------------------------ producer warp ---
-    int yslot = 0;                       // next y-row slot (ring of ry)
+  if (warp >= NCONS) {
+    // ------------------------------------------------------- two producer warps, by role ---
+    // One warp needs ~2800 cycles of dependent instructions per tile (mbarrier polls, table reads,
+    // shuffles, seven serialised UBLKCP) while the consumers work a tile off in ~2100-2700: measured
+    // with LJ_TILE_DBG, the single producer was busy 93 % of the kernel and the consumers waited.
+    // Warp Y stages the y-rows (and the mixed kernel's dummy record), warp L the list segment, the
+    // row metadata and the header; each arrives once on the tile's full barrier (count 2).  Both
+    // walk the same unit sequence: Y claims units from the global counter and posts them to L
+    // through a two-entry mailbox.
+    const bool isY = warp == NCONS;
     int tseq = 0, tslot = 0;             // tile being assembled: sequence number, slot (ring of rl)
     int done = 0, dslot = 0, dphase = 0; // tiles known to be released: [0, done)
+    long long p_idle = 0;                // diagnostics: cycles spent waiting for the consumers
+    const long long p_begin = P.dbg ? clock64() : 0;
     auto ensure_done = [&](int q) {      // block until tile q has been released by every consumer
       while (done <= q) {
+        const long long w0 = P.dbg ? clock64() : 0;
         mbar_wait(&tempty[dslot], dphase);
+        if (P.dbg) p_idle += clock64() - w0;
         done++;
         if (++dslot == rl) { dslot = 0; dphase ^= 1; }
       }
     };
-    // table rows of unit u -> staging buffer b: y-rows max(y0-2,0) .. min(y1+1,ny-1), tiles y0 .. y1-1
+    // k-th unit of this CTA.  Units are dealt dynamically (tiles differ in size by 2x, a static deal
+    // leaves SMs idle at the end); a unit is claimed one ahead so that its tables can be staged early.
+    auto next_unit = [&](int k) {
+      const int b = k & 1;
+      int v = 0;
+      if (isY) {
+        if (lane == 0) v = atomicAdd(P.unit_counter, 1);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if (k >= 2) mbar_wait(&mempty[b], ((k >> 1) - 1) & 1);  // L has read entry k - 2
+        if (lane == 0) { umail[b] = v; mbar_arrive(&mfull[b]); }
+      } else {
+        mbar_wait(&mfull[b], (k >> 1) & 1);
+        v = *reinterpret_cast<volatile int*>(&umail[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mempty[b]);
+      }
+      return v;
+    };
+    // table rows of unit u -> staging buffer b: y-rows max(y0-2,0) .. min(y1+1,ny-1) (warp Y),
+    // tiles y0 .. y1-1 (warp L)
     auto stage_tables = [&](int u, int b) {
       const int col = u % P.ncols, seg = u / P.ncols;
       const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
       const int ylo = max(y0 - 2, 0), yhi = min(y1 + 1, P.ny - 1);
       if (lane == 0) {
-        const uint32_t yb = (uint32_t)(yhi - ylo + 1) * kTileYTab * 8u, tb = (uint32_t)(y1 - y0) * kTileTTab * 16u;
-        mbar_arrive_expect_tx(&tabbar[b], yb + tb);
-        bulk_g2s(&ytab_s[b][0], P.ytab + ((size_t)col * P.ny + ylo) * kTileYTab, yb, &tabbar[b]);
-        bulk_g2s(&ttab_s[b][0], P.ttab + ((size_t)col * P.ny + y0) * kTileTTab, tb, &tabbar[b]);
+        if (isY) {
+          const uint32_t yb = (uint32_t)(yhi - ylo + 1) * kTileYTab * 8u;
+          mbar_arrive_expect_tx(&tabbar[0][b], yb);
+          bulk_g2s(&ytab_s[b][0], P.ytab + ((size_t)col * P.ny + ylo) * kTileYTab, yb, &tabbar[0][b]);
+        } else {
+          const uint32_t tb = (uint32_t)(y1 - y0) * kTileTTab * 16u;
+          mbar_arrive_expect_tx(&tabbar[1][b], tb);
+          bulk_g2s(&ttab_s[b][0], P.ttab + ((size_t)col * P.ny + y0) * kTileTTab, tb, &tabbar[1][b]);
+        }
       }
     };
-    // units are dealt dynamically (tiles differ in size by 2x, a static deal leaves SMs idle at the
-    // end); the next unit is claimed one unit ahead so that its tables can be staged early
-    auto claim = [&]() {
-      int v = 0;
-      if (lane == 0) v = atomicAdd(P.unit_counter, 1);
-      return __shfl_sync(0xffffffffu, v, 0);
-    };
-    int nu = 0;  // units done by this CTA
-    int u = claim();
+    int yslot = 0;  // warp Y: next y-row slot (ring of ry)
+    int nu = 0;     // units done by this CTA
+    int u = next_unit(0);
     if (u < nunits) stage_tables(u, 0);
     for (; u < nunits; nu++) {
-      const int u_next = claim();
+      const int u_next = next_unit(nu + 1);
       const int seg = u / P.ncols;
       const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
       const int ntile = y1 - y0;
       const int tb = nu & 1;
-      // MX: the dummy record rows are padded with.  Fixed-point coordinates live modulo 2^32
-      // counts, so no point is far from everything; half a period away in z from this unit's
-      // cell layer is far from every row of the unit (all in z-cell cz, give or take the skin).
-      int dummy_z = 0;
-      if (MX) {
-        const int cz = (u % P.ncols) / P.ntx;
-        const double zc = P.grid->oz + ((double)cz + 0.5) / P.grid->inv_cell;
-        dummy_z = (int)((uint32_t)__double2ll_rn(zc * P.fx_scale) + 0x80000000u);
-      }
       __syncwarp();  // every lane is done with the other buffer (the previous unit's tables)
       if (u_next < nunits) stage_tables(u_next, tb ^ 1);
-      mbar_wait(&tabbar[tb], (nu >> 1) & 1);
-      const int ylo = max(y0 - 2, 0);
-      auto load_y = [&](int Y) {  // lane dz < 5: {st, pb}; lane 5: {0, length}
-        uint2 e = make_uint2(0u, 0u);
-        if (lane < kTileYTab && Y >= 0 && Y < P.ny) e = ytab_s[tb][(Y - ylo) * kTileYTab + lane];
-        return e;
-      };
-      auto load_t = [&](int cy) {  // lanes 0, 1: the two uint4 of the tile
-        uint4 e = make_uint4(0u, 0u, 0u, 0u);
-        if (lane < kTileTTab && cy >= y0 && cy < y1) e = ttab_s[tb][(cy - y0) * kTileTTab + lane];
-        return e;
-      };
-      uint2 ey_next = load_y(y0 - 2);
-      uint4 et_next = load_t(y0);
-      const int tbase = tseq;
-      int first_yslot = yslot;  // slot of the oldest y-row of the tile being assembled
-      for (int i = 0; i < ntile + 4; i++) {
-        const int Y = y0 - 2 + i;
-        const uint2 ey = ey_next;
-        ey_next = load_y(Y + 1);  // in flight while this iteration waits and issues
-        // the tile this y-row completes on: tile 0 for the first five rows, then one row per tile.
-        // Its slot (barrier, list, header) must be free before the first contribution.
-        if (i == 0 || i > 4) { if (tseq >= rl) ensure_done(tseq - rl); }
-        // ---- y-row Y -> y slot
-        {
+      mbar_wait(&tabbar[isY ? 0 : 1][tb], (nu >> 1) & 1);
+      if (isY) {
+        // ================================================================ warp Y: y-rows
+        // MX: the dummy record rows are padded with.  Fixed-point coordinates live modulo 2^32
+        // counts, so no point is far from everything; half a period away in z from this unit's
+        // cell layer is far from every row of the unit (all in z-cell cz, give or take the skin).
+        int dummy_z = 0;
+        if (MX) {
+          const int cz = (u % P.ncols) / P.ntx;
+          const double zc = P.grid->oz + ((double)cz + 0.5) / P.grid->inv_cell;
+          dummy_z = (int)((uint32_t)__double2ll_rn(zc * P.fx_scale) + 0x80000000u);
+        }
+        const int ylo = max(y0 - 2, 0);
+        auto load_y = [&](int Y) {  // lane dz < 5: {st, pb}; lane 5: {0, length}
+          uint2 e = make_uint2(0u, 0u);
+          if (lane < kTileYTab && Y >= 0 && Y < P.ny) e = ytab_s[tb][(Y - ylo) * kTileYTab + lane];
+          return e;
+        };
+        uint2 ey_next = load_y(y0 - 2);
+        const int tbase = tseq;
+        int first_yslot = yslot;  // slot of the oldest y-row of the tile being assembled
+        for (int i = 0; i < ntile + 4; i++) {
+          const int Y = y0 - 2 + i;
+          const uint2 ey = ey_next;
+          ey_next = load_y(Y + 1);  // in flight while this iteration waits and issues
+          // the tile this y-row completes on: tile 0 for the first five rows, then one row per tile.
+          // Its slot (barrier, header) must be free before the first contribution.
+          if (i == 0 || i > 4) { if (tseq >= rl) ensure_done(tseq - rl); }
           const int rel = yrel[yslot];
           if (rel >= 0) ensure_done(rel);
           const uint32_t pb_next = __shfl_down_sync(0xffffffffu, ey.y, 1);
@@ -249,10 +285,26 @@ lj_celltile_force(const ct_params P) {
             }
           }
           if (++yslot == ry) yslot = 0;
+          if (i >= 4) {  // the tile's five y-rows are on their way: this warp's one arrival
+            if (lane == 0) {
+              hdr[tslot].yslot0 = first_yslot;
+              mbar_arrive(&tfull[tslot]);
+            }
+            tseq++;
+            if (++tslot == rl) tslot = 0;
+            if (++first_yslot == ry) first_yslot = 0;
+          }
         }
-        // ---- tile cy = Y - 2: list segment, metadata, header; then the barrier's one arrival
-        if (i >= 4) {
-          const int cy = Y - 2;
+      } else {
+        // ================================================================ warp L: list, metadata, header
+        auto load_t = [&](int cy) {  // lanes 0, 1: the two uint4 of the tile
+          uint4 e = make_uint4(0u, 0u, 0u, 0u);
+          if (lane < kTileTTab && cy >= y0 && cy < y1) e = ttab_s[tb][(cy - y0) * kTileTTab + lane];
+          return e;
+        };
+        uint4 et_next = load_t(y0);
+        for (int cy = y0; cy < y1; cy++) {
+          if (tseq >= rl) ensure_done(tseq - rl);
           const uint4 et = et_next;
           et_next = load_t(cy + 1);
           const uint32_t s0 = __shfl_sync(0xffffffffu, et.x, 0), ns = __shfl_sync(0xffffffffu, et.y, 0);
@@ -263,7 +315,6 @@ lj_celltile_force(const ct_params P) {
           unsigned char* dst = lbase + (size_t)tslot * P.lslot_bytes;
           if (lane == 0) {
             hdr[tslot].ns = (int)ns; hdr[tslot].self0 = (int)self0 + 2 * cap_y; hdr[tslot].u0 = u0;
-            hdr[tslot].yslot0 = first_yslot;
             mbar_arrive_expect_tx(&tfull[tslot], units_c * 16u + ns_c * 16u);
           }
           __syncwarp();
@@ -271,16 +322,19 @@ lj_celltile_force(const ct_params P) {
           if (lane == 1 && ns_c) bulk_g2s(dst + (size_t)P.cap_units * 16, P.meta + s0, ns * 16u, &tfull[tslot]);
           tseq++;
           if (++tslot == rl) tslot = 0;
-          if (++first_yslot == ry) first_yslot = 0;
         }
       }
       u = u_next;
     }
-    // end marker for the consumers: a tile header with ns < 0
+    // end marker for the consumers: a tile header with ns < 0 (both producer warps arrive)
     if (tseq >= rl) ensure_done(tseq - rl);
     if (lane == 0) {
-      hdr[tslot].ns = -1;
+      if (!isY) hdr[tslot].ns = -1;
       mbar_arrive(&tfull[tslot]);
+      if (P.dbg) {  // producer records: {idle, 0, tiles, total}
+        long long* d = P.dbg + ((size_t)gridDim.x * NCONS + 2 * blockIdx.x + (isY ? 0 : 1)) * 4;
+        d[0] = p_idle; d[1] = 0; d[2] = tseq; d[3] = clock64() - p_begin;
+      }
     }
     return;
   }
@@ -317,7 +371,8 @@ lj_celltile_force(const ct_params P) {
       const int4 h = *reinterpret_cast<const int4*>(&hdr[tslot]);  // ns, self0, u0, yslot0
       const int ns = h.x;
       if (ns < 0) break;  // end marker
-      const int nquads = (ns + 3) >> 2;
+      constexpr int kRows = MX ? 32 / kCtLanesMx : 4;  // rows a warp works on in lock step
+      const int nquads = (ns + kRows - 1) / kRows;
       int quad = first;
       const bool had_quad = quad < nquads;
       first = (first + NCONS - nquads % NCONS) % NCONS;
@@ -337,7 +392,15 @@ lj_celltile_force(const ct_params P) {
           // eight records are distinct modulo 8, which runs of consecutive indices are.
           // Two copies of the loop: most tiles have their five y-rows in consecutive ring slots
           // (record address = one IMAD); the others wrap around the end of the ring (+ ISETP, IADD).
-          const uint32_t c1 = ybase_s + off0 * 16u;
+          // G lanes per row, 32/G rows per warp in lock step (a "quad" of the FP64 kernel).  G = 4: eight
+          // rows share the ~110 instructions of row set-up and reduction, twice the trips per set-up.
+          constexpr int G = kCtLanesMx, R = 32 / G;
+          const int lgx = lane & (G - 1), gix = lane / G;
+          // the ring offset of this tile, made opaque (a shuffle) so that ptxas keeps it in a register:
+          // it otherwise re-derives yslot0 * cap_y inside the pair loop, one IMAD per pair
+          const uint32_t c1 = __shfl_sync(0xffffffffu, ybase_s + off0 * 16u, 0);
+          const int ngroups = nquads;  // groups of R rows, dealt round-robin across tiles like the FP64 quads
+          int grp = quad;
           const uint32_t ring_end = ybase_s + ring * 16u, ring_bytes = ring * 16u;
           auto run = [&](auto wrap_tag) {
             constexpr bool WRAP = decltype(wrap_tag)::value;
@@ -348,16 +411,16 @@ lj_celltile_force(const ct_params P) {
               asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
               return v;
             };
-            for (; quad < nquads; quad += NCONS) {
-              const int r = quad * 4 + gi;
+            for (; grp < ngroups; grp += NCONS) {
+              const int r = grp * R + gix;
               const bool valid = r < ns;
               int4 m = make_int4(0, (int)u0, 0, 0);
               if (valid) m = meta[r];
               const int np = m.x;
-              const int trips = (np + 7) >> 3;
+              const int trips = ((np + 7) >> 3) * (8 / G);  // rows are padded to 8 entries
               const int tmin = __reduce_min_sync(0xffffffffu, trips);
               const int tmax = __reduce_max_sync(0xffffffffu, trips);
-              const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lg;
+              const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lgx;
               const int4 me = fetchx(valid ? (uint32_t)(self0 + r) : dummy);
               float fx = 0.f, fy = 0.f, fz = 0.f;
               float nearest = 3.0e38f;  // min |r2 - cl2| over the row's pairs of this lane
@@ -391,7 +454,7 @@ lj_celltile_force(const ct_params P) {
               for (; k + kCtUnrollMx <= tmin; k += kCtUnrollMx) {
                 uint32_t en[kCtUnrollMx];
 #pragma unroll
-                for (int v = 0; v < kCtUnrollMx; v++) en[v] = e[(k + v) * 8];
+                for (int v = 0; v < kCtUnrollMx; v++) en[v] = e[(k + v) * G];
                 int4 pj[kCtUnrollMx];
 #pragma unroll
                 for (int v = 0; v < kCtUnrollMx; v++) pj[v] = fetchx(en[v]);
@@ -399,15 +462,15 @@ lj_celltile_force(const ct_params P) {
                 for (int v = 0; v < kCtUnrollMx; v++) pairx(pj[v]);
               }
               for (; k < tmax; k += 2) {  // warp-uniform; rows that are already done look at the dummy point
-                const uint32_t e0 = k < trips ? (uint32_t)e[k * 8] : dummy;
-                const uint32_t e1 = k + 1 < trips ? (uint32_t)e[(k + 1) * 8] : dummy;
+                const uint32_t e0 = k < trips ? (uint32_t)e[k * G] : dummy;
+                const uint32_t e1 = k + 1 < trips ? (uint32_t)e[(k + 1) * G] : dummy;
                 const int4 p0 = fetchx(e0), p1 = fetchx(e1);
                 pairx(p0);
                 pairx(p1);
               }
               if (nearest <= P.band) {  // rare (about one row in 300 at rho = 1): the borderline pairs, exactly
                 for (int kk = 0; kk < trips; kk++) {
-                  const int4 pj = fetchx((uint32_t)e[kk * 8]);
+                  const int4 pj = fetchx((uint32_t)e[kk * G]);
                   float dx, dy, dz;
                   const float r2 = dist(pj, dx, dy, dz);
                   if (r2 <= lo_c || !(fabsf(r2 - cl2f) <= P.band)) continue;
@@ -424,10 +487,10 @@ lj_celltile_force(const ct_params P) {
                 }
               }
               // FP32 per-lane partial sums (about 17 pairs each), FP64 from here on
-              const double sx = group_sum<8>((double)fx);
-              const double sy = group_sum<8>((double)fy);
-              const double sz = group_sum<8>((double)fz);
-              if (lg == 0 && np > 0) red_mom<LAYOUT>(P.p, m.z, P.plane, sx, sy, sz);
+              const double sx = group_sum<G>((double)fx);
+              const double sy = group_sum<G>((double)fy);
+              const double sz = group_sum<G>((double)fz);
+              if (lgx == 0 && np > 0) red_mom<LAYOUT>(P.p, m.z, P.plane, sx, sy, sz);
               n_quads++;
             }
           };
@@ -503,18 +566,20 @@ lj_celltile_force(const ct_params P) {
   }
 }
 
-template <int LAYOUT, bool MX, int NCONS>
+template <int LAYOUT, bool MX, int NCONS, int NB>
 int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
                     cudaStream_t st) {
   const lj_tile_geom& g = ctx->tl_g;
   const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
+  // per CTA: its share of the SM's 227 KB minus the static shared memory and the 1 KB the system reserves
+  const size_t budget = NB == 1 ? kTileSmemBudget : (size_t)(227 * 1024) / NB - 9 * 1024;
   // ring sizes.  A tile holds five y-rows and one list slot; at a unit boundary the last tile of the
   // old unit and the first tile of the new one hold ten y-rows between them, so fewer than ten
   // y slots drain the pipeline at every boundary.  Prefer >= 10 y slots, then balance look-ahead.
   int ry = 0, rl = 0, best = -1;
   for (int l = kCtMaxL; l >= kTileMinLSlots; l--) {
-    if ((size_t)l * ls + kTileMinYSlots * ys > kTileSmemBudget) continue;
-    int y = (int)((kTileSmemBudget - (size_t)l * ls) / ys);
+    if ((size_t)l * ls + kTileMinYSlots * ys > budget) continue;
+    int y = (int)((budget - (size_t)l * ls) / ys);
     if (y > kCtMaxY) y = kCtMaxY;
     int score = (y - 5 < l - 1) ? y - 5 : l - 1;
     if (y >= 10 && l >= 3) score += 100;
@@ -529,7 +594,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   }
   static const int seg_env = [] { const char* e = getenv("LJ_TILE_SEG"); return e ? atoi(e) : 0; }();
   const int ncols = g.ntx * g.nz;
-  int nseg = (16 * ctx->sm_count + ncols - 1) / ncols;  // >= 16 units per CTA: the dynamic deal ends evenly
+  int nseg = (16 * NB * ctx->sm_count + ncols - 1) / ncols;  // >= 16 units per CTA: the dynamic deal ends evenly
   if (nseg > g.ny / 6) nseg = g.ny / 6;                 // but every unit re-stages four y-rows: keep them long
   if (nseg < 1) nseg = 1;
   int seg_len = seg_env > 0 ? seg_env : (g.ny + nseg - 1) / nseg;
@@ -564,24 +629,24 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
     P.dbg = dbg_buf;
   }
   const size_t smem = (size_t)ry * ys + (size_t)rl * ls;
-  auto kern = lj_celltile_force<LAYOUT, MX, NCONS>;
+  auto kern = lj_celltile_force<LAYOUT, MX, NCONS, NB>;
   static size_t configured = 0;
   if (smem > configured) {
     LJ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int nunits = ncols * nseg;
-  const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
+  const int grid = nunits < NB * ctx->sm_count ? nunits : NB * ctx->sm_count;
   if (getenv("LJ_TILE_DEBUG"))
     fprintf(stderr, "[lj] cell-tile force: %d units (%d columns x %d segments of %d), y ring %d x %zu B, list ring "
             "%d x %zu B, smem %zu B\n", nunits, ncols, nseg, seg_len, ry, ys, rl, ls, smem);
-  kern<<<(unsigned)grid, (NCONS + 1) * 32, smem, st>>>(P);
+  kern<<<(unsigned)grid, (NCONS + 2) * 32, smem, st>>>(P);
   LJ_LAUNCHED(ctx);
   if (P.dbg) {  // diagnostics only: synchronises
     static int dumps = 0;
     cudaStreamSynchronize(st);
     if (dumps++ == 3) {
-      std::vector<long long> h((size_t)4 * NCONS * grid);
+      std::vector<long long> h((size_t)4 * (NCONS + 2) * grid);
       cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       double w = 0, k = 0, q = 0, t = 0, tmax = 0, tmin = 1e30, qmax = 0, qmin = 1e30;
       for (int b = 0; b < grid; b++) {
@@ -591,6 +656,17 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
           w += d[0]; k += d[1]; q += d[2]; t += d[3]; qb += d[2]; if (d[3] > tb) tb = d[3];
         }
         if (tb > tmax) tmax = tb; if (tb < tmin) tmin = tb; if (qb > qmax) qmax = qb; if (qb < qmin) qmin = qb;
+      }
+      {
+        for (int w = 0; w < 2; w++) {
+          double pi = 0, pt = 0, ptl = 0;
+          for (int b = 0; b < grid; b++) {
+            const long long* d = &h[((size_t)grid * NCONS + 2 * b + w) * 4];
+            pi += d[0]; ptl += d[2]; pt += d[3];
+          }
+          fprintf(stderr, "[lj] celltile dbg: producer warp %c avg idle %.0f of %.0f cycles, %.1f tiles per CTA -> busy %.0f cycles per tile\n",
+                  w ? 'L' : 'Y', pi / grid, pt / grid, ptl / grid, (pt - pi) / ptl);
+        }
       }
       const double n = (double)grid * NCONS;
       fprintf(stderr, "[lj] celltile dbg: per warp avg wait %.0f, work %.0f, total %.0f cycles, quads %.1f (%.0f cycles/quad); "
@@ -627,9 +703,10 @@ int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, do
     const int nc = nc_env ? nc_env : kCtConsumersMx;
 #define LJ_CT_MX(L)                                                                        \
     switch (nc) {                                                                          \
-      case 24: return launch_celltile<L, true, 24>(ctx, a, c24, c48, cl2_bits, st);        \
-      case 31: return launch_celltile<L, true, 31>(ctx, a, c24, c48, cl2_bits, st);        \
-      default: return launch_celltile<L, true, 16>(ctx, a, c24, c48, cl2_bits, st);        \
+      case 8: return launch_celltile<L, true, 8, 2>(ctx, a, c24, c48, cl2_bits, st);       \
+      case 24: return launch_celltile<L, true, 24, 1>(ctx, a, c24, c48, cl2_bits, st);     \
+      case 30: return launch_celltile<L, true, 30, 1>(ctx, a, c24, c48, cl2_bits, st);     \
+      default: return launch_celltile<L, true, 16, 1>(ctx, a, c24, c48, cl2_bits, st);     \
     }
     switch (a->layout) {
       case LJ_AOS_D4: LJ_CT_MX(LJ_AOS_D4)
@@ -639,10 +716,18 @@ int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, do
 #undef LJ_CT_MX
     return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
   }
+  static const int ncf_env = [] { const char* e = getenv("LJ_TILE_CONSUMERS"); return e ? atoi(e) : 0; }();
+  if (ncf_env == 8) {
+    switch (a->layout) {
+      case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, 8, 2>(ctx, a, c24, c48, cl2_bits, st);
+      case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, 8, 2>(ctx, a, c24, c48, cl2_bits, st);
+      case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, 8, 2>(ctx, a, c24, c48, cl2_bits, st);
+    }
+  }
   switch (a->layout) {
-    case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, kCtConsumers>(ctx, a, c24, c48, cl2_bits, st);
-    case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, kCtConsumers>(ctx, a, c24, c48, cl2_bits, st);
-    case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, kCtConsumers>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, kCtConsumers, 1>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, kCtConsumers, 1>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, kCtConsumers, 1>(ctx, a, c24, c48, cl2_bits, st);
   }
   return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
 }

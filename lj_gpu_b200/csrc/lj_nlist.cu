@@ -1146,11 +1146,11 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
     ctx->tl_qz = ctx->tl_qs + 2 * (size_t)(pn + 2);
     ctx->tl_pn_cap = pn;
   }
-  static const int target_rows = [] {
+  static const int rows_env = [] {
     const char* e = getenv("LJ_TILE_ROWS");
-    const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 40;
+    return e ? atoi(e) : 0;
   }();
+  const int target_rows = rows_env > 0 ? rows_env : (a->flags & LJ_LIST_TILES_WIDE) ? 56 : 40;
   k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
   LJ_LAUNCHED(ctx);
   k_tile_rows<<<(unsigned)blocks_for(pn + 1, 256), 256, 0, st>>>(pn, sorted_pos32, a->number_of_partners,
