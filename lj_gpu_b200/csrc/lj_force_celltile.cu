@@ -1,4 +1,4 @@
-// lj_force_celltile.cu -- FP64 force kernel on the cell-tile mirror (sm_100a).
+// lj_force_celltile.cu -- force kernels on the cell-tile mirror (sm_100a): FP64 and mixed precision.
 //
 // Why: the per-row gather kernels are bound by the L1/LSU data pipe.  A 32-lane LDG.E.256 gather
 // costs ~2 SM-cycles per distinct 128-byte line it touches (8-32 lines), the 4-byte list words are
@@ -7,24 +7,30 @@
 //
 //   * persistent CTAs, one per SM.  A CTA walks COLUMNS of tiles (fixed x-range and z, y
 //     ascending).  The neighbours of a tile are the 25 pencils (y-2..y+2) x (z-2..z+2); the five
-//     pencils of one y form a y-row, and consecutive tiles share four of their five y-rows.  A
-//     producer warp keeps a ring of y-rows in shared memory and stages ONE new y-row per tile
-//     (five TMA bulk copies, cp.async.bulk -> UBLKCP) plus the tile's list segment and row
-//     metadata, each completion counted in bytes on an mbarrier: 16 KB per tile instead of the
-//     60 KB of a whole region (the L2 -> SM path is the scarce resource: ~43 B/cycle/SM);
+//     pencils of one y form a y-row, and consecutive tiles share four of their five y-rows.  Two
+//     producer warps keep the rings in shared memory filled: warp Y stages ONE new y-row per tile
+//     (five TMA bulk copies, cp.async.bulk -> UBLKCP; ten for FP64, see below), warp L the tile's
+//     list segment, its row metadata and its header; completions are counted in bytes on the
+//     tile's mbarrier: ~16 KB per tile instead of the 60 KB of a whole region;
 //   * the mirror list holds 16-bit region-local indices (2 B per pair from HBM instead of 4),
 //     rows padded to 8 entries with an index that points at a far-away dummy point, so the inner
 //     loop has no bounds logic;
-//   * per pair-iteration a warp issues one LDS.U16 and three LDS.64 on packed double3 records at
-//     ~30-cycle latency, instead of one list LDG and one 32-line gather at L2 latency.
+//   * FP64: the ring holds a plane of {x,y} pairs and a plane of z; per pair-iteration a warp
+//     issues LDS.U16 (index), LDS.128 and LDS.64 at ~30-cycle latency instead of one list LDG and
+//     one 32-line gather at L2 latency;
+//   * mixed precision (LJ_PREC_MIXED): the ring holds 16-byte fixed-point records {x, y, z,
+//     original index}, 32-bit counts of a power-of-two unit modulo 2^32 (lj_fx_frame): one LDS.128
+//     per pair, exact integer differences, FP32 pair arithmetic (MUFU.RCP), FP32 per-lane partial
+//     sums, FP64 reduction and momenta.  Pairs within the FP32 error band of the cutoff are left
+//     out of the hot loop and re-decided in FP64 from the caller's positions (rare rows only).
 //
 // Sixteen consumer warps: eight lanes per row, four rows (a quad) per warp in lock step with
 // warp-uniform trip counts, quads dealt round-robin across tiles, shuffle reduction, one
-// RED.ADD.F64 per component and row (exactly one add per step: deterministic).  Results are
+// RED.ADD.F64 per component and row (exactly one add per step: deterministic).  FP64 results are
 // bit-identical to the per-row kernel with group = 8 on the same list order.  Positions are
-// re-permuted into cell order at the start of every step (k_tile_permute, ~10 us at N = 1M), so
-// moving particles are handled exactly like in the per-row kernels: the list decides membership,
-// the current q decides the force.
+// re-permuted into cell order at the start of every step (k_tile_permute[_fx], ~10 us at N = 1M),
+// so moving particles are handled exactly like in the per-row kernels: the list decides
+// membership, the current q decides the force.
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -54,6 +60,12 @@ constexpr int kCtUnrollMx = LJ_CT_UNROLL_MX;
 #define LJ_CT_LANES_MX 8
 #endif
 constexpr int kCtLanesMx = LJ_CT_LANES_MX;  // lanes per row in the mixed kernel: 8 or 4
+#ifndef LJ_CT_ALU_SUB
+#define LJ_CT_ALU_SUB 0
+#endif
+#ifndef LJ_CT_DIAG
+#define LJ_CT_DIAG 0  // 1: the mixed kernel honours LJ_TILE_MODE = 1 (no pair math) and 2 (no gather)
+#endif
 
 struct __align__(16) tile_hdr { int ns, self0; uint32_t u0; int yslot0; };
 
@@ -144,6 +156,7 @@ lj_celltile_force(const ct_params P) {
   unsigned char* const lbase = smem_raw + (size_t)ry * cap_y * RB;
   if (threadIdx.x == 0) {
     kconst[0] = P.unit2; kconst[1] = P.c24u; kconst[2] = P.c48u; kconst[3] = P.lo_c; kconst[4] = P.cl2f;
+    kconst[5] = __int_as_float(0x7fffffff);
     for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 2); mbar_init(&tempty[b], NCONS); }
     for (int b = 0; b < 2; b++) {
       mbar_init(&tabbar[0][b], 1); mbar_init(&tabbar[1][b], 1);
@@ -187,12 +200,16 @@ lj_celltile_force(const ct_params P) {
     };
     // k-th unit of this CTA.  Units are dealt dynamically (tiles differ in size by 2x, a static deal
     // leaves SMs idle at the end); a unit is claimed one ahead so that its tables can be staged early.
+    // The global atomic takes ~2000 cycles to return: warp Y issues the claim of unit k + 1 while it
+    // takes delivery of unit k (the value sits in lane 0's register for a whole unit).
+    int claim_pending = 0;
+    if (isY && lane == 0) claim_pending = atomicAdd(P.unit_counter, 1);
     auto next_unit = [&](int k) {
       const int b = k & 1;
       int v = 0;
       if (isY) {
-        if (lane == 0) v = atomicAdd(P.unit_counter, 1);
-        v = __shfl_sync(0xffffffffu, v, 0);
+        v = __shfl_sync(0xffffffffu, claim_pending, 0);
+        if (lane == 0 && v < nunits) claim_pending = atomicAdd(P.unit_counter, 1);  // claim k + 1, used a unit later
         if (k >= 2) mbar_wait(&mempty[b], ((k >> 1) - 1) & 1);  // L has read entry k - 2
         if (lane == 0) { umail[b] = v; mbar_arrive(&mfull[b]); }
       } else {
@@ -344,7 +361,9 @@ lj_celltile_force(const ct_params P) {
   // live in registers.  Left as kernel parameters, ptxas re-reads the constant bank inside the
   // pair loop (9 of 116 instructions per four pairs).
   float unit2 = 0.f, c24u = 0.f, c48u = 0.f, lo_c = 0.f, cl2f = 0.f;
+  int kbig = 0x7fffffff;  // INT_MAX, opaque to ptxas (LJ_CT_ALU_SUB)
   if (MX) {
+    asm volatile("ld.volatile.shared.s32 %0, [%1+20];" : "=r"(kbig) : "r"(smem_u32(kconst)));
     const uint32_t ka = smem_u32(kconst);
     asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(unit2) : "r"(ka));
     asm volatile("ld.volatile.shared.f32 %0, [%1+4];" : "=f"(c24u) : "r"(ka));
@@ -384,7 +403,6 @@ lj_celltile_force(const ct_params P) {
         const int4* __restrict__ meta = reinterpret_cast<const int4*>(lptr + (size_t)P.cap_units * 16);
         // region-local index L -> ring record: (slot of the tile's first y-row) * cap_y + L, wrapped
         const uint32_t off0 = (uint32_t)h.w * (uint32_t)cap_y;
-        const uint32_t off0w = off0 - ring;
         if constexpr (MX) {
           // ---------------------------------------------------------- mixed precision ---
           // Same quads, same lock-step trips; per pair one LDS.U16 (index) and one LDS.128 (record).
@@ -399,6 +417,9 @@ lj_celltile_force(const ct_params P) {
           // the ring offset of this tile, made opaque (a shuffle) so that ptxas keeps it in a register:
           // it otherwise re-derives yslot0 * cap_y inside the pair loop, one IMAD per pair
           const uint32_t c1 = __shfl_sync(0xffffffffu, ybase_s + off0 * 16u, 0);
+#if LJ_CT_DIAG
+          const int dmode = P.mode & 15;
+#endif
           const int ngroups = nquads;  // groups of R rows, dealt round-robin across tiles like the FP64 quads
           int grp = quad;
           const uint32_t ring_end = ybase_s + ring * 16u, ring_bytes = ring * 16u;
@@ -424,11 +445,22 @@ lj_celltile_force(const ct_params P) {
               const int4 me = fetchx(valid ? (uint32_t)(self0 + r) : dummy);
               float fx = 0.f, fy = 0.f, fz = 0.f;
               float nearest = 3.0e38f;  // min |r2 - cl2| over the row's pairs of this lane
+#if LJ_CT_ALU_SUB
+              const int4 nme = make_int4((int)(0u - (uint32_t)me.x), (int)(0u - (uint32_t)me.y), (int)(0u - (uint32_t)me.z), 0);
+#endif
               // r2 from exact differences in counts (modulo 2^32: correct for |d| < 2^31 counts)
               auto dist = [&](const int4 pj, float& dx, float& dy, float& dz) {
+#if LJ_CT_ALU_SUB
+                // the subtraction as VIADDMNMX (ALU pipe): ptxas otherwise emits IMAD.IADD, and the FMA
+                // pipe already carries the 12 FP32 operations of the pair
+                dx = (float)__viaddmin_s32(pj.x, nme.x, kbig);
+                dy = (float)__viaddmin_s32(pj.y, nme.y, kbig);
+                dz = (float)__viaddmin_s32(pj.z, nme.z, kbig);
+#else
                 dx = (float)(int)((uint32_t)pj.x - (uint32_t)me.x);
                 dy = (float)(int)((uint32_t)pj.y - (uint32_t)me.y);
                 dz = (float)(int)((uint32_t)pj.z - (uint32_t)me.z);
+#endif
                 return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) * unit2;
               };
               auto force = [&](float r2) {  // df * unit: the differences stay in counts
@@ -456,8 +488,21 @@ lj_celltile_force(const ct_params P) {
 #pragma unroll
                 for (int v = 0; v < kCtUnrollMx; v++) en[v] = e[(k + v) * G];
                 int4 pj[kCtUnrollMx];
+#if LJ_CT_DIAG
+                if (dmode == 2) {  // diagnostics: all lanes read one record (no conflicts, no gather)
+#pragma unroll
+                  for (int v = 0; v < kCtUnrollMx; v++) en[v] = (en[v] & 0u) + dummy;
+                }
+#endif
 #pragma unroll
                 for (int v = 0; v < kCtUnrollMx; v++) pj[v] = fetchx(en[v]);
+#if LJ_CT_DIAG
+                if (dmode == 1) {  // diagnostics: loads only, no pair arithmetic
+#pragma unroll
+                  for (int v = 0; v < kCtUnrollMx; v++) { fx += __int_as_float(pj[v].x); fy += __int_as_float(pj[v].y); fz += __int_as_float(pj[v].z); }
+                  continue;
+                }
+#endif
 #pragma unroll
                 for (int v = 0; v < kCtUnrollMx; v++) pairx(pj[v]);
               }
