@@ -220,6 +220,22 @@ LJ_API int lj_list_invalidate(lj_ctx* ctx);
 LJ_API int lj_list_result(lj_ctx* ctx, int64_t* number_of_pairs_out, int32_t* max_partners_out,
                    void* stream);
 
+/* ------------------------------------------------ six-array SoA (OpenACC SoA program) - */
+/* The SoA-on-GPU interface of openacc/force_oacc_soa.cpp: six separately allocated device
+ * arrays qx,qy,qz,px,py,pz (:17-22) instead of one block with a plane stride.  `fa` / `la`
+ * carry everything else (list arrays, dt, CL2, variant, ...); their q, p, layout and
+ * plane_stride fields are ignored.  force_reactless (:203-232) = CSR list, force_reactless_memopt
+ * (:234-263) = ELL list.  When the three q (and p) arrays are equally spaced in one allocation
+ * the kernels read them in place (LJ_SOA_D); otherwise q is gathered into a library-owned SoA
+ * block once per call, p is gathered before and scattered back after the `loop` steps, so the
+ * copies amortise over the loop exactly like the reference's acc update device / update host
+ * around its LOOP (:279-292). */
+LJ_API int lj_force_loop_soa6(lj_ctx* ctx, const double* qx, const double* qy, const double* qz,
+                              double* px, double* py, double* pz, const lj_force_args* fa, int loop,
+                              void* stream);
+LJ_API int lj_build_list_soa6(lj_ctx* ctx, const double* qx, const double* qy, const double* qz,
+                              const lj_list_args* la, int64_t* number_of_pairs_out, void* stream);
+
 /* Replaces make_transposed_pairlist() (cuda/force_cuda.cu:229-240): CSR -> column-major
  * ELL with stride pn, zero padding up to max_partners rows.  capacity_entries must be
  * >= max_partners*pn (LJ_ERR_CAPACITY otherwise; max_partners_out tells how many). */

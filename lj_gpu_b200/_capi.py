@@ -92,6 +92,8 @@ PROTOTYPES = {
     "lj_force_step": (C.c_int, [_vp, C.POINTER(LjForceArgs), _vp]),
     "lj_force_loop": (C.c_int, [_vp, C.POINTER(LjForceArgs), C.c_int, C.c_int, _vp]),
     "lj_build_list": (C.c_int, [_vp, C.POINTER(LjListArgs), C.POINTER(_i64), _vp]),
+    "lj_force_loop_soa6": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(LjForceArgs), C.c_int, _vp]),
+    "lj_build_list_soa6": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(LjListArgs), C.POINTER(_i64), _vp]),
     "lj_list_invalidate": (C.c_int, [_vp]),
     "lj_list_result": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i32), _vp]),
     "lj_build_ell": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, C.POINTER(_i32), _vp]),

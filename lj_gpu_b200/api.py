@@ -333,6 +333,60 @@ class LJContext:
             a.row_begin, a.row_end = rows
         return a
 
+    # ------------------------------------------------------------------ six-array SoA
+    def makepair_soa6(self, qx, qy, qz, search_len: float = SEARCH_LENGTH, half: bool = False,
+                      tiles=False, stream=None) -> PairList:
+        """makepair() for the OpenACC SoA program's six separate arrays
+        (openacc/force_oacc_soa.cpp:17-22, 101-141)."""
+        import torch
+        n, dev = qx.numel(), qx.device
+        nop = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        ptr = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        lst = torch.empty(0, dtype=torch.int32, device=dev)
+        a = capi.LjListArgs()
+        a.pn, a.half, a.search_len = n, int(half), search_len
+        a.number_of_partners, a.pointer = nop.data_ptr(), ptr.data_ptr()
+        a.flags = (capi.LJ_LIST_TILES if tiles else 0) | (capi.LJ_LIST_TILES_WIDE if tiles == "wide" else 0)
+        total = C.c_int64(0)
+        st = self._stream(stream)
+        for _ in range(2):
+            a.sorted_list, a.capacity = (lst.data_ptr() if lst.numel() else None), lst.numel()
+            rc = self.lib.lj_build_list_soa6(self.h, qx.data_ptr(), qy.data_ptr(), qz.data_ptr(), C.byref(a),
+                                             C.byref(total), st)
+            if rc == capi.LJ_ERR_CAPACITY and lst.numel() == 0:
+                lst = torch.empty(total.value + total.value // 64 + 1024, dtype=torch.int32, device=dev)
+                continue
+            self._check(rc)
+            break
+        mx = C.c_int32(0)
+        self._check(self.lib.lj_list_result(self.h, C.byref(total), C.byref(mx), st))
+        return PairList(nop, ptr, lst, int(total.value), int(mx.value), half)
+
+    def force_loop_soa6(self, qx, qy, qz, px, py, pz, pl: PairList, loop: int = LOOP, dt: float = DT,
+                        cl2: float = CL2, ell: bool = False, variant="auto", group: int = 0,
+                        precision: str = "fp64", stream=None):
+        """force_reactless / force_reactless_memopt of the OpenACC SoA program
+        (openacc/force_oacc_soa.cpp:203-263) on its six arrays, LOOP times (measure(), :279-284)."""
+        a = capi.LjForceArgs()
+        a.pn, a.dt, a.cl2 = qx.numel(), dt, cl2
+        if ell:
+            if pl.transposed_list is None:
+                raise ValueError("call make_transposed_pairlist first")
+            a.list, a.pointer, a.list_layout = pl.transposed_list.data_ptr(), None, LJ_LIST_ELL
+        else:
+            a.list, a.pointer, a.list_layout = pl.sorted_list.data_ptr(), pl.pointer.data_ptr(), LJ_LIST_CSR
+            a.list_entries = pl.sorted_list.numel()
+        a.number_of_partners = pl.number_of_partners.data_ptr()
+        v = VARIANTS[variant] if isinstance(variant, str) else variant
+        if pl.half and not ell:
+            v = LJ_VARIANT_NEWTON3
+        a.variant, a.group = v, group
+        a.precision = {"fp64": LJ_PREC_FP64, "mixed": LJ_PREC_MIXED}[precision]
+        a.pointer64 = int(pl.pointer64)
+        self._check(self.lib.lj_force_loop_soa6(self.h, qx.data_ptr(), qy.data_ptr(), qz.data_ptr(),
+                                                px.data_ptr(), py.data_ptr(), pz.data_ptr(), C.byref(a), loop,
+                                                self._stream(stream)))
+
     def force_step(self, q, p, pl: PairList, stream=None, **kw):
         """One kernel launch of measure() (cuda/force_cuda.cu:334): p += dt * F(q), in place."""
         a = self.force_args(q, p, pl, **kw)

@@ -94,6 +94,9 @@ struct lj_ctx {
   uint32_t* tl_off = nullptr;            // [pn+1] exclusive scan of tl_units
   double* tl_qs = nullptr;               // positions in cell order, refreshed every step: [cap+2] {x,y} ...
   double* tl_qz = nullptr;               // ... followed by [cap+2] z (inside the tl_qs allocation)
+  double* soa6_q = nullptr;              // six-array SoA entry points: gathered q / p planes
+  double* soa6_p = nullptr;
+  int64_t soa6_cap = 0;
   int4* tl_qfx = nullptr;                // [pn+2] the same in 32-bit fixed point + original index (mixed precision)
   int64_t tl_qfx_cap = 0;
   uint32_t* tl_cell_start = nullptr;     // [ncell+1] private copy of the cell offsets

@@ -94,7 +94,7 @@ int lj_ctx_destroy(lj_ctx* ctx) {
   void* frees[] = {ctx->bbox, ctx->grid, ctx->totals, ctx->cell_of, ctx->cell_slot, ctx->cell_count,
                    ctx->cell_start, ctx->sorted_pos, ctx->sorted_tmp, ctx->scan_tmp, ctx->q32,
                    ctx->cl_list, ctx->cl_ptr, ctx->cl_cnt, ctx->tl_geom, ctx->tl_order, ctx->tl_cnt,
-                   ctx->tl_units, ctx->tl_off, ctx->tl_qs, ctx->tl_qfx, ctx->tl_cell_start, ctx->tl_list, ctx->tl_tab, ctx->tl_ttab, ctx->tl_meta};
+                   ctx->tl_units, ctx->tl_off, ctx->tl_qs, ctx->tl_qfx, ctx->soa6_q, ctx->soa6_p, ctx->tl_cell_start, ctx->tl_list, ctx->tl_tab, ctx->tl_ttab, ctx->tl_meta};
   for (void* f : frees)
     if (f) cudaFreeAsync(f, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
@@ -345,6 +345,88 @@ int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int use_grap
   LJ_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, st));
   ctx->launches += ctx->graph_step_launches * loop;  // kernels the replay executes
   return LJ_OK;
+}
+
+// ------------------------------------------------------------------ six-array SoA ------
+// openacc/force_oacc_soa.cpp:17-22 keeps qx,qy,qz,px,py,pz as six separate allocations.
+static bool soa6_in_place(const double* x, const double* y, const double* z, int64_t pn, int64_t* stride) {
+  const ptrdiff_t d1 = y - x, d2 = z - y;
+  if (d1 != d2 || d1 < pn) return false;
+  *stride = (int64_t)d1;
+  return true;
+}
+
+static int soa6_reserve(lj_ctx* ctx, int64_t pn, cudaStream_t st) {
+  if (pn <= ctx->soa6_cap) return LJ_OK;
+  if (ctx->soa6_q) LJ_CUDA(ctx, cudaFreeAsync(ctx->soa6_q, st));
+  if (ctx->soa6_p) LJ_CUDA(ctx, cudaFreeAsync(ctx->soa6_p, st));
+  ctx->soa6_q = ctx->soa6_p = nullptr;
+  const int64_t cap = (pn + 31) & ~(int64_t)31;
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->soa6_q, sizeof(double) * 3 * (size_t)cap, ctx->pool, st));
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->soa6_p, sizeof(double) * 3 * (size_t)cap, ctx->pool, st));
+  ctx->soa6_cap = cap;
+  ctx->graph_loop = -1;
+  return LJ_OK;
+}
+
+static int soa6_gather(lj_ctx* ctx, double* dst, const double* x, const double* y, const double* z,
+                       int64_t pn, cudaStream_t st) {
+  const size_t b = sizeof(double) * (size_t)pn;
+  const int64_t cap = ctx->soa6_cap;
+  LJ_CUDA(ctx, cudaMemcpyAsync(dst, x, b, cudaMemcpyDeviceToDevice, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(dst + cap, y, b, cudaMemcpyDeviceToDevice, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(dst + 2 * cap, z, b, cudaMemcpyDeviceToDevice, st));
+  return LJ_OK;
+}
+
+int lj_force_loop_soa6(lj_ctx* ctx, const double* qx, const double* qy, const double* qz, double* px,
+                       double* py, double* pz, const lj_force_args* fa, int loop, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, fa && qx && qy && qz && px && py && pz && loop >= 0, "lj_force_loop_soa6: bad arguments");
+  cudaStream_t st = lj_stream(ctx, stream);
+  const int64_t pn = fa->pn;
+  if (pn == 0 || loop == 0) return LJ_OK;
+  lj_force_args a = *fa;
+  a.layout = LJ_SOA_D;
+  int64_t sq = 0, sp = 0;
+  const bool q_in_place = soa6_in_place(qx, qy, qz, pn, &sq);
+  const bool p_in_place = soa6_in_place(px, py, pz, pn, &sp);
+  if (q_in_place && p_in_place && sq == sp) {  // one block each, same spacing: nothing to copy
+    a.q = qx; a.p = px; a.plane_stride = sq;
+    return lj_force_loop(ctx, &a, loop, 0, stream);
+  }
+  int rc = soa6_reserve(ctx, pn, st);
+  if (rc) return rc;
+  if ((rc = soa6_gather(ctx, ctx->soa6_q, qx, qy, qz, pn, st))) return rc;
+  if ((rc = soa6_gather(ctx, ctx->soa6_p, px, py, pz, pn, st))) return rc;
+  a.q = ctx->soa6_q; a.p = ctx->soa6_p; a.plane_stride = ctx->soa6_cap;
+  if ((rc = lj_force_loop(ctx, &a, loop, 0, stream))) return rc;
+  const size_t b = sizeof(double) * (size_t)pn;
+  LJ_CUDA(ctx, cudaMemcpyAsync(px, ctx->soa6_p, b, cudaMemcpyDeviceToDevice, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(py, ctx->soa6_p + ctx->soa6_cap, b, cudaMemcpyDeviceToDevice, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(pz, ctx->soa6_p + 2 * ctx->soa6_cap, b, cudaMemcpyDeviceToDevice, st));
+  return LJ_OK;
+}
+
+int lj_build_list_soa6(lj_ctx* ctx, const double* qx, const double* qy, const double* qz,
+                       const lj_list_args* la, int64_t* number_of_pairs_out, void* stream) {
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  LJ_REQUIRE(ctx, la && qx && qy && qz, "lj_build_list_soa6: bad arguments");
+  cudaStream_t st = lj_stream(ctx, stream);
+  lj_list_args a = *la;
+  a.layout = LJ_SOA_D;
+  int64_t sq = 0;
+  if (soa6_in_place(qx, qy, qz, a.pn, &sq)) {
+    a.q = qx; a.plane_stride = sq;
+  } else {
+    int rc = soa6_reserve(ctx, a.pn, st);
+    if (rc) return rc;
+    if ((rc = soa6_gather(ctx, ctx->soa6_q, qx, qy, qz, a.pn, st))) return rc;
+    a.q = ctx->soa6_q; a.plane_stride = ctx->soa6_cap;
+  }
+  // the cell-tile mirror is tied to the arrays of one call sequence; a gathered q block is
+  // refreshed by every soa6 call, so the mirror stays valid for lj_force_loop_soa6
+  return lj_build_list(ctx, &a, number_of_pairs_out, stream);
 }
 
 // ------------------------------------------------------------------ measure() ---------

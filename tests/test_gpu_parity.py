@@ -669,6 +669,46 @@ def test_full_size_1M_properties_and_oracle(ctx, torch, oracle):
         assert np.abs(pmx.cpu().numpy()[:, :3] - p_o).max() / scale < TOL_MIXED
 
 
+# ------------------------------------------------------------------------ six-array SoA
+def test_six_array_soa_interface_of_the_openacc_program(ctx, torch, sysS):
+    """openacc/force_oacc_soa.cpp keeps qx,qy,qz,px,py,pz as six separate allocations (:17-22):
+    list build and force loop on them, separately allocated (gathered into a library-owned block)
+    and as equally spaced views of one allocation (read in place); CSR, ELL, cell-tile, mixed."""
+    s = sysS
+    qs = [torch.from_numpy(np.ascontiguousarray(s.q[:, c])).cuda() for c in range(3)]
+    junk = torch.empty(1237, device="cuda")                       # breaks any regular spacing
+    ps = [torch.zeros(s.pn, dtype=torch.float64, device="cuda") for _ in range(3)]
+    pl = ctx.makepair_soa6(*qs, tiles=True)
+    nop, ptr, lst = list_to_host(pl)
+    assert pl.number_of_pairs == len(s.full[2]) and np.array_equal(nop[:s.pn], s.full[0])
+    assert np.array_equal(s.lo.sort_rows(nop, ptr, lst), s.full[2])
+    for kw, tol in ((dict(variant="subwarp", group=8), TOL_FP64), (dict(variant="celltile"), TOL_FP64),
+                    (dict(variant="celltile", precision="mixed"), TOL_MIXED)):
+        for p in ps:
+            p.zero_()
+        ctx.force_loop_soa6(*qs, *ps, pl, loop=s.steps, **kw)
+        ph = torch.stack(ps, dim=1).cpu().numpy()
+        assert np.abs(ph - s.p).max() / s.scale < tol, kw
+    ctx.make_transposed_pairlist(pl)
+    for p in ps:
+        p.zero_()
+    ctx.force_loop_soa6(*qs, *ps, pl, loop=s.steps, ell=True)      # force_reactless_memopt
+    assert np.abs(torch.stack(ps, dim=1).cpu().numpy() - s.p).max() / s.scale < TOL_FP64
+    # one allocation, equal spacing: no copies (the p views are updated in place)
+    stride = s.pn + 8
+    qb = torch.zeros(3 * stride, dtype=torch.float64, device="cuda")
+    pb = torch.zeros(3 * stride, dtype=torch.float64, device="cuda")
+    qv = [qb[c * stride:c * stride + s.pn] for c in range(3)]
+    pv = [pb[c * stride:c * stride + s.pn] for c in range(3)]
+    for c in range(3):
+        qv[c].copy_(qs[c])
+    pl2 = ctx.makepair_soa6(*qv)
+    assert pl2.number_of_pairs == pl.number_of_pairs
+    ctx.force_loop_soa6(*qv, *pv, pl2, loop=s.steps, variant="subwarp", group=8)
+    assert np.abs(torch.stack(pv, dim=1).cpu().numpy() - s.p).max() / s.scale < TOL_FP64
+    del junk
+
+
 # ------------------------------------------------------------------------ cell-tile mirror
 def _rows_as_sets(nop, ptr, lst, pn):
     rows = np.repeat(np.arange(pn, dtype=np.int64), nop[:pn])
