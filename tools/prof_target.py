@@ -11,6 +11,7 @@ ap.add_argument("--steps", type=int, default=3); ap.add_argument("--rebuild", ty
 ap.add_argument("--prec", default="fp64"); ap.add_argument("--L", type=float, default=100.1)
 ap.add_argument("--density", type=float, default=1.0); ap.add_argument("--sort-rows", action="store_true")
 ap.add_argument("--tb", type=int, default=0); ap.add_argument("--layout", default="aos4")
+ap.add_argument("--wide", action="store_true", help="mirror with the wide tiles of the mixed kernel")
 a = ap.parse_args()
 import numpy as np, torch
 from lj_gpu_b200 import LJContext, init_fcc
@@ -25,6 +26,8 @@ else:
 npn = pn if a.layout == "soa" else None
 qd = torch.from_numpy(qh).cuda(); pd = torch.zeros_like(qd)
 tiles = a.variant in ("celltile", "auto")
+if tiles and a.wide:
+    tiles = "wide"
 pl = ctx.makepair(qd, layout=a.layout, pn=npn, sort_rows=a.sort_rows, clusters=(a.variant == "cluster"), tiles=tiles)
 for _ in range(a.rebuild):
     ctx.rebuild(qd, pl, layout=a.layout, pn=npn, sort_rows=a.sort_rows, clusters=(a.variant == "cluster"), tiles=tiles)
