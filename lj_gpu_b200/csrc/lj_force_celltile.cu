@@ -543,7 +543,9 @@ lj_celltile_force(const ct_params P) {
         } else {
           // ------------------------------------------------------------------ FP64 ---
           const uint32_t zbase_s = smem_u32(zbase);
-          const uint32_t c1 = ybase_s + off0 * 16u, c1z = zbase_s + off0 * 8u;
+          // ring offsets of this tile, opaque to ptxas (see the mixed branch)
+          const uint32_t c1 = __shfl_sync(0xffffffffu, ybase_s + off0 * 16u, 0);
+          const uint32_t c1z = __shfl_sync(0xffffffffu, zbase_s + off0 * 8u, 0);
           const uint32_t ring_end = ybase_s + ring * 16u, ring_xy = ring * 16u, ring_z = ring * 8u;
           auto run = [&](auto wrap_tag) {
             constexpr bool WRAP = decltype(wrap_tag)::value;
@@ -762,6 +764,13 @@ int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, do
     return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
   }
   static const int ncf_env = [] { const char* e = getenv("LJ_TILE_CONSUMERS"); return e ? atoi(e) : 0; }();
+  if (ncf_env == 24) {
+    switch (a->layout) {
+      case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, 24, 1>(ctx, a, c24, c48, cl2_bits, st);
+      case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, 24, 1>(ctx, a, c24, c48, cl2_bits, st);
+      case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, 24, 1>(ctx, a, c24, c48, cl2_bits, st);
+    }
+  }
   if (ncf_env == 8) {
     switch (a->layout) {
       case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, 8, 2>(ctx, a, c24, c48, cl2_bits, st);
