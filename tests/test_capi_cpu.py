@@ -43,6 +43,23 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert not leaked, leaked[:5]
 
 
+def test_enum_values_match_the_header(tmp_path):
+    """Every LJ_* enumerator of include/lj_b200.h has the same value in the ctypes mirror."""
+    from lj_gpu_b200 import _capi
+    text = open(HEADER).read()
+    names = sorted(set(re.findall(r"^\s*(LJ_[A-Z0-9_]+)\s*=\s*\d+", text, flags=re.M)))
+    assert {"LJ_LIST_TILES", "LJ_LIST_TILES_WIDE", "LJ_VARIANT_CELLTILE", "LJ_PREC_MIXED", "LJ_SOA_D"} <= set(names)
+    src = tmp_path / "en.c"
+    src.write_text('#include <stdio.h>\n#include "lj_b200.h"\nint main(void){'
+                   + "".join('printf("%s %%d\\n", (int)%s);' % (n, n) for n in names) + 'return 0;}\n')
+    exe = tmp_path / "en"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n in names:
+        assert hasattr(_capi, n), n
+        assert int(got[n]) == getattr(_capi, n), n
+
+
 def test_struct_layout_matches_the_header(tmp_path):
     from lj_gpu_b200 import _capi
     src = tmp_path / "sz.c"
