@@ -36,7 +36,9 @@ struct lj_tile_geom {
   int max_rows;    // largest number of rows (particles) in one tile
   int max_yrow;    // longest y-row (five pencils), particles; cap_y = max_yrow + 8
   int max_units;   // largest list segment of one tile, in units of 8 entries
-  int pad;
+  int pad;         // the force kernel's unit counter lives here
+  int ncols_active;  // columns (tx, cz) with at least one list entry; the others (ghost layers of a
+  int pad2;          // decomposed run) are skipped by the force kernel
   unsigned long long total_units;  // whole mirror list, units of 8 entries
 };
 
@@ -103,6 +105,8 @@ struct lj_ctx {
   uint16_t* tl_list = nullptr;
   uint2* tl_tab = nullptr;               // [ntiles][6] y-row table (lj_celltile.cuh)
   uint4* tl_ttab = nullptr;              // [ntiles][2] tile table
+  int32_t* tl_cols = nullptr;            // [ncols_active] the active columns, ascending
+  int64_t tl_cols_cap = 0;
   int4* tl_meta = nullptr;               // [pn] {entries, first unit, original index, 0} of row s
   int64_t tl_pn_cap = 0, tl_cells_cap = 0, tl_list_cap = 0, tl_tab_cap = 0;  // particles, cells, units, tiles
   bool tl_valid = false;

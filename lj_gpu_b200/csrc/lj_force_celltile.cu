@@ -103,7 +103,8 @@ struct ct_params {
   float unit2, cl2f, lo_c;  // unit^2; the cutoff^2; r2 <= lo_c = cl2f - margin: inside for sure
   float band;               // |r2 - cl2f| <= band: too close to call in FP32 (slightly above margin)
   const uint2* ytab; const uint4* ttab; const int4* meta; const uint16_t* list;
-  int ntx, ny, ncols;    // tiles per pencil, cells in y, columns = ntx * nz
+  int ntx, ny, ncols;    // tiles per pencil, cells in y, ACTIVE columns (all of them: ntx * nz)
+  const int32_t* cols;   // the active columns, or NULL when every column is active
   int seg_len, nseg;     // a unit = one column x [seg*seg_len, min(ny, (seg+1)*seg_len))
   int cap_y, cap_units, cap_rows;
   int ry, rl;            // ring sizes: y-row slots, tile slots (list + metadata + barriers)
@@ -222,8 +223,9 @@ lj_celltile_force(const ct_params P) {
     };
     // table rows of unit u -> staging buffer b: y-rows max(y0-2,0) .. min(y1+1,ny-1) (warp Y),
     // tiles y0 .. y1-1 (warp L)
-    auto stage_tables = [&](int u, int b) {
-      const int col = u % P.ncols, seg = u / P.ncols;
+    auto stage_tables = [&](int u, int b) {  // returns the unit's column (tx, cz)
+      const int ci = u % P.ncols, seg = u / P.ncols;
+      const int col = P.cols ? __ldg(P.cols + ci) : ci;
       const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
       const int ylo = max(y0 - 2, 0), yhi = min(y1 + 1, P.ny - 1);
       if (lane == 0) {
@@ -237,11 +239,13 @@ lj_celltile_force(const ct_params P) {
           bulk_g2s(&ttab_s[b][0], P.ttab + ((size_t)col * P.ny + y0) * kTileTTab, tb, &tabbar[1][b]);
         }
       }
+      return col;
     };
     int yslot = 0;  // warp Y: next y-row slot (ring of ry)
     int nu = 0;     // units done by this CTA
     int u = next_unit(0);
-    if (u < nunits) stage_tables(u, 0);
+    int col_cur = 0, col_next = 0;
+    if (u < nunits) col_cur = stage_tables(u, 0);
     for (; u < nunits; nu++) {
       const int u_next = next_unit(nu + 1);
       const int seg = u / P.ncols;
@@ -249,7 +253,7 @@ lj_celltile_force(const ct_params P) {
       const int ntile = y1 - y0;
       const int tb = nu & 1;
       __syncwarp();  // every lane is done with the other buffer (the previous unit's tables)
-      if (u_next < nunits) stage_tables(u_next, tb ^ 1);
+      if (u_next < nunits) col_next = stage_tables(u_next, tb ^ 1);
       mbar_wait(&tabbar[isY ? 0 : 1][tb], (nu >> 1) & 1);
       if (isY) {
         // ================================================================ warp Y: y-rows
@@ -258,7 +262,7 @@ lj_celltile_force(const ct_params P) {
         // cell layer is far from every row of the unit (all in z-cell cz, give or take the skin).
         int dummy_z = 0;
         if (MX) {
-          const int cz = (u % P.ncols) / P.ntx;
+          const int cz = col_cur / P.ntx;
           const double zc = P.grid->oz + ((double)cz + 0.5) / P.grid->inv_cell;
           dummy_z = (int)((uint32_t)__double2ll_rn(zc * P.fx_scale) + 0x80000000u);
         }
@@ -342,6 +346,7 @@ lj_celltile_force(const ct_params P) {
         }
       }
       u = u_next;
+      col_cur = col_next;
     }
     // end marker for the consumers: a tile header with ns < 0 (both producer warps arrive)
     if (tseq >= rl) ensure_done(tseq - rl);
@@ -640,7 +645,9 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
     if (rl_env >= kTileMinLSlots && rl_env < rl) rl = rl_env;
   }
   static const int seg_env = [] { const char* e = getenv("LJ_TILE_SEG"); return e ? atoi(e) : 0; }();
-  const int ncols = g.ntx * g.nz;
+  // columns without a single list entry (the ghost layers of a decomposed run) are skipped
+  const bool all_cols = g.ncols_active <= 0 || g.ncols_active >= g.ntx * g.nz;
+  const int ncols = all_cols ? g.ntx * g.nz : g.ncols_active;
   int nseg = (16 * NB * ctx->sm_count + ncols - 1) / ncols;  // >= 16 units per CTA: the dynamic deal ends evenly
   if (nseg > g.ny / 6) nseg = g.ny / 6;                 // but every unit re-stages four y-rows: keep them long
   if (nseg < 1) nseg = 1;
@@ -664,6 +671,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   }
   P.ytab = ctx->tl_tab; P.ttab = ctx->tl_ttab; P.meta = ctx->tl_meta; P.list = ctx->tl_list;
   P.ntx = g.ntx; P.ny = g.ny; P.ncols = ncols; P.seg_len = seg_len; P.nseg = nseg;
+  P.cols = all_cols ? nullptr : ctx->tl_cols;
   P.cap_y = lj_celltile_cap_y(g); P.cap_units = g.max_units; P.cap_rows = g.max_rows;
   P.ry = ry; P.rl = rl; P.lslot_bytes = (int)ls;
   static const int mode_env = [] { const char* e = getenv("LJ_TILE_MODE"); return e ? atoi(e) : 0; }();

@@ -668,6 +668,7 @@ __global__ void k_tile_prepare(const grid_ext* __restrict__ ge, int64_t pn, int 
   tg->nx = g.nx; tg->ny = g.ny; tg->nz = g.nz;
   tg->ntiles = tg->ntx * g.ny * g.nz;
   tg->max_rows = 0; tg->max_yrow = 0; tg->max_units = 0; tg->pad = 0;
+  tg->ncols_active = 0; tg->pad2 = 0;
   tg->total_units = 0;
 }
 
@@ -696,7 +697,8 @@ k_tile_meta(int64_t pn, const int32_t* __restrict__ order, const int32_t* __rest
 // region-local index of the tile's first row (it lives in the centre pencil: dy = 2, dz = 2).
 __global__ void __launch_bounds__(128)
 k_tile_table(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ off,
-             lj_tile_geom* __restrict__ tg, uint2* __restrict__ ytab, uint4* __restrict__ ttab) {
+             lj_tile_geom* __restrict__ tg, uint2* __restrict__ ytab, uint4* __restrict__ ttab,
+             int32_t* __restrict__ col_flag) {
   const lj_tile_geom g = *tg;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.ntiles) return;
@@ -720,6 +722,23 @@ k_tile_table(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict
   atomicMax(&tg->max_rows, (int)(s1 - s0));
   atomicMax(&tg->max_yrow, (int)base);
   atomicMax(&tg->max_units, (int)(off[s1] - off[s0]));
+  if (off[s1] != off[s0]) col_flag[t / g.ny] = 1;  // column (cz * ntx + tx) has work
+}
+
+// flags -> ascending list of the active columns (in place), count into the geometry.  One warp:
+// a few thousand columns at most.
+__global__ void k_tile_cols(int ncols, int32_t* __restrict__ cols, lj_tile_geom* __restrict__ tg) {
+  const int lane = threadIdx.x;
+  int count = 0;
+  for (int base = 0; base < ncols; base += 32) {
+    const int c = base + lane;
+    const bool on = c < ncols && cols[c] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, on);  // every flag of this round is read before any write
+    if (on) cols[count + __popc(b & ((1u << lane) - 1u))] = c;
+    count += __popc(b);
+    __syncwarp();
+  }
+  if (lane == 0) tg->ncols_active = count;
 }
 
 // FILL pass of the mirror: k_search in cell order, writing region-local 16-bit indices.  With
@@ -1189,8 +1208,16 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
   }
   LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_cell_start, ctx->cell_start, sizeof(uint32_t) * ncell1,
                                cudaMemcpyDeviceToDevice, st));
+  const int ncols_all = g.ntx * g.nz;
+  if (ncols_all > ctx->tl_cols_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cols, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    ctx->tl_cols_cap = ncols_all;
+  }
+  LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_cols, 0, sizeof(int32_t) * (size_t)ncols_all, st));
   k_tile_table<<<(unsigned)blocks_for(g.ntiles, 128), 128, 0, st>>>(ctx->tl_cell_start, ctx->tl_off,
-                                                                     ctx->tl_geom, ctx->tl_tab, ctx->tl_ttab);
+                                                                     ctx->tl_geom, ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols);
+  LJ_LAUNCHED(ctx);
+  k_tile_cols<<<1, 32, 0, st>>>(ncols_all, ctx->tl_cols, ctx->tl_geom);
   LJ_LAUNCHED(ctx);
   const unsigned fblocks = (unsigned)blocks_for(pn * kSearchLanes, 256);
 #define LJ_TILE_FILL(PUB, P64)                                                                        \
