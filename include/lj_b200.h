@@ -76,7 +76,8 @@ typedef enum lj_variant {
 
 typedef enum lj_precision {
   LJ_PREC_FP64 = 0,  /* all arithmetic FP64 (the reference's Dtype = double)                */
-  LJ_PREC_MIXED = 1  /* FP32 pair arithmetic on origin-shifted coordinates, FP64 accumulation */
+  LJ_PREC_MIXED = 1  /* FP32 pair arithmetic on 32-bit fixed-point coordinates (exact differences),
+                        FP64 accumulation of the momenta; cutoff decisions near r2 == cl2 in FP64 */
 } lj_precision;
 
 /* ---------------------------------------------------------------- context ------------- */
