@@ -197,6 +197,8 @@ def run_cuda(args):
     # "auto" on a list the library builds itself: the build also emits the cell-tile mirror and the
     # FP64 step runs on it (k_tile_permute + lj_celltile_force, two launches per step)
     use_tiles = args.variant in ("auto", "celltile")
+    if use_tiles and args.prec == "mixed":
+        use_tiles = "wide"   # LJ_LIST_TILES_WIDE: the tile size the mixed kernel prefers
     pl = ctx.makepair(qd, pointer64=False, clusters=use_cl, tiles=use_tiles)
     P = pl.number_of_pairs
     fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
