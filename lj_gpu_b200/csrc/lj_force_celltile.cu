@@ -43,7 +43,7 @@ namespace {
 #ifndef LJ_CT_CONSUMERS
 #define LJ_CT_CONSUMERS 16
 #endif
-constexpr int kCtConsumers = LJ_CT_CONSUMERS;  // consumer warps of the FP64 kernel (+ one producer warp)
+constexpr int kCtConsumers = LJ_CT_CONSUMERS;  // consumer warps of the FP64 kernel (+ two producer warps)
 #ifndef LJ_CT_CONSUMERS_MX
 #define LJ_CT_CONSUMERS_MX 16
 #endif
@@ -61,7 +61,7 @@ constexpr int kCtUnrollMx = LJ_CT_UNROLL_MX;
 #endif
 constexpr int kCtLanesMx = LJ_CT_LANES_MX;  // lanes per row in the mixed kernel: 8 or 4
 #ifndef LJ_CT_ALU_SUB
-#define LJ_CT_ALU_SUB 0
+#define LJ_CT_ALU_SUB 0  // 1: integer differences as VIADDMNMX on the ALU pipe (measured: no gain)
 #endif
 #ifndef LJ_CT_DIAG
 #define LJ_CT_DIAG 0  // 1: the mixed kernel honours LJ_TILE_MODE = 1 (no pair math) and 2 (no gather)
