@@ -242,6 +242,8 @@ lj_celltile_force(const ct_params P) {
       return col;
     };
     int yslot = 0;  // warp Y: next y-row slot (ring of ry)
+    double grid_oz = 0.0, grid_edge = 0.0;  // MX, warp Y: read once (two global loads and a division)
+    if (MX && isY) { grid_oz = P.grid->oz; grid_edge = 1.0 / P.grid->inv_cell; }
     int nu = 0;     // units done by this CTA
     int u = next_unit(0);
     int col_cur = 0, col_next = 0;
@@ -263,7 +265,7 @@ lj_celltile_force(const ct_params P) {
         int dummy_z = 0;
         if (MX) {
           const int cz = col_cur / P.ntx;
-          const double zc = P.grid->oz + ((double)cz + 0.5) / P.grid->inv_cell;
+          const double zc = grid_oz + ((double)cz + 0.5) * grid_edge;
           dummy_z = (int)((uint32_t)__double2ll_rn(zc * P.fx_scale) + 0x80000000u);
         }
         const int ylo = max(y0 - 2, 0);
