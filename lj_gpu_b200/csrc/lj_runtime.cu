@@ -383,6 +383,7 @@ int lj_force_loop_soa6(lj_ctx* ctx, const double* qx, const double* qy, const do
                        double* py, double* pz, const lj_force_args* fa, int loop, void* stream) {
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, fa && qx && qy && qz && px && py && pz && loop >= 0, "lj_force_loop_soa6: bad arguments");
+  LJ_REQUIRE(ctx, fa->pn >= 0, "lj_force_loop_soa6: negative particle_number");
   cudaStream_t st = lj_stream(ctx, stream);
   const int64_t pn = fa->pn;
   if (pn == 0 || loop == 0) return LJ_OK;
@@ -412,6 +413,7 @@ int lj_build_list_soa6(lj_ctx* ctx, const double* qx, const double* qy, const do
                        const lj_list_args* la, int64_t* number_of_pairs_out, void* stream) {
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, la && qx && qy && qz, "lj_build_list_soa6: bad arguments");
+  LJ_REQUIRE(ctx, la->pn >= 0 && la->pn < 2147483647LL, "lj_build_list_soa6: particle_number out of range");
   cudaStream_t st = lj_stream(ctx, stream);
   lj_list_args a = *la;
   a.layout = LJ_SOA_D;
