@@ -15,8 +15,12 @@
 //   --density R  --L X  --layout aos3|aos4|soa  --variant auto|warp|thread|subwarp|tile|n3
 //   --group G  --prec fp64|mixed  --steps K  --rebuild-every M  --graph  --test  --all
 //   --cache   use / create the reference's text pair cache .cache_pair_{all,half}.dat in the CWD
+//   --soa6    the OpenACC SoA program (openacc/force_oacc_soa.cpp): six separate arrays, CSR run
+//             (acc_reactless_soa) then transposed-list run (acc_reactless_memopt_soa), each followed
+//             by print_results()
 //             (loadpair()/makepaircache(), cuda/force_cuda.cu:165-227): a cached list is uploaded
 //             like the reference does, otherwise the list is built on the GPU and written out
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,7 +36,7 @@ struct Options {
   double density = 0.5, L = 50.0;
   std::string layout = "aos4", variant = "auto", prec = "fp64";
   int group = 0, steps = 100, rebuild_every = 0;
-  bool graph = false, test = false, all = false, cache = false;
+  bool graph = false, test = false, all = false, cache = false, soa6 = false;
 };
 
 [[noreturn]] void die(lj_ctx* ctx, int rc, const char* where) {
@@ -141,6 +145,76 @@ void measure(lj_ctx* ctx, const Options& o, const std::vector<double>& xyz, int6
   if (print) print_results(p, pn, lay);
 }
 
+// The OpenACC SoA program (openacc/force_oacc_soa.cpp) on the new library: six separately
+// allocated arrays qx,qy,qz,px,py,pz (:17-22), makepair + CSR list (force_reactless, OACC_REF) or
+// the transposed list (force_reactless_memopt, OACC_TRANS), LOOP force calls between one upload
+// and one download (measure(), :265-296), print_results() (:298-306).
+void measure_soa6(lj_ctx* ctx, const Options& o, const std::vector<double>& xyz, int64_t pn, bool transposed) {
+  std::vector<double> h[3];
+  for (int c = 0; c < 3; c++) {
+    h[c].resize((size_t)pn);
+    for (int64_t i = 0; i < pn; i++) h[c][(size_t)i] = xyz[3 * i + c];
+  }
+  void* q[3] = {nullptr, nullptr, nullptr};
+  void* p[3] = {nullptr, nullptr, nullptr};
+  void *nop = nullptr, *ptr = nullptr, *list = nullptr, *tl = nullptr, *spacer = nullptr;
+  const size_t b = (size_t)pn * sizeof(double);
+  int rc = LJ_OK;
+  for (int c = 0; c < 3 && !rc; c++) {
+    rc = lj_dev_alloc(ctx, b, &q[c], nullptr);
+    if (!rc && c == 0) rc = lj_dev_alloc(ctx, 4096 + 8 * 17, &spacer, nullptr);  // no regular spacing
+    if (!rc) rc = lj_dev_alloc(ctx, b, &p[c], nullptr);
+    if (!rc) rc = lj_upload(ctx, q[c], h[c].data(), b, nullptr);
+  }
+  std::vector<double> zero((size_t)pn, 0.0);
+  for (int c = 0; c < 3 && !rc; c++) rc = lj_upload(ctx, p[c], zero.data(), b, nullptr);
+  if (!rc) rc = lj_dev_alloc(ctx, (size_t)pn * 4, &nop, nullptr);
+  if (!rc) rc = lj_dev_alloc(ctx, (size_t)pn * 4, &ptr, nullptr);
+  if (rc) die(ctx, rc, "measure_soa6: allocate");
+  lj_list_args l{};
+  l.pn = pn; l.search_len = 3.3;
+  l.number_of_partners = (int32_t*)nop; l.pointer = ptr;
+  int64_t npairs = 0;
+  rc = lj_build_list_soa6(ctx, (double*)q[0], (double*)q[1], (double*)q[2], &l, &npairs, nullptr);
+  if (rc == LJ_ERR_CAPACITY) rc = LJ_OK;  // first call sizes the list
+  if (!rc) rc = lj_dev_alloc(ctx, (size_t)(npairs ? npairs : 1) * 4, &list, nullptr);
+  l.sorted_list = (int32_t*)list; l.capacity = npairs;
+  if (!rc) rc = lj_build_list_soa6(ctx, (double*)q[0], (double*)q[1], (double*)q[2], &l, &npairs, nullptr);
+  if (rc) die(ctx, rc, "lj_build_list_soa6");
+  lj_force_args a{};
+  a.pn = pn; a.dt = 0.001; a.cl2 = 3.0 * 3.0;
+  a.number_of_partners = (int32_t*)nop;
+  a.variant = LJ_VARIANT_AUTO;
+  a.precision = o.prec == "mixed" ? LJ_PREC_MIXED : LJ_PREC_FP64;
+  a.threads_per_block = o.thread_block;
+  if (transposed) {  // make_transposed_list() (:143-154)
+    int32_t max_np = 0;
+    rc = lj_list_result(ctx, nullptr, &max_np, nullptr);
+    if (!rc) rc = lj_dev_alloc(ctx, (size_t)(max_np ? max_np : 1) * (size_t)pn * 4, &tl, nullptr);
+    if (!rc) rc = lj_build_ell(ctx, (int32_t*)list, (int32_t*)nop, ptr, 0, pn, (int32_t*)tl, (int64_t)max_np * pn, &max_np, nullptr);
+    if (rc) die(ctx, rc, "lj_build_ell");
+    a.list = (int32_t*)tl; a.pointer = nullptr; a.list_layout = LJ_LIST_ELL;
+  } else {
+    a.list = (int32_t*)list; a.pointer = ptr; a.list_layout = LJ_LIST_CSR; a.list_entries = npairs;
+  }
+  lj_sync(ctx, nullptr);
+  const auto t0 = std::chrono::steady_clock::now();
+  rc = lj_force_loop_soa6(ctx, (double*)q[0], (double*)q[1], (double*)q[2], (double*)p[0], (double*)p[1],
+                          (double*)p[2], &a, o.steps, nullptr);
+  if (!rc) rc = lj_sync(ctx, nullptr);
+  if (rc) die(ctx, rc, "lj_force_loop_soa6");
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::fprintf(stderr, "N=%d, %s %f [sec] (without Host<->Device)\n", (int)pn,
+               transposed ? "acc_reactless_memopt_soa" : "acc_reactless_soa", sec);
+  for (int c = 0; c < 3 && !rc; c++) rc = lj_download(ctx, h[c].data(), p[c], b, nullptr);
+  if (!rc) rc = lj_sync(ctx, nullptr);
+  if (rc) die(ctx, rc, "measure_soa6: download");
+  for (int64_t i = 0; i < 5; i++) std::fprintf(stdout, "%.10f %.10f %.10f\n", h[0][i], h[1][i], h[2][i]);
+  for (int64_t i = pn - 5; i < pn; i++) std::fprintf(stdout, "%.10f %.10f %.10f\n", h[0][i], h[1][i], h[2][i]);
+  for (void* d : {q[0], q[1], q[2], p[0], p[1], p[2], nop, ptr, list, tl, spacer})
+    if (d) lj_dev_free(ctx, d, nullptr);
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -163,6 +237,7 @@ int main(int argc, char** argv) {
     else if (s == "--test") o.test = true;
     else if (s == "--all") o.all = true;
     else if (s == "--cache") o.cache = true;
+    else if (s == "--soa6") o.soa6 = true;
     else if (s[0] != '-') o.thread_block = std::atoi(s.c_str());
     else { std::fprintf(stderr, "unknown option %s\n", s.c_str()); return 1; }
   }
@@ -181,7 +256,12 @@ int main(int argc, char** argv) {
   int rc = lj_ctx_create(&ctx, 0);
   if (rc) die(nullptr, rc, "lj_ctx_create");
 
-  if (o.test) {
+  if (o.soa6) {
+    // openacc/force_oacc_soa.cpp main(): OACC_REF (CSR list) then OACC_TRANS (transposed list);
+    // each prints the ten momenta of ref_data/density*.dat
+    measure_soa6(ctx, o, xyz, pn, false);
+    measure_soa6(ctx, o, xyz, pn, true);
+  } else if (o.test) {
     // the EN_TEST_GPU build: one kernel for double3 then double4, then print p_d3.  Unlike the
     // reference (which re-uploads the accumulated p, force_cuda.cu:331,338) each measure()
     // here starts from p = 0, so the printed values are those of ONE 100-step run.

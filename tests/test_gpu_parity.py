@@ -602,6 +602,13 @@ def test_cpp_driver_prints_the_goldens():
         assert "[sec] (without Host<->Device)" in r.stderr and "force_kernel_warp_unroll2_double3" in r.stderr
     r = subprocess.run([exe, "32"], capture_output=True, text=True)
     assert r.returncode == 1 and "THREAD_BLOCK size is too large or small." in r.stderr
+    # the OpenACC SoA program on six separate arrays: CSR run, then transposed-list run
+    r = subprocess.run([exe, "--soa6"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    with open(os.path.join(GOLDEN, "density0.5.dat")) as f:
+        gold = f.read()
+    assert r.stdout == gold + gold
+    assert "acc_reactless_soa" in r.stderr and "acc_reactless_memopt_soa" in r.stderr
 
 
 def test_cpp_driver_pair_cache(tmp_path, oracle):
