@@ -331,7 +331,10 @@ def run_cuda(args):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch")
+            if args.prec == "mixed":  # the mixed kernel has its own capture
+                traffic = tj.get("mixed_kernel", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
 
