@@ -5,7 +5,9 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/lj_b200.h"
 
@@ -120,6 +122,14 @@ struct lj_ctx {
   float4* q32 = nullptr;
   int64_t q32_len = 0;
 
+  // per-context (= per-device) record of what cudaFuncSetAttribute has been applied to which kernel:
+  // the attributes are per device, a process-wide flag would leave a second GPU unconfigured
+  std::unordered_map<const void*, size_t> func_smem;  // kernel -> opted-in dynamic shared memory
+  std::unordered_map<const void*, int> func_occ;      // kernel -> resident CTAs per SM (occupancy query)
+
+  long long* diag_buf = nullptr;  // LJ_DIAG builds only: per-warp cycle counters of the cell-tile kernel
+  int diag_dumps = 0;
+
   // cached CUDA graph for lj_force_loop
   cudaGraphExec_t graph_exec = nullptr;
   lj_force_args graph_args{};
@@ -146,6 +156,39 @@ int lj_set_error(lj_ctx* ctx, int status, const char* what, const char* detail);
     (ctx)->launches++;                                                                    \
     cudaError_t e__ = cudaGetLastError();                                                 \
     if (e__ != cudaSuccess) return lj_set_error((ctx), LJ_ERR_CUDA, "kernel launch", cudaGetErrorString(e__)); \
+  } while (0)
+
+// Diagnostic knobs (environment variables LJ_TILE_*) exist only in builds with -DLJ_DIAG=1
+// (make DIAG=1); the product build reads no environment and carries no tuning side doors.
+#ifndef LJ_DIAG
+#define LJ_DIAG 0
+#endif
+static inline int lj_diag_int(const char* name) {
+#if LJ_DIAG
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
+}
+static inline bool lj_diag_set(const char* name) {
+#if LJ_DIAG
+  return getenv(name) != nullptr;
+#else
+  (void)name;
+  return false;
+#endif
+}
+
+// opt a kernel in to `bytes` of dynamic shared memory on this context's device (idempotent, cached per ctx)
+#define LJ_FUNC_SMEM(ctx, kern, bytes)                                                              \
+  do {                                                                                              \
+    size_t& have__ = (ctx)->func_smem[reinterpret_cast<const void*>(kern)];                         \
+    if ((size_t)(bytes) > have__) {                                                                 \
+      LJ_CUDA((ctx), cudaFuncSetAttribute((kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      have__ = (size_t)(bytes);                                                                     \
+    }                                                                                               \
   } while (0)
 
 // NULL is the CUDA legacy default stream, exactly as for a kernel launch: the reference runs

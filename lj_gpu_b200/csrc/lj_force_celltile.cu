@@ -40,14 +40,6 @@
 
 namespace {
 
-#ifndef LJ_CT_CONSUMERS
-#define LJ_CT_CONSUMERS 16
-#endif
-constexpr int kCtConsumers = LJ_CT_CONSUMERS;  // consumer warps of the FP64 kernel (+ two producer warps)
-#ifndef LJ_CT_CONSUMERS_MX
-#define LJ_CT_CONSUMERS_MX 16
-#endif
-constexpr int kCtConsumersMx = LJ_CT_CONSUMERS_MX;  // default for the mixed-precision kernel
 #ifndef LJ_CT_UNROLL
 #define LJ_CT_UNROLL 4
 #endif
@@ -129,9 +121,17 @@ struct ct_params {
 // (measured: 0.14 ms per step with every copy and all pair work switched off), which is half of
 // what 16 consumer warps need to work a tile off -- any hiccup and they wait (22 % of their time).
 // Two CTAs of 8 consumer warps per SM are two independent pipelines at half the tile rate each.
-template <int LAYOUT, bool MX, int NCONS, int NB>
+// WPG = consumer warps per GROUP.  The NCONS / WPG groups take the tiles of the CTA's stream in turn
+// (tile t belongs to group t % NG): a consumer warp visits 1 / NG of the tiles instead of every one
+// (the per-tile visit -- barrier wait, header, arrive -- was 10 % of the executed instructions and
+// 21 % of the stall samples with 16 warps on every tile), and NG tiles are worked on at once, so a
+// group that waits for its tile leaves the other groups' warps on every scheduler.  A group is four
+// consecutive warps = one warp per SM sub-partition.  WPG == NCONS is the single-group pipeline.
+template <int LAYOUT, bool MX, int NCONS, int NB, int WPG>
 __global__ void __launch_bounds__((NCONS + 2) * 32, NB)
 lj_celltile_force(const ct_params P) {
+  static_assert(NCONS % WPG == 0, "whole groups");
+  constexpr int NG = NCONS / WPG;
   constexpr uint32_t RB = MX ? 16u : 24u;  // bytes per staged position record
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t tfull[kCtMaxL], tempty[kCtMaxL];
@@ -158,7 +158,7 @@ lj_celltile_force(const ct_params P) {
   if (threadIdx.x == 0) {
     kconst[0] = P.unit2; kconst[1] = P.c24u; kconst[2] = P.c48u; kconst[3] = P.lo_c; kconst[4] = P.cl2f;
     kconst[5] = __int_as_float(0x7fffffff);
-    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 2); mbar_init(&tempty[b], NCONS); }
+    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 2); mbar_init(&tempty[b], WPG); }
     for (int b = 0; b < 2; b++) {
       mbar_init(&tabbar[0][b], 1); mbar_init(&tabbar[1][b], 1);
       mbar_init(&mfull[b], 1); mbar_init(&mempty[b], 1);
@@ -350,14 +350,20 @@ lj_celltile_force(const ct_params P) {
       u = u_next;
       col_cur = col_next;
     }
-    // end marker for the consumers: a tile header with ns < 0 (both producer warps arrive)
-    if (tseq >= rl) ensure_done(tseq - rl);
+    // end markers for the consumers, one per group: a tile header with ns < 0 (both producer warps arrive)
+    for (int g = 0; g < NG; g++) {
+      if (tseq >= rl) ensure_done(tseq - rl);
+      if (lane == 0) {
+        if (!isY) hdr[tslot].ns = -1;
+        mbar_arrive(&tfull[tslot]);
+      }
+      tseq++;
+      if (++tslot == rl) tslot = 0;
+    }
     if (lane == 0) {
-      if (!isY) hdr[tslot].ns = -1;
-      mbar_arrive(&tfull[tslot]);
       if (P.dbg) {  // producer records: {idle, 0, tiles, total}
         long long* d = P.dbg + ((size_t)gridDim.x * NCONS + 2 * blockIdx.x + (isY ? 0 : 1)) * 4;
-        d[0] = p_idle; d[1] = 0; d[2] = tseq; d[3] = clock64() - p_begin;
+        d[0] = p_idle; d[1] = 0; d[2] = tseq - NG; d[3] = clock64() - p_begin;
       }
     }
     return;
@@ -382,11 +388,11 @@ lj_celltile_force(const ct_params P) {
   const uint32_t ring = (uint32_t)ry * (uint32_t)cap_y;
   const uint32_t ybase_s = smem_u32(ybase);
   const uint32_t dummy = (uint32_t)cap_y - 1u;
-  int tslot = 0, tphase = 0;
+  int tslot = warp / WPG, tphase = 0;  // this group's first tile (rl >= NG: checked at launch)
   long long t_wait = 0, t_work = 0, n_quads = 0;
   const long long t_begin = P.dbg ? clock64() : 0;
-  int first = warp;  // quads are dealt round-robin over the warps ACROSS tiles: tiles hold fewer
-                     // quads than there are warps, a per-tile deal would leave the high warps idle
+  int first = warp % WPG;  // quads are dealt round-robin over the group's warps ACROSS its tiles: a
+                           // per-tile deal would always leave the same warps with the extra quad
   for (;;) {
     {
       long long tw0 = 0;
@@ -401,7 +407,7 @@ lj_celltile_force(const ct_params P) {
       const int nquads = (ns + kRows - 1) / kRows;
       int quad = first;
       const bool had_quad = quad < nquads;
-      first = (first + NCONS - nquads % NCONS) % NCONS;
+      first = (first + WPG - nquads % WPG) % WPG;
       if (quad < nquads && (P.mode & 15) != 3) {
         const int self0 = h.y;
         const uint32_t u0 = (uint32_t)h.z;
@@ -439,7 +445,7 @@ lj_celltile_force(const ct_params P) {
               asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
               return v;
             };
-            for (; grp < ngroups; grp += NCONS) {
+            for (; grp < ngroups; grp += WPG) {
               const int r = grp * R + gix;
               const bool valid = r < ns;
               int4 m = make_int4(0, (int)u0, 0, 0);
@@ -562,7 +568,7 @@ lj_celltile_force(const ct_params P) {
               asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
               asm volatile("ld.shared.f64 %0, [%1];" : "=d"(z) : "r"(az));
             };
-            for (; quad < nquads; quad += NCONS) {
+            for (; quad < nquads; quad += WPG) {
               const int r = quad * 4 + gi;
               const bool valid = r < ns;
               int4 m = make_int4(0, (int)u0, 0, 0);
@@ -611,7 +617,8 @@ lj_celltile_force(const ct_params P) {
       __syncwarp();
       if (P.dbg && had_quad) t_work += clock64() - tw1;
       if (lane == 0) mbar_arrive(&tempty[tslot]);  // this warp is through with the tile
-      if (++tslot == rl) { tslot = 0; tphase ^= 1; }
+      tslot += NG;                                 // the group's next tile
+      if (tslot >= rl) { tslot -= rl; tphase ^= 1; }
     }
   }
   if (P.dbg && lane == 0) {
@@ -620,33 +627,38 @@ lj_celltile_force(const ct_params P) {
   }
 }
 
-template <int LAYOUT, bool MX, int NCONS, int NB>
-int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
-                    cudaStream_t st) {
-  const lj_tile_geom& g = ctx->tl_g;
-  const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
-  // per CTA: its share of the SM's 227 KB minus the static shared memory and the 1 KB the system reserves
-  const size_t budget = NB == 1 ? kTileSmemBudget : (size_t)(227 * 1024) / NB - 9 * 1024;
-  // ring sizes.  A tile holds five y-rows and one list slot; at a unit boundary the last tile of the
-  // old unit and the first tile of the new one hold ten y-rows between them, so fewer than ten
-  // y slots drain the pipeline at every boundary.  Prefer >= 10 y slots, then balance look-ahead.
-  int ry = 0, rl = 0, best = -1;
+// ring sizes for a CTA with `budget` bytes of dynamic shared memory.  A tile holds five y-rows and
+// one list slot; with NG groups NG consecutive tiles are in work at once (NG + 4 y-rows, NG list
+// slots) and the producers should be a few tiles ahead of them.  At a unit boundary the last tile
+// of the old unit and the first tile of the new one hold ten y-rows between them.
+static bool ring_sizes(size_t budget, size_t ys, size_t ls, int ng, int& ry, int& rl) {
+  int best = -1;
+  ry = rl = 0;
   for (int l = kCtMaxL; l >= kTileMinLSlots; l--) {
     if ((size_t)l * ls + kTileMinYSlots * ys > budget) continue;
     int y = (int)((budget - (size_t)l * ls) / ys);
     if (y > kCtMaxY) y = kCtMaxY;
-    int score = (y - 5 < l - 1) ? y - 5 : l - 1;
-    if (y >= 10 && l >= 3) score += 100;
+    // look-ahead in tiles beyond the ng in work, as the y ring and the list ring allow it
+    const int ahead_y = y - 4 - ng, ahead_l = l - ng;
+    int score = ahead_y < ahead_l ? ahead_y : ahead_l;
+    if (score < 1) continue;
+    if (y >= 9 + ng && l >= 2 + ng) score += 100;
     if (score > best) { best = score; ry = y; rl = l; }
   }
-  LJ_REQUIRE(ctx, best >= 0, "lj_force_step: cell-tile geometry does not fit in shared memory");
+  return best >= 0;
+}
+
+template <int LAYOUT, bool MX, int NCONS, int NB, int WPG>
+int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
+                    cudaStream_t st, int ry, int rl) {
+  const lj_tile_geom& g = ctx->tl_g;
+  const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
   {  // diagnostics: cap the ring sizes
-    static const int ry_env = [] { const char* e = getenv("LJ_TILE_RY"); return e ? atoi(e) : 0; }();
-    static const int rl_env = [] { const char* e = getenv("LJ_TILE_RL"); return e ? atoi(e) : 0; }();
+    const int ry_env = lj_diag_int("LJ_TILE_RY"), rl_env = lj_diag_int("LJ_TILE_RL");
     if (ry_env >= kTileMinYSlots && ry_env < ry) ry = ry_env;
-    if (rl_env >= kTileMinLSlots && rl_env < rl) rl = rl_env;
+    if (rl_env >= kTileMinLSlots && rl_env >= NCONS / WPG && rl_env < rl) rl = rl_env;
   }
-  static const int seg_env = [] { const char* e = getenv("LJ_TILE_SEG"); return e ? atoi(e) : 0; }();
+  const int seg_env = lj_diag_int("LJ_TILE_SEG");
   // columns without a single list entry (the ghost layers of a decomposed run) are skipped
   const bool all_cols = g.ncols_active <= 0 || g.ncols_active >= g.ntx * g.nz;
   const int ncols = all_cols ? g.ntx * g.nz : g.ncols_active;
@@ -676,33 +688,30 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   P.cols = all_cols ? nullptr : ctx->tl_cols;
   P.cap_y = lj_celltile_cap_y(g); P.cap_units = g.max_units; P.cap_rows = g.max_rows;
   P.ry = ry; P.rl = rl; P.lslot_bytes = (int)ls;
-  static const int mode_env = [] { const char* e = getenv("LJ_TILE_MODE"); return e ? atoi(e) : 0; }();
-  P.mode = mode_env;
+  P.mode = lj_diag_int("LJ_TILE_MODE");
   P.unit_counter = &ctx->tl_geom->pad;
   P.dbg = nullptr;
-  static long long* dbg_buf = nullptr;
-  if (getenv("LJ_TILE_DBG")) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 32 * 1024);
-    P.dbg = dbg_buf;
+#if LJ_DIAG
+  if (lj_diag_set("LJ_TILE_DBG")) {
+    if (!ctx->diag_buf) cudaMalloc(&ctx->diag_buf, sizeof(long long) * 4 * 32 * 1024);
+    P.dbg = ctx->diag_buf;
   }
+#endif
   const size_t smem = (size_t)ry * ys + (size_t)rl * ls;
-  auto kern = lj_celltile_force<LAYOUT, MX, NCONS, NB>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    LJ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  auto kern = lj_celltile_force<LAYOUT, MX, NCONS, NB, WPG>;
+  LJ_FUNC_SMEM(ctx, kern, smem);
   const int nunits = ncols * nseg;
   const int grid = nunits < NB * ctx->sm_count ? nunits : NB * ctx->sm_count;
-  if (getenv("LJ_TILE_DEBUG"))
-    fprintf(stderr, "[lj] cell-tile force: %d units (%d columns x %d segments of %d), y ring %d x %zu B, list ring "
-            "%d x %zu B, smem %zu B\n", nunits, ncols, nseg, seg_len, ry, ys, rl, ls, smem);
+  if (lj_diag_set("LJ_TILE_DEBUG"))
+    fprintf(stderr, "[lj] cell-tile force: %d consumer warps in groups of %d, %d units (%d columns x %d segments of %d), "
+            "y ring %d x %zu B, list ring %d x %zu B, smem %zu B\n", NCONS, WPG, nunits, ncols, nseg, seg_len, ry, ys, rl,
+            ls, smem);
   kern<<<(unsigned)grid, (NCONS + 2) * 32, smem, st>>>(P);
   LJ_LAUNCHED(ctx);
+#if LJ_DIAG
   if (P.dbg) {  // diagnostics only: synchronises
-    static int dumps = 0;
     cudaStreamSynchronize(st);
-    if (dumps++ == 3) {
+    if (ctx->diag_dumps++ == 3) {
       std::vector<long long> h((size_t)4 * (NCONS + 2) * grid);
       cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       double w = 0, k = 0, q = 0, t = 0, tmax = 0, tmin = 1e30, qmax = 0, qmin = 1e30;
@@ -714,23 +723,52 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
         }
         if (tb > tmax) tmax = tb; if (tb < tmin) tmin = tb; if (qb > qmax) qmax = qb; if (qb < qmin) qmin = qb;
       }
-      {
-        for (int w = 0; w < 2; w++) {
-          double pi = 0, pt = 0, ptl = 0;
-          for (int b = 0; b < grid; b++) {
-            const long long* d = &h[((size_t)grid * NCONS + 2 * b + w) * 4];
-            pi += d[0]; ptl += d[2]; pt += d[3];
-          }
-          fprintf(stderr, "[lj] celltile dbg: producer warp %c avg idle %.0f of %.0f cycles, %.1f tiles per CTA -> busy %.0f cycles per tile\n",
-                  w ? 'L' : 'Y', pi / grid, pt / grid, ptl / grid, (pt - pi) / ptl);
+      for (int pw = 0; pw < 2; pw++) {
+        double pi = 0, pt = 0, ptl = 0;
+        for (int b = 0; b < grid; b++) {
+          const long long* d = &h[((size_t)grid * NCONS + 2 * b + pw) * 4];
+          pi += d[0]; ptl += d[2]; pt += d[3];
         }
+        fprintf(stderr, "[lj] celltile dbg: producer warp %c avg idle %.0f of %.0f cycles, %.1f tiles per CTA -> busy %.0f cycles per tile\n",
+                pw ? 'L' : 'Y', pi / grid, pt / grid, ptl / grid, (pt - pi) / ptl);
       }
       const double n = (double)grid * NCONS;
       fprintf(stderr, "[lj] celltile dbg: per warp avg wait %.0f, work %.0f, total %.0f cycles, quads %.1f (%.0f cycles/quad); "
               "CTA total min %.0f max %.0f, quads per CTA min %.0f max %.0f\n", w / n, k / n, t / n, q / n, k / q, tmin, tmax, qmin, qmax);
     }
   }
+#endif
   return LJ_OK;
+}
+
+// consumer-warp layout: NCONS warps in groups of 4 when the rings hold the groups' tiles plus some
+// look-ahead, else one group (every warp on every tile, the round-1 pipeline)
+template <int LAYOUT, bool MX>
+int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
+                      cudaStream_t st) {
+  const lj_tile_geom& g = ctx->tl_g;
+  const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
+  int ry = 0, rl = 0;
+  const int nc = lj_diag_int("LJ_TILE_CONSUMERS"), wpg = lj_diag_int("LJ_TILE_WPG");
+#if LJ_DIAG
+  if (nc == 8) {  // two CTAs per SM (measured slower: two pipelines, twice the producers)
+    const size_t half = (size_t)(227 * 1024) / 2 - 9 * 1024;
+    LJ_REQUIRE(ctx, ring_sizes(half, ys, ls, 1, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
+    return launch_celltile<LAYOUT, MX, 8, 2, 8>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  }
+  if (nc == 24 && wpg != 24 && ring_sizes(kTileSmemBudget, ys, ls, 6, ry, rl))
+    return launch_celltile<LAYOUT, MX, 24, 1, 4>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  if (nc == 24 && ring_sizes(kTileSmemBudget, ys, ls, 1, ry, rl))
+    return launch_celltile<LAYOUT, MX, 24, 1, 24>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  if (nc == 20 && ring_sizes(kTileSmemBudget, ys, ls, 5, ry, rl))
+    return launch_celltile<LAYOUT, MX, 20, 1, 4>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  if (wpg == 8 && ring_sizes(kTileSmemBudget, ys, ls, 2, ry, rl))
+    return launch_celltile<LAYOUT, MX, 16, 1, 8>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+#endif
+  if (wpg != 16 && ring_sizes(kTileSmemBudget, ys, ls, 4, ry, rl))
+    return launch_celltile<LAYOUT, MX, 16, 1, 4>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, 1, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
+  return launch_celltile<LAYOUT, MX, 16, 1, 16>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
 }
 
 }  // namespace
@@ -754,44 +792,17 @@ int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, do
                              long long cl2_bits, cudaStream_t st) {
   int rc = lj_celltile_permute(ctx, a, st);
   if (rc) return rc;
-  if (a->precision == LJ_PREC_MIXED) {
-    // consumer warps of the mixed kernel: FP32 needs fewer registers, so more warps fit (diagnostics)
-    static const int nc_env = [] { const char* e = getenv("LJ_TILE_CONSUMERS"); return e ? atoi(e) : 0; }();
-    const int nc = nc_env ? nc_env : kCtConsumersMx;
-#define LJ_CT_MX(L)                                                                        \
-    switch (nc) {                                                                          \
-      case 8: return launch_celltile<L, true, 8, 2>(ctx, a, c24, c48, cl2_bits, st);       \
-      case 24: return launch_celltile<L, true, 24, 1>(ctx, a, c24, c48, cl2_bits, st);     \
-      case 30: return launch_celltile<L, true, 30, 1>(ctx, a, c24, c48, cl2_bits, st);     \
-      default: return launch_celltile<L, true, 16, 1>(ctx, a, c24, c48, cl2_bits, st);     \
-    }
-    switch (a->layout) {
-      case LJ_AOS_D4: LJ_CT_MX(LJ_AOS_D4)
-      case LJ_AOS_D3: LJ_CT_MX(LJ_AOS_D3)
-      case LJ_SOA_D: LJ_CT_MX(LJ_SOA_D)
-    }
-#undef LJ_CT_MX
-    return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
-  }
-  static const int ncf_env = [] { const char* e = getenv("LJ_TILE_CONSUMERS"); return e ? atoi(e) : 0; }();
-  if (ncf_env == 24) {
-    switch (a->layout) {
-      case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, 24, 1>(ctx, a, c24, c48, cl2_bits, st);
-      case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, 24, 1>(ctx, a, c24, c48, cl2_bits, st);
-      case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, 24, 1>(ctx, a, c24, c48, cl2_bits, st);
-    }
-  }
-  if (ncf_env == 8) {
-    switch (a->layout) {
-      case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, 8, 2>(ctx, a, c24, c48, cl2_bits, st);
-      case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, 8, 2>(ctx, a, c24, c48, cl2_bits, st);
-      case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, 8, 2>(ctx, a, c24, c48, cl2_bits, st);
-    }
-  }
+  const bool mx = a->precision == LJ_PREC_MIXED;
   switch (a->layout) {
-    case LJ_AOS_D4: return launch_celltile<LJ_AOS_D4, false, kCtConsumers, 1>(ctx, a, c24, c48, cl2_bits, st);
-    case LJ_AOS_D3: return launch_celltile<LJ_AOS_D3, false, kCtConsumers, 1>(ctx, a, c24, c48, cl2_bits, st);
-    case LJ_SOA_D: return launch_celltile<LJ_SOA_D, false, kCtConsumers, 1>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_AOS_D4:
+      return mx ? dispatch_celltile<LJ_AOS_D4, true>(ctx, a, c24, c48, cl2_bits, st)
+                : dispatch_celltile<LJ_AOS_D4, false>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_AOS_D3:
+      return mx ? dispatch_celltile<LJ_AOS_D3, true>(ctx, a, c24, c48, cl2_bits, st)
+                : dispatch_celltile<LJ_AOS_D3, false>(ctx, a, c24, c48, cl2_bits, st);
+    case LJ_SOA_D:
+      return mx ? dispatch_celltile<LJ_SOA_D, true>(ctx, a, c24, c48, cl2_bits, st)
+                : dispatch_celltile<LJ_SOA_D, false>(ctx, a, c24, c48, cl2_bits, st);
   }
   return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
 }

@@ -211,7 +211,7 @@ int launch_tile(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, dou
   kern<<<(unsigned)grid, kTileThreads, smem, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24, c48,
                                                     cl2_bits, a->list, a->number_of_partners,
                                                     a->pointer, a->list_entries,
-                                                    getenv("LJ_TILE_CONTIG") ? 1 : 0);  // contiguous measured slower (0.50 vs 0.45 ms): load imbalance
+                                                    lj_diag_set("LJ_TILE_CONTIG") ? 1 : 0);  // contiguous measured slower (0.50 vs 0.45 ms): load imbalance
   LJ_LAUNCHED(ctx);
   return LJ_OK;
 }

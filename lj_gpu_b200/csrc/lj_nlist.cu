@@ -1165,10 +1165,7 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
     ctx->tl_qz = ctx->tl_qs + 2 * (size_t)(pn + 2);
     ctx->tl_pn_cap = pn;
   }
-  static const int rows_env = [] {
-    const char* e = getenv("LJ_TILE_ROWS");
-    return e ? atoi(e) : 0;
-  }();
+  const int rows_env = lj_diag_int("LJ_TILE_ROWS");
   const int target_rows = rows_env > 0 ? rows_env : (a->flags & LJ_LIST_TILES_WIDE) ? 56 : 40;
   k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
   LJ_LAUNCHED(ctx);
@@ -1224,7 +1221,7 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
   k_tile_fill<PUB, P64><<<fblocks, 256, 0, st>>>(                                                     \
       pn, ge, ctx->tl_geom, ctx->cell_of, ctx->tl_cell_start, ctx->sorted_pos, sorted_pos32,          \
       a->search_len * a->search_len, ctx->tl_cnt, ctx->tl_off, ctx->tl_tab, ctx->tl_list, ctx->totals, \
-      a->pointer, a->sorted_list, a->capacity, getenv("LJ_TILE_FAKE") ? 1 : 0)
+      a->pointer, a->sorted_list, a->capacity, lj_diag_set("LJ_TILE_FAKE") ? 1 : 0)
   if (!fill_public) LJ_TILE_FILL(false, false);
   else if (a->pointer64) LJ_TILE_FILL(true, true);
   else LJ_TILE_FILL(true, false);
@@ -1238,7 +1235,7 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
     return lj_set_error(ctx, LJ_ERR_INVALID_LIST, "lj_build_list", "cell-tile mirror disagrees with the CSR list");
   if (ctx->totals_host->overflow) return LJ_OK;  // capacity problems are reported by lj_list_result
   g = *ctx->tl_geom_host;
-  if (getenv("LJ_TILE_DEBUG"))
+  if (lj_diag_set("LJ_TILE_DEBUG"))
     fprintf(stderr, "[lj] cell-tile mirror: grid %dx%dx%d, %d cells per tile, %d tiles, max rows %d, y-row %d, "
             "list units %d, y slot %zu B, list slot %zu B, %llu units total\n", g.nx, g.ny, g.nz, g.tc,
             g.ntiles, g.max_rows, g.max_yrow, g.max_units, lj_celltile_yslot_bytes(g),

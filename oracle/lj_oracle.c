@@ -173,6 +173,47 @@ int64_t ljo_makepair_brute(const double *q_xyz, int64_t pn, double sl2, int full
 }
 
 /* ------------------------------------------------------------------------------------
+ * Brute-force rows for a SAMPLE of particles (systems too large for the O(N^2) build):
+ * row k = every j != rows[k] with r2 < sl2 (full) or additionally j > rows[k] (half), ascending
+ * in j -- the reference's membership test and row order (cuda/force_cuda.cu:122-145) applied
+ * to the sampled i only, each against ALL pn particles.  out_ptr[k] is the offset of row k in
+ * out_list (exclusive scan, nrows + 1 entries).  Returns the total, or -(needed) when cap is
+ * too small.  Rows are independent: threaded.
+ * ---------------------------------------------------------------------------------- */
+int64_t ljo_rows_brute(const double *q_xyz, int64_t pn, double sl2, int full, const int64_t *rows,
+                       int64_t nrows, int32_t *out_nop, int64_t *out_ptr, int32_t *out_list,
+                       int64_t cap) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t k = 0; k < nrows; k++) {
+    const int64_t i = rows[k];
+    const double xi = q_xyz[3 * i], yi = q_xyz[3 * i + 1], zi = q_xyz[3 * i + 2];
+    int32_t cnt = 0;
+    for (int64_t j = full ? 0 : i + 1; j < pn; j++) {
+      if (j == i) continue;
+      const double dx = xi - q_xyz[3 * j], dy = yi - q_xyz[3 * j + 1], dz = zi - q_xyz[3 * j + 2];
+      if (r2_search(dx, dy, dz) < sl2) cnt++;
+    }
+    out_nop[k] = cnt;
+  }
+  int64_t total = 0;
+  for (int64_t k = 0; k < nrows; k++) { out_ptr[k] = total; total += out_nop[k]; }
+  out_ptr[nrows] = total;
+  if (total > cap) return -total;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t k = 0; k < nrows; k++) {
+    const int64_t i = rows[k];
+    const double xi = q_xyz[3 * i], yi = q_xyz[3 * i + 1], zi = q_xyz[3 * i + 2];
+    int64_t w = out_ptr[k];
+    for (int64_t j = full ? 0 : i + 1; j < pn; j++) {
+      if (j == i) continue;
+      const double dx = xi - q_xyz[3 * j], dy = yi - q_xyz[3 * j + 1], dz = zi - q_xyz[3 * j + 2];
+      if (r2_search(dx, dy, dz) < sl2) out_list[w++] = (int32_t)j;
+    }
+  }
+  return total;
+}
+
+/* ------------------------------------------------------------------------------------
  * Same contract, O(N): bin atoms into cubic cells of edge >= search length, scan the
  * 27-cell stencil, collect, sort each row ascending in j.
  * ---------------------------------------------------------------------------------- */
@@ -348,6 +389,71 @@ void ljo_force_gather(const double *q, int64_t q_comp, int64_t q_elem, double *p
       PX(i) += fx;
       PY(i) += fy;
       PZ(i) += fz;
+    }
+  }
+}
+
+/* The same `steps` applications for callers that KNOW q does not change between them (the
+ * reference's benchmark: "static positions", cuda/force_cuda.cu:333-335 launches the kernel LOOP
+ * times on the same q).  The per-step increment of row i is then the same double every step, so it
+ * is evaluated once and accumulated `steps` times: bit-identical to ljo_force_gather (checked in
+ * tests/test_oracle_cpu.py), at 1/steps of the cost -- this is what makes the full 100-step
+ * comparison affordable at N = 1M on a small host. */
+void ljo_force_gather_static(const double *q, int64_t q_comp, int64_t q_elem, double *p,
+                             int64_t p_comp, int64_t p_elem, int64_t pn, double dt, double cl2,
+                             const int32_t *sorted_list, const int32_t *number_of_partners,
+                             const int64_t *pointer, int steps) {
+  const ljo_stride qs = {q_comp, q_elem}, ps = {p_comp, p_elem};
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < pn; i++) {
+    const double xi = QX(i), yi = QY(i), zi = QZ(i);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    const int64_t kp = pointer[i];
+    const int32_t np = number_of_partners[i];
+    for (int32_t k = 0; k < np; k++) {
+      const int64_t j = sorted_list[kp + k];
+      const double dx = QX(j) - xi, dy = QY(j) - yi, dz = QZ(j) - zi;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const double r6 = r2 * r2 * r2;
+      double df = ((24.0 * r6 - 48.0) / (r6 * r6 * r2)) * dt;
+      if (r2 > cl2) df = 0.0;
+      fx += df * dx;
+      fy += df * dy;
+      fz += df * dz;
+    }
+    for (int s = 0; s < steps; s++) {
+      PX(i) += fx;
+      PY(i) += fy;
+      PZ(i) += fz;
+    }
+  }
+}
+
+/* Gather for a SAMPLE of rows (see ljo_rows_brute): row k of the sample belongs to particle
+ * rows[k], its entries are list[ptr[k] .. ptr[k] + nop[k]).  out_p[3k..3k+2] += the momentum of
+ * that particle after `steps` applications (same arithmetic and order as ljo_force_gather). */
+void ljo_force_rows(const double *q_xyz, const int64_t *rows, int64_t nrows, const int32_t *nop,
+                    const int64_t *ptr, const int32_t *list, double dt, double cl2, int steps,
+                    double *out_p) {
+  for (int64_t k = 0; k < nrows; k++) {
+    const int64_t i = rows[k];
+    const double xi = q_xyz[3 * i], yi = q_xyz[3 * i + 1], zi = q_xyz[3 * i + 2];
+    for (int s = 0; s < steps; s++) {
+      double fx = 0.0, fy = 0.0, fz = 0.0;
+      for (int32_t e = 0; e < nop[k]; e++) {
+        const int64_t j = list[ptr[k] + e];
+        const double dx = q_xyz[3 * j] - xi, dy = q_xyz[3 * j + 1] - yi, dz = q_xyz[3 * j + 2] - zi;
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        const double r6 = r2 * r2 * r2;
+        double df = ((24.0 * r6 - 48.0) / (r6 * r6 * r2)) * dt;
+        if (r2 > cl2) df = 0.0;
+        fx += df * dx;
+        fy += df * dy;
+        fz += df * dz;
+      }
+      out_p[3 * k] += fx;
+      out_p[3 * k + 1] += fy;
+      out_p[3 * k + 2] += fz;
     }
   }
 }

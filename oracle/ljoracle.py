@@ -61,7 +61,10 @@ class Oracle:
             f = getattr(L, name)
             f.restype = C.c_int64
             f.argtypes = [_f64p, C.c_int64, C.c_double, C.c_int, _i32p, _i64p, _i32p, C.c_int64]
-        for name in ("ljo_force_sorted", "ljo_force_gather"):
+        L.ljo_force_rows.restype = None
+        L.ljo_force_rows.argtypes = [_f64p, _i64p, C.c_int64, _i32p, _i64p, _i32p, C.c_double, C.c_double,
+                                     C.c_int, _f64p]
+        for name in ("ljo_force_sorted", "ljo_force_gather", "ljo_force_gather_static"):
             f = getattr(L, name)
             f.restype = None
             f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
@@ -70,6 +73,9 @@ class Oracle:
         L.ljo_force_gather_ell.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                            C.c_int64, C.c_int64, C.c_double, C.c_double, _i32p,
                                            _i32p, C.c_int]
+        L.ljo_rows_brute.restype = C.c_int64
+        L.ljo_rows_brute.argtypes = [_f64p, C.c_int64, C.c_double, C.c_int, _i64p, C.c_int64, _i32p, _i64p,
+                                     _i32p, C.c_int64]
         L.ljo_shuffle_rows.restype = None
         L.ljo_shuffle_rows.argtypes = [_i32p, _i32p, _i64p, C.c_int64, C.c_uint32]
         L.ljo_transpose_list.restype = C.c_int32
@@ -109,6 +115,23 @@ class Oracle:
             return self.makepair(q, search_len, full, brute, cap=-total)
         return nop, ptr, lst[:total].copy()
 
+    def rows_brute(self, q: np.ndarray, rows, search_len: float = SEARCH_LENGTH, full: bool = True):
+        """Brute-force rows of the SAMPLED particles `rows`, each against all of q (ascending j)
+        -> (number_of_partners int32[n], pointer int64[n+1], list int32[total])."""
+        q = np.ascontiguousarray(q, np.float64)
+        rows = np.ascontiguousarray(rows, np.int64)
+        n = len(rows)
+        nop = np.zeros(n, np.int32)
+        ptr = np.zeros(n + 1, np.int64)
+        cap = max(1024, 200 * n)
+        while True:
+            lst = np.zeros(cap, np.int32)
+            total = self.lib.ljo_rows_brute(q.reshape(-1), q.shape[0], search_len * search_len, int(full),
+                                            rows, n, nop, ptr, lst, cap)
+            if total >= 0:
+                return nop, ptr, lst[:total].copy()
+            cap = -total
+
     # ---- force ----
     @staticmethod
     def _strides(a: np.ndarray):
@@ -130,10 +153,23 @@ class Oracle:
         self._force(self.lib.ljo_force_sorted, q, p, len(nop) if pn is None else pn, nop, ptr, lst,
                     steps, dt, cl2)
 
-    def force_gather(self, q, p, nop, ptr, lst, steps=1, dt=DT, cl2=CL2, pn=None):
-        """full list gather, in place on p (cuda/kernel.cuh:36-65)."""
-        self._force(self.lib.ljo_force_gather, q, p, len(nop) if pn is None else pn, nop, ptr, lst,
-                    steps, dt, cl2)
+    def force_gather(self, q, p, nop, ptr, lst, steps=1, dt=DT, cl2=CL2, pn=None, static_q=False):
+        """full list gather, in place on p (cuda/kernel.cuh:36-65).  static_q=True: the caller
+        states that q is the same for all `steps` (the reference benchmark); the per-step increment
+        is evaluated once and accumulated `steps` times -- the same bits at 1/steps of the cost."""
+        fn = self.lib.ljo_force_gather_static if static_q else self.lib.ljo_force_gather
+        self._force(fn, q, p, len(nop) if pn is None else pn, nop, ptr, lst, steps, dt, cl2)
+
+    def force_rows(self, q, rows, nop, ptr, lst, steps=1, dt=DT, cl2=CL2):
+        """momenta [n,3] of the sampled particles `rows` after `steps` gather applications on
+        their rows (nop, ptr, lst) as rows_brute() returns them."""
+        q = np.ascontiguousarray(q, np.float64)
+        rows = np.ascontiguousarray(rows, np.int64)
+        out = np.zeros((len(rows), 3), np.float64)
+        self.lib.ljo_force_rows(q.reshape(-1), rows, len(rows), np.ascontiguousarray(nop, np.int32),
+                                np.ascontiguousarray(ptr, np.int64), np.ascontiguousarray(lst, np.int32),
+                                dt, cl2, steps, out.reshape(-1))
+        return out
 
     def force_gather_ell(self, q, p, nop, tlist, steps=1, dt=DT, cl2=CL2):
         qc, qe = self._strides(q)

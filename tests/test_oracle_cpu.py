@@ -146,3 +146,26 @@ def test_edge_cases(oracle):
     r2 = 9.0; r6 = r2 ** 3
     df = ((24.0 * r6 - 48.0) / (r6 * r6 * r2)) * lo.DT
     assert p[0, 0] == df * 3.0 and p[1, 0] == -df * 3.0
+
+
+def test_sampled_rows_and_static_gather_are_the_same_oracle(oracle):
+    """The large-system checkers (config C for 100 steps, config D on sampled rows) must be the SAME
+    oracle as the pinned one: rows_brute() == rows of the brute-force list, force_rows() and
+    force_gather(static_q=True) == force_gather(), bit for bit."""
+    q = oracle.init_fcc(1.0, 9.6)
+    pn = len(q)
+    for full in (True, False):
+        nop, ptr, lst = oracle.makepair(q, full=full, brute=True)
+        rows = np.array([0, 1, pn // 3, pn // 2, pn - 2, pn - 1])
+        n2, p2, l2 = oracle.rows_brute(q, rows, full=full)
+        for k, i in enumerate(rows):
+            assert n2[k] == nop[i]
+            assert np.array_equal(l2[p2[k]:p2[k + 1]], lst[ptr[i]:ptr[i] + nop[i]])
+    nop, ptr, lst = oracle.makepair(q, full=True)
+    p_loop = np.zeros_like(q)
+    oracle.force_gather(q, p_loop, nop, ptr, lst, steps=17)
+    p_static = np.zeros_like(q)
+    oracle.force_gather(q, p_static, nop, ptr, lst, steps=17, static_q=True)
+    assert np.array_equal(p_loop, p_static)
+    n2, p2, l2 = oracle.rows_brute(q, rows)
+    assert np.array_equal(oracle.force_rows(q, rows, n2, p2, l2, steps=17), p_loop[rows])
