@@ -48,14 +48,20 @@ typedef enum lj_layout {
   LJ_AOS_D4 = 1, /* {x,y,z,w} doubles, 32 B stride, 32 B aligned; .w ignored on read and
                     preserved on the write of p                                          */
   LJ_SOA_D = 2,  /* planes x[], y[], z[] of doubles: base + c*plane_stride + i            */
-  LJ_AOS_F4 = 3  /* {x,y,z,w} floats, 16 B stride: list build, and force with LJ_PREC_MIXED
+  LJ_AOS_F4 = 3, /* {x,y,z,w} floats, 16 B stride: list build, and force with LJ_PREC_MIXED
                     (FP32 pair math, p accumulated in float, one rounding per step)      */
+  LJ_AOS_F3 = 4  /* packed {x,y,z} floats, 12 B stride (q_f3 / p_f3, cuda/force_cuda.cu:24):
+                    list build, and force with LJ_PREC_MIXED, like LJ_AOS_F4             */
 } lj_layout;
 
 /* Neighbour-list storage.  CSR = sorted_list + number_of_partners + pointer (no sentinel,
  * cuda/force_cuda.cu:146-162); ELL = column-major transposed_list[i + k*pn], zero padded
  * (cuda/force_cuda.cu:229-240), pointer unused (the reference passes nullptr, :430-436). */
-typedef enum lj_list_layout { LJ_LIST_CSR = 0, LJ_LIST_ELL = 1 } lj_list_layout;
+/* ELL_ROWS = row-major padded table list[i*ell_width + k], zero padded, the layout
+ * make_sorted_list2d() aims at (cuda/force_cuda.cu:242-253) -- there with a fixed width of 60 that
+ * is smaller than the longest row (rows overlap; no reference kernel reads it).  Here the width
+ * is checked against max_partners by lj_build_ell_rows(). */
+typedef enum lj_list_layout { LJ_LIST_CSR = 0, LJ_LIST_ELL = 1, LJ_LIST_ELL_ROWS = 2 } lj_list_layout;
 
 /* Thread mapping.  Replaces the choice among the 20 kernels of cuda/kernel.cuh. */
 typedef enum lj_variant {
@@ -65,7 +71,9 @@ typedef enum lj_variant {
   LJ_VARIANT_TILE_TMA = 2,  /* CTA tile of rows, j-indices staged in shared memory by a TMA
                                bulk copy, `group` lanes per i (CSR only)                     */
   LJ_VARIANT_NEWTON3 = 3,   /* half list, reaction scattered with FP64 atomics
-                               (the *_with_aar kernels, kernel.cuh:238-469)                  */
+                               (the *_with_aar kernels, kernel.cuh:238-469): CSR with `group`
+                               lanes per i, or the half ELL table with one thread per i
+                               (memopt2/memopt3_with_aar, kernel.cuh:344-423)                */
   LJ_VARIANT_CLUSTER = 4,   /* cluster pair list built by lj_build_list(LJ_LIST_CLUSTERS) for
                                exactly these list arrays; error if there is none             */
   LJ_VARIANT_CELLTILE = 5   /* cell-tile mirror built by lj_build_list(LJ_LIST_TILES) for exactly
@@ -138,7 +146,7 @@ typedef struct lj_force_args {
   double cl2;                        /* CL2 = cutoff^2                                     */
   const int32_t* list;               /* sorted_list (CSR) or transposed_list (ELL)         */
   const int32_t* number_of_partners;
-  const void* pointer;               /* int32[pn] or int64[pn] (pointer64); NULL for ELL   */
+  const void* pointer;               /* int32[pn] or int64[pn] (pointer64); NULL for ELL / ELL_ROWS */
   int32_t layout;                    /* lj_layout of q and p                               */
   int32_t list_layout;               /* lj_list_layout                                     */
   int32_t variant;                   /* lj_variant                                         */
@@ -153,6 +161,7 @@ typedef struct lj_force_args {
   int64_t list_entries;              /* optional: entries allocated in `list` (number_of_pairs);
                                         0 = unknown.  Lets LJ_VARIANT_TILE_TMA round its bulk
                                         copies up to 16 bytes without reading past the array */
+  int64_t ell_width;                 /* LJ_LIST_ELL_ROWS: entries per row of the padded table   */
 } lj_force_args;
 
 LJ_API int lj_force_step(lj_ctx* ctx, const lj_force_args* args, void* stream);
@@ -243,6 +252,16 @@ LJ_API int lj_build_list_soa6(lj_ctx* ctx, const double* qx, const double* qy, c
 LJ_API int lj_build_ell(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* number_of_partners,
                  const void* pointer, int32_t pointer64, int64_t pn, int32_t* transposed_list,
                  int64_t capacity_entries, int32_t* max_partners_out, void* stream);
+
+/* Replaces make_sorted_list2d() (cuda/force_cuda.cu:242-253) with a CORRECT padded table: CSR ->
+ * row-major sorted_list2d[i*width + k], zero padded.  width must be >= the longest row
+ * (LJ_ERR_CAPACITY otherwise -- the reference's NUM_NEIGH = 60 is smaller than its own max_partners
+ * of 78 and its rows overlap silently; max_partners_out tells the width that is needed) and
+ * capacity_entries >= width*pn.  Consumed by lj_force_step with LJ_LIST_ELL_ROWS + ell_width. */
+LJ_API int lj_build_ell_rows(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* number_of_partners,
+                      const void* pointer, int32_t pointer64, int64_t pn, int32_t width,
+                      int32_t* sorted_list2d, int64_t capacity_entries, int32_t* max_partners_out,
+                      void* stream);
 
 /* Replaces random_shfl() (cuda/force_cuda.cu:255-263) in spirit: a deterministic per-row
  * permutation on the device (NOT the same permutation as std::shuffle), to prove kernels do

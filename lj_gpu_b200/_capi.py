@@ -16,8 +16,8 @@ LIB_PATH = os.environ.get("LJ_B200_LIB", os.path.join(HERE, "liblj_b200.so"))  #
 # enums of include/lj_b200.h
 LJ_OK, LJ_ERR_CUDA, LJ_ERR_BAD_ARG, LJ_ERR_CAPACITY, LJ_ERR_OVERFLOW32, LJ_ERR_NO_DEVICE, \
     LJ_ERR_INVALID_LIST = range(7)
-LJ_AOS_D3, LJ_AOS_D4, LJ_SOA_D, LJ_AOS_F4 = range(4)
-LJ_LIST_CSR, LJ_LIST_ELL = 0, 1
+LJ_AOS_D3, LJ_AOS_D4, LJ_SOA_D, LJ_AOS_F4, LJ_AOS_F3 = range(5)
+LJ_LIST_CSR, LJ_LIST_ELL, LJ_LIST_ELL_ROWS = 0, 1, 2
 LJ_VARIANT_AUTO, LJ_VARIANT_SUBWARP, LJ_VARIANT_TILE_TMA, LJ_VARIANT_NEWTON3, LJ_VARIANT_CLUSTER, \
     LJ_VARIANT_CELLTILE = range(6)
 LJ_PREC_FP64, LJ_PREC_MIXED = 0, 1
@@ -40,7 +40,7 @@ class LjForceArgs(C.Structure):
         ("variant", C.c_int32), ("group", C.c_int32), ("precision", C.c_int32),
         ("pointer64", C.c_int32), ("threads_per_block", C.c_int32), ("list_scalar", C.c_int32),
         ("plane_stride", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
-        ("list_entries", C.c_int64),
+        ("list_entries", C.c_int64), ("ell_width", C.c_int64),
     ]
 
 
@@ -97,6 +97,7 @@ PROTOTYPES = {
     "lj_list_invalidate": (C.c_int, [_vp]),
     "lj_list_result": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i32), _vp]),
     "lj_build_ell": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, C.POINTER(_i32), _vp]),
+    "lj_build_ell_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i64, C.POINTER(_i32), _vp]),
     "lj_shuffle_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_uint32, _vp]),
     "lj_validate_list": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp]),
     "lj_init_fcc": (_i64, [_dbl, _dbl, _vp, _i64, C.POINTER(_i32)]),

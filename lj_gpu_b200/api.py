@@ -26,7 +26,7 @@ SEARCH_LENGTH = 3.3
 CL2 = CUTOFF_LENGTH * CUTOFF_LENGTH
 LOOP = 100
 
-LAYOUTS = {"aos3": LJ_AOS_D3, "aos4": LJ_AOS_D4, "soa": LJ_SOA_D, "f4": capi.LJ_AOS_F4}
+LAYOUTS = {"aos3": LJ_AOS_D3, "aos4": LJ_AOS_D4, "soa": LJ_SOA_D, "f4": capi.LJ_AOS_F4, "f3": capi.LJ_AOS_F3}
 VARIANTS = {"auto": LJ_VARIANT_AUTO, "subwarp": LJ_VARIANT_SUBWARP, "warp": LJ_VARIANT_SUBWARP,
             "thread": LJ_VARIANT_SUBWARP, "tile": LJ_VARIANT_TILE_TMA, "n3": LJ_VARIANT_NEWTON3,
             "cluster": capi.LJ_VARIANT_CLUSTER, "celltile": capi.LJ_VARIANT_CELLTILE}
@@ -125,6 +125,9 @@ class PairList:
     max_partners: int
     half: bool = False
     transposed_list: "torch.Tensor | None" = None
+    sorted_list2d: "torch.Tensor | None" = None   # row-major padded table [pn, ell_width]
+    ell_width: int = 0
+    build_flags: dict | None = None      # tiles / clusters / sort_rows / per_particle of the build: rebuild() reuses them
 
     @property
     def pointer64(self) -> bool:
@@ -183,7 +186,8 @@ class LJContext:
         if layout is not None:
             return LAYOUTS[layout] if isinstance(layout, str) else layout
         if q.dim() == 2 and q.shape[1] == 3:
-            return LJ_AOS_D3
+            import torch
+            return capi.LJ_AOS_F3 if q.dtype == torch.float32 else LJ_AOS_D3
         if q.dim() == 2 and q.shape[1] == 4:
             import torch
             return capi.LJ_AOS_F4 if q.dtype == torch.float32 else LJ_AOS_D4
@@ -239,12 +243,24 @@ class LJContext:
             break
         mx = C.c_int32(0)
         self._check(self.lib.lj_list_result(self.h, C.byref(total), C.byref(mx), st))
-        return PairList(nop, ptr, lst, int(total.value), int(mx.value), half)
+        return PairList(nop, ptr, lst, int(total.value), int(mx.value), half, None, None, 0,
+                        dict(tiles=tiles, clusters=clusters, sort_rows=sort_rows, per_particle=per_particle,
+                             rows=rows))
 
     def rebuild(self, q, pl: PairList, search_len: float = SEARCH_LENGTH, layout=None,
-                sort_rows: bool = False, rows=None, pn=None, clusters: bool = False,
-                per_particle: bool = False, tiles: bool = False, stream=None):
-        """Asynchronous rebuild into existing arrays (no host sync, no reallocation)."""
+                sort_rows=None, rows=None, pn=None, clusters=None,
+                per_particle=None, tiles=None, stream=None):
+        """Asynchronous rebuild into existing arrays (no host sync, no reallocation).  Flags left at
+        None are the ones the list was built with (a mirror built by makepair(tiles=True) is rebuilt
+        with the list instead of being silently dropped)."""
+        bf = pl.build_flags or {}
+        sort_rows = bf.get("sort_rows", False) if sort_rows is None else sort_rows
+        clusters = bf.get("clusters", False) if clusters is None else clusters
+        per_particle = bf.get("per_particle", False) if per_particle is None else per_particle
+        tiles = bf.get("tiles", False) if tiles is None else tiles
+        rows = bf.get("rows") if rows is None else rows
+        pl.build_flags = dict(tiles=tiles, clusters=clusters, sort_rows=sort_rows, per_particle=per_particle,
+                              rows=rows)
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
         if pn is not None:
@@ -283,6 +299,22 @@ class LJContext:
         pl.transposed_list = tl
         return tl
 
+    def make_sorted_list2d(self, pl: PairList, width: int | None = None, stream=None):
+        """make_sorted_list2d() (cuda/force_cuda.cu:242-253) done right: row-major padded table
+        [pn, width], zero padded; width defaults to max_partners, a narrower one raises LJError
+        (the reference's fixed NUM_NEIGH = 60 lets rows overlap)."""
+        import torch
+        pn = pl.number_of_partners.numel()
+        width = pl.max_partners if width is None else width
+        t2 = torch.empty(max(1, width * pn), dtype=torch.int32, device=pl.sorted_list.device)
+        mx = C.c_int32(0)
+        self._check(self.lib.lj_build_ell_rows(self.h, pl.sorted_list.data_ptr(),
+                                               pl.number_of_partners.data_ptr(), pl.pointer.data_ptr(),
+                                               int(pl.pointer64), pn, width, t2.data_ptr(), t2.numel(),
+                                               C.byref(mx), self._stream(stream)))
+        pl.sorted_list2d, pl.ell_width = t2, width
+        return t2
+
     def random_shfl(self, pl: PairList, seed: int = 10, stream=None):
         """random_shfl() in spirit (cuda/force_cuda.cu:255-263): per-row device permutation."""
         self._check(self.lib.lj_shuffle_rows(self.h, pl.sorted_list.data_ptr(),
@@ -300,14 +332,20 @@ class LJContext:
     # ------------------------------------------------------------------ force
     def force_args(self, q, p, pl: PairList, dt: float = DT, cl2: float = CL2, layout=None,
                    ell: bool = False, variant="auto", group: int = 0, precision: str = "fp64",
-                   threads_per_block: int = 0, rows=None, pn=None, list_scalar: int = 0) -> capi.LjForceArgs:
+                   threads_per_block: int = 0, rows=None, pn=None, list_scalar: int = 0,
+                   ell_rows: bool = False) -> capi.LjForceArgs:
         lay = self._layout_of(q, layout)
         n, stride = self._pn_stride(q, lay)
         if pn is not None:
             n = pn
         a = capi.LjForceArgs()
         a.q, a.p, a.pn, a.dt, a.cl2 = q.data_ptr(), p.data_ptr(), n, dt, cl2
-        if ell:
+        if ell_rows:
+            if pl.sorted_list2d is None:
+                raise ValueError("call make_sorted_list2d first")
+            a.list, a.pointer, a.list_layout = pl.sorted_list2d.data_ptr(), None, capi.LJ_LIST_ELL_ROWS
+            a.ell_width = pl.ell_width
+        elif ell:
             if pl.transposed_list is None:
                 raise ValueError("call make_transposed_pairlist first")
             a.list, a.pointer, a.list_layout = pl.transposed_list.data_ptr(), None, LJ_LIST_ELL
@@ -317,8 +355,8 @@ class LJContext:
         a.number_of_partners = pl.number_of_partners.data_ptr()
         a.layout = lay
         v = VARIANTS[variant] if isinstance(variant, str) else variant
-        if pl.half and not ell:
-            v = LJ_VARIANT_NEWTON3
+        if pl.half:
+            v = LJ_VARIANT_NEWTON3   # CSR: group lanes per i; half ELL table: thread per i (memopt2/3_with_aar)
         if variant == "warp" and group == 0:
             group = 32
         if variant == "thread" and group == 0:

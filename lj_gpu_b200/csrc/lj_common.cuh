@@ -191,6 +191,16 @@ static inline bool lj_diag_set(const char* name) {
     }                                                                                               \
   } while (0)
 
+// Top of every public entry point: a context belongs to ONE device; make it current for the calling
+// host thread (a caller driving several GPUs from one thread switches contexts, not devices).
+#define LJ_ENTER(ctx)                                                          \
+  do {                                                                         \
+    if (!(ctx)) return LJ_ERR_BAD_ARG;                                         \
+    int cur__ = -1;                                                            \
+    if (cudaGetDevice(&cur__) != cudaSuccess || cur__ != (ctx)->device)        \
+      LJ_CUDA((ctx), cudaSetDevice((ctx)->device));                            \
+  } while (0)
+
 // NULL is the CUDA legacy default stream, exactly as for a kernel launch: the reference runs
 // everything there (cuda/force_cuda.cu:334) and torch hands out 0 for its default stream.
 static inline cudaStream_t lj_stream(lj_ctx* ctx, void* s) { (void)ctx; return (cudaStream_t)s; }
@@ -299,6 +309,9 @@ __device__ __forceinline__ void load_pos(const void* __restrict__ q, int64_t i, 
   } else if (LAYOUT == LJ_AOS_F4) {  // float4 positions (cuda/force_cuda.cu:25): widened exactly
     const float4 v = __ldg(reinterpret_cast<const float4*>(q) + i);
     x = (double)v.x; y = (double)v.y; z = (double)v.z;
+  } else if (LAYOUT == LJ_AOS_F3) {  // float3 positions (cuda/force_cuda.cu:24): widened exactly
+    const float* b = reinterpret_cast<const float*>(q) + 3 * i;
+    x = (double)__ldg(b); y = (double)__ldg(b + 1); z = (double)__ldg(b + 2);
   } else {
     const double* b = reinterpret_cast<const double*>(q) + i;
     x = __ldg(b); y = __ldg(b + plane); z = __ldg(b + 2 * plane);
@@ -323,6 +336,9 @@ __device__ __forceinline__ void add_mom(void* __restrict__ p, int64_t i, int64_t
     float4 v = *b;
     v.x = (float)((double)v.x + fx); v.y = (float)((double)v.y + fy); v.z = (float)((double)v.z + fz);
     *b = v;
+  } else if (LAYOUT == LJ_AOS_F3) {  // float3 momenta: one rounding per step
+    float* b = reinterpret_cast<float*>(p) + 3 * i;
+    b[0] = (float)((double)b[0] + fx); b[1] = (float)((double)b[1] + fy); b[2] = (float)((double)b[2] + fz);
   } else {
     double* b = reinterpret_cast<double*>(p) + i;
     b[0] += fx; b[plane] += fy; b[2 * plane] += fz;

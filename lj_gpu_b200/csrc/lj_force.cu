@@ -298,9 +298,85 @@ lj_newton3_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_beg
   if (lg == 0) red_mom<LAYOUT>(p, i, plane, fx, fy, fz);
 }
 
+// --------------------------------------------------------------------------------------
+// Newton-3 on the HALF column-major ELL table, one thread per i (memopt2/memopt3_with_aar,
+// cuda/kernel.cuh:344-423): coalesced list reads, i side in registers, j side by RED.
+// --------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(1024)
+lj_newton3_ell(const void* __restrict__ q, void* __restrict__ p, int64_t pn, int64_t row_begin,
+               int64_t row_end, int64_t plane, double c24, double c48, long long cl2_bits,
+               const int32_t* __restrict__ tlist, const int32_t* __restrict__ nop) {
+  const int64_t i = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= row_end) return;
+  double xi, yi, zi;
+  load_pos<LAYOUT>(q, i, plane, xi, yi, zi);
+  const int np = __ldg(nop + i);
+  const int32_t* __restrict__ col = tlist + i;
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  for (int k = 0; k < np; k++) {
+    const int j = __ldg(col + (int64_t)k * pn);
+    double xj, yj, zj;
+    load_pos<LAYOUT>(q, j, plane, xj, yj, zj);
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    lj_pair(xj - xi, yj - yi, zj - zi, c24, c48, cl2_bits, gx, gy, gz);
+    if (gx != 0.0 || gy != 0.0 || gz != 0.0) {
+      fx += gx; fy += gy; fz += gz;
+      red_mom<LAYOUT>(p, j, plane, -gx, -gy, -gz);
+    }
+  }
+  // p[i] also receives reactions from other rows concurrently -> atomic here too
+  red_mom<LAYOUT>(p, i, plane, fx, fy, fz);
+}
+
+// --------------------------------------------------------------------------------------
+// Gather on the row-major padded table list[i*width + k] (LJ_LIST_ELL_ROWS, the corrected
+// sorted_list2d of cuda/force_cuda.cu:242-253), G lanes per row: a row is one contiguous run, so
+// the G lanes read consecutive words like on the CSR list, without pointer[].
+// --------------------------------------------------------------------------------------
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(1024)
+lj_gather_ellrows(const void* __restrict__ q, void* __restrict__ p, int64_t row_begin, int64_t row_end,
+                  int64_t plane, double c24, double c48, long long cl2_bits,
+                  const int32_t* __restrict__ list, const int32_t* __restrict__ nop, int64_t width) {
+  const int rows_per_block = blockDim.x / G;
+  const int64_t i = row_begin + (int64_t)blockIdx.x * rows_per_block + threadIdx.x / G;
+  const int lg = threadIdx.x % G;
+  if (i >= row_end) return;  // whole groups leave together (G divides 32)
+  double xi, yi, zi;
+  load_pos<LAYOUT>(q, i, plane, xi, yi, zi);
+  const int np = __ldg(nop + i);
+  const int32_t* __restrict__ row = list + i * width;
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  int k = lg;
+  for (; k + (kUnroll - 1) * G < np; k += kUnroll * G) {
+    int j[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) j[u] = __ldg(row + k + u * G);
+    double xj[kUnroll], yj[kUnroll], zj[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) load_pos<LAYOUT>(q, j[u], plane, xj[u], yj[u], zj[u]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++)
+      lj_pair(xj[u] - xi, yj[u] - yi, zj[u] - zi, c24, c48, cl2_bits, fx, fy, fz);
+  }
+  for (; k < np; k += G) {
+    const int j = __ldg(row + k);
+    double xj, yj, zj;
+    load_pos<LAYOUT>(q, j, plane, xj, yj, zj);
+    lj_pair(xj - xi, yj - yi, zj - zi, c24, c48, cl2_bits, fx, fy, fz);
+  }
+  if (G > 1) {
+    fx = group_sum<G>(fx);
+    fy = group_sum<G>(fy);
+    fz = group_sum<G>(fz);
+  }
+  if (lg == 0) add_mom<LAYOUT>(p, i, plane, fx, fy, fz);
+}
+
 // -------------------------------------------------------------------------- dispatch ---
 template <int G, int LAYOUT, bool PTR64>
-void launch_csr(const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c24, double c48,
+void launch_csr(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c24, double c48,
                 long long cl2_bits, bool newton3, cudaStream_t st) {
   const int rows_per_block = tb / G;
   const int64_t rows = r1 - r0;
@@ -313,6 +389,7 @@ void launch_csr(const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c
     lj_gather_csr_v4<(G >= 4 ? G : 4), LAYOUT, PTR64><<<blocks, tb, 0, st>>>(
         a->q, a->p, r0, r1, a->plane_stride, c24, c48, cl2_bits, a->list, a->number_of_partners,
         a->pointer, a->list_entries);
+#if LJ_DIAG  // kernel-surgery variants 100..105 (tools/diag_force.py): diagnostic builds only
   else if (a->variant == 100 && G == 8 && LAYOUT == LJ_AOS_D4)
     lj_gather_csr<G, LAYOUT, PTR64, 1><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                                c48, cl2_bits, a->list,
@@ -367,13 +444,15 @@ void launch_csr(const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c
     lj_gather_csr<G, LAYOUT, PTR64, 4><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                                c48, cl2_bits, a->list,
                                                                a->number_of_partners, a->pointer);
+#endif
   else {
     // the gather kernels use no shared memory: give the whole 228 KB array to L1
-    static bool carved = false;
+    // (per context = per device: the attribute is a property of the function ON a device)
+    int& carved = ctx->func_occ[reinterpret_cast<const void*>(lj_gather_csr<G, LAYOUT, PTR64>)];
     if (!carved) {
       cudaFuncSetAttribute(lj_gather_csr<G, LAYOUT, PTR64>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxL1);
-      carved = true;
+      carved = 1;
     }
     lj_gather_csr<G, LAYOUT, PTR64><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                             c48, cl2_bits, a->list,
@@ -382,31 +461,51 @@ void launch_csr(const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c
 }
 
 template <int LAYOUT, bool PTR64>
-bool launch_csr_g(int g, const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c24,
+bool launch_csr_g(lj_ctx* ctx, int g, const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c24,
                   double c48, long long cl2_bits, bool n3, cudaStream_t st) {
   switch (g) {
-    case 1: launch_csr<1, LAYOUT, PTR64>(a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
-    case 2: launch_csr<2, LAYOUT, PTR64>(a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
-    case 4: launch_csr<4, LAYOUT, PTR64>(a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
-    case 8: launch_csr<8, LAYOUT, PTR64>(a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
-    case 16: launch_csr<16, LAYOUT, PTR64>(a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
-    case 32: launch_csr<32, LAYOUT, PTR64>(a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
+    case 1: launch_csr<1, LAYOUT, PTR64>(ctx, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
+    case 2: launch_csr<2, LAYOUT, PTR64>(ctx, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
+    case 4: launch_csr<4, LAYOUT, PTR64>(ctx, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
+    case 8: launch_csr<8, LAYOUT, PTR64>(ctx, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
+    case 16: launch_csr<16, LAYOUT, PTR64>(ctx, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
+    case 32: launch_csr<32, LAYOUT, PTR64>(ctx, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); return true;
   }
   return false;
 }
 
 template <int LAYOUT>
-bool launch_layout(int g, const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c24,
+bool launch_layout(lj_ctx* ctx, int g, const lj_force_args* a, int64_t r0, int64_t r1, int tb, double c24,
                    double c48, long long cl2_bits, bool n3, cudaStream_t st) {
   if (a->list_layout == LJ_LIST_ELL) {
     const int64_t rows = r1 - r0;
     const unsigned blocks = (unsigned)((rows + tb - 1) / tb);
-    lj_gather_ell<LAYOUT><<<blocks, tb, 0, st>>>(a->q, a->p, a->pn, r0, r1, a->plane_stride, c24, c48,
-                                                  cl2_bits, a->list, a->number_of_partners);
+    if (n3)
+      lj_newton3_ell<LAYOUT><<<blocks, tb, 0, st>>>(a->q, a->p, a->pn, r0, r1, a->plane_stride, c24, c48,
+                                                     cl2_bits, a->list, a->number_of_partners);
+    else
+      lj_gather_ell<LAYOUT><<<blocks, tb, 0, st>>>(a->q, a->p, a->pn, r0, r1, a->plane_stride, c24, c48,
+                                                    cl2_bits, a->list, a->number_of_partners);
     return true;
   }
-  return a->pointer64 ? launch_csr_g<LAYOUT, true>(g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st)
-                      : launch_csr_g<LAYOUT, false>(g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st);
+  if (a->list_layout == LJ_LIST_ELL_ROWS) {
+    const int64_t rows = r1 - r0;
+#define LJ_ELLROWS(GG)                                                                              \
+    lj_gather_ellrows<GG, LAYOUT><<<(unsigned)((rows + tb / GG - 1) / (tb / GG)), tb, 0, st>>>(     \
+        a->q, a->p, r0, r1, a->plane_stride, c24, c48, cl2_bits, a->list, a->number_of_partners, a->ell_width)
+    switch (g) {
+      case 1: LJ_ELLROWS(1); return true;
+      case 2: LJ_ELLROWS(2); return true;
+      case 4: LJ_ELLROWS(4); return true;
+      case 8: LJ_ELLROWS(8); return true;
+      case 16: LJ_ELLROWS(16); return true;
+      case 32: LJ_ELLROWS(32); return true;
+    }
+#undef LJ_ELLROWS
+    return false;
+  }
+  return a->pointer64 ? launch_csr_g<LAYOUT, true>(ctx, g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st)
+                      : launch_csr_g<LAYOUT, false>(ctx, g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st);
 }
 
 }  // namespace
@@ -424,13 +523,18 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
   LJ_REQUIRE(ctx, a->pn >= 0, "lj_force_step: negative particle_number");
   if (a->pn == 0) return LJ_OK;
   LJ_REQUIRE(ctx, a->q && a->p && a->list && a->number_of_partners, "lj_force_step: null array");
-  LJ_REQUIRE(ctx, a->list_layout == LJ_LIST_CSR || a->list_layout == LJ_LIST_ELL,
+  LJ_REQUIRE(ctx, a->list_layout == LJ_LIST_CSR || a->list_layout == LJ_LIST_ELL || a->list_layout == LJ_LIST_ELL_ROWS,
              "lj_force_step: unknown list layout");
-  LJ_REQUIRE(ctx, a->list_layout == LJ_LIST_ELL || a->pointer != nullptr,
+  LJ_REQUIRE(ctx, a->list_layout != LJ_LIST_CSR || a->pointer != nullptr,
              "lj_force_step: CSR list needs pointer[]");
+  LJ_REQUIRE(ctx, a->list_layout != LJ_LIST_ELL_ROWS || a->ell_width > 0,
+             "lj_force_step: LJ_LIST_ELL_ROWS needs ell_width");
   LJ_REQUIRE(ctx, a->layout == LJ_AOS_D3 || a->layout == LJ_AOS_D4 || a->layout == LJ_SOA_D ||
-                      (a->layout == LJ_AOS_F4 && a->precision == LJ_PREC_MIXED),
-             "lj_force_step: layout must be AOS_D3, AOS_D4, SOA_D, or AOS_F4 with LJ_PREC_MIXED");
+                      ((a->layout == LJ_AOS_F4 || a->layout == LJ_AOS_F3) && a->precision == LJ_PREC_MIXED),
+             "lj_force_step: layout must be AOS_D3, AOS_D4, SOA_D, or AOS_F4 / AOS_F3 with LJ_PREC_MIXED");
+  if (a->layout == LJ_AOS_F3)
+    LJ_REQUIRE(ctx, ((uintptr_t)a->q % 4 == 0) && ((uintptr_t)a->p % 4 == 0),
+               "lj_force_step: float3 arrays must be 4-byte aligned");
   if (a->layout == LJ_AOS_F4)
     LJ_REQUIRE(ctx, ((uintptr_t)a->q % 16 == 0) && ((uintptr_t)a->p % 16 == 0),
                "lj_force_step: float4 arrays must be 16-byte aligned");
@@ -452,7 +556,7 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
   int variant = a->variant;
   if (variant == LJ_VARIANT_AUTO || variant == LJ_VARIANT_CLUSTER || variant >= 100) variant = LJ_VARIANT_SUBWARP;
   const bool n3 = variant == LJ_VARIANT_NEWTON3;
-  LJ_REQUIRE(ctx, !(n3 && a->list_layout == LJ_LIST_ELL), "lj_force_step: Newton-3 needs a CSR list");
+  LJ_REQUIRE(ctx, !(n3 && a->list_layout == LJ_LIST_ELL_ROWS), "lj_force_step: Newton-3 needs a CSR or ELL list");
   int g = a->group;
   if (g == 0) g = (a->list_layout == LJ_LIST_ELL) ? 1 : 8;
   LJ_REQUIRE(ctx, g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32,
@@ -499,9 +603,9 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
 
   bool ok = false;
   switch (a->layout) {
-    case LJ_AOS_D3: ok = launch_layout<LJ_AOS_D3>(g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); break;
-    case LJ_AOS_D4: ok = launch_layout<LJ_AOS_D4>(g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); break;
-    case LJ_SOA_D: ok = launch_layout<LJ_SOA_D>(g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); break;
+    case LJ_AOS_D3: ok = launch_layout<LJ_AOS_D3>(ctx, g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); break;
+    case LJ_AOS_D4: ok = launch_layout<LJ_AOS_D4>(ctx, g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); break;
+    case LJ_SOA_D: ok = launch_layout<LJ_SOA_D>(ctx, g, a, r0, r1, tb, c24, c48, cl2_bits, n3, st); break;
   }
   LJ_REQUIRE(ctx, ok, "lj_force_step: no kernel for this configuration");
   LJ_LAUNCHED(ctx);

@@ -121,17 +121,13 @@ struct ct_params {
 // (measured: 0.14 ms per step with every copy and all pair work switched off), which is half of
 // what 16 consumer warps need to work a tile off -- any hiccup and they wait (22 % of their time).
 // Two CTAs of 8 consumer warps per SM are two independent pipelines at half the tile rate each.
-// WPG = consumer warps per GROUP.  The NCONS / WPG groups take the tiles of the CTA's stream in turn
-// (tile t belongs to group t % NG): a consumer warp visits 1 / NG of the tiles instead of every one
-// (the per-tile visit -- barrier wait, header, arrive -- was 10 % of the executed instructions and
-// 21 % of the stall samples with 16 warps on every tile), and NG tiles are worked on at once, so a
-// group that waits for its tile leaves the other groups' warps on every scheduler.  A group is four
-// consecutive warps = one warp per SM sub-partition.  WPG == NCONS is the single-group pipeline.
-template <int LAYOUT, bool MX, int NCONS, int NB, int WPG>
+// Every consumer warp waits on EVERY tile's full barrier, in order.  (Round 2 tried dealing the
+// tiles to groups of warps so that a warp visits only every second or fourth tile: 2 % faster and
+// WRONG -- a tile's older y-rows complete on the barriers of the preceding tiles, which a warp that
+// skips those tiles never waits for; results were off by 1e-6..1e-5 in one run out of a few.)
+template <int LAYOUT, bool MX, int NCONS, int NB>
 __global__ void __launch_bounds__((NCONS + 2) * 32, NB)
 lj_celltile_force(const ct_params P) {
-  static_assert(NCONS % WPG == 0, "whole groups");
-  constexpr int NG = NCONS / WPG;
   constexpr uint32_t RB = MX ? 16u : 24u;  // bytes per staged position record
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t tfull[kCtMaxL], tempty[kCtMaxL];
@@ -158,7 +154,7 @@ lj_celltile_force(const ct_params P) {
   if (threadIdx.x == 0) {
     kconst[0] = P.unit2; kconst[1] = P.c24u; kconst[2] = P.c48u; kconst[3] = P.lo_c; kconst[4] = P.cl2f;
     kconst[5] = __int_as_float(0x7fffffff);
-    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 2); mbar_init(&tempty[b], WPG); }
+    for (int b = 0; b < rl; b++) { mbar_init(&tfull[b], 2); mbar_init(&tempty[b], NCONS); }
     for (int b = 0; b < 2; b++) {
       mbar_init(&tabbar[0][b], 1); mbar_init(&tabbar[1][b], 1);
       mbar_init(&mfull[b], 1); mbar_init(&mempty[b], 1);
@@ -350,20 +346,14 @@ lj_celltile_force(const ct_params P) {
       u = u_next;
       col_cur = col_next;
     }
-    // end markers for the consumers, one per group: a tile header with ns < 0 (both producer warps arrive)
-    for (int g = 0; g < NG; g++) {
-      if (tseq >= rl) ensure_done(tseq - rl);
-      if (lane == 0) {
-        if (!isY) hdr[tslot].ns = -1;
-        mbar_arrive(&tfull[tslot]);
-      }
-      tseq++;
-      if (++tslot == rl) tslot = 0;
-    }
+    // end marker for the consumers: a tile header with ns < 0 (both producer warps arrive)
+    if (tseq >= rl) ensure_done(tseq - rl);
     if (lane == 0) {
+      if (!isY) hdr[tslot].ns = -1;
+      mbar_arrive(&tfull[tslot]);
       if (P.dbg) {  // producer records: {idle, 0, tiles, total}
         long long* d = P.dbg + ((size_t)gridDim.x * NCONS + 2 * blockIdx.x + (isY ? 0 : 1)) * 4;
-        d[0] = p_idle; d[1] = 0; d[2] = tseq - NG; d[3] = clock64() - p_begin;
+        d[0] = p_idle; d[1] = 0; d[2] = tseq; d[3] = clock64() - p_begin;
       }
     }
     return;
@@ -388,11 +378,11 @@ lj_celltile_force(const ct_params P) {
   const uint32_t ring = (uint32_t)ry * (uint32_t)cap_y;
   const uint32_t ybase_s = smem_u32(ybase);
   const uint32_t dummy = (uint32_t)cap_y - 1u;
-  int tslot = warp / WPG, tphase = 0;  // this group's first tile (rl >= NG: checked at launch)
+  int tslot = 0, tphase = 0;
   long long t_wait = 0, t_work = 0, n_quads = 0;
   const long long t_begin = P.dbg ? clock64() : 0;
-  int first = warp % WPG;  // quads are dealt round-robin over the group's warps ACROSS its tiles: a
-                           // per-tile deal would always leave the same warps with the extra quad
+  int first = warp;  // quads are dealt round-robin over the warps ACROSS tiles: tiles hold fewer
+                     // quads than there are warps, a per-tile deal would leave the high warps idle
   for (;;) {
     {
       long long tw0 = 0;
@@ -407,7 +397,7 @@ lj_celltile_force(const ct_params P) {
       const int nquads = (ns + kRows - 1) / kRows;
       int quad = first;
       const bool had_quad = quad < nquads;
-      first = (first + WPG - nquads % WPG) % WPG;
+      first = (first + NCONS - nquads % NCONS) % NCONS;
       if (quad < nquads && (P.mode & 15) != 3) {
         const int self0 = h.y;
         const uint32_t u0 = (uint32_t)h.z;
@@ -445,7 +435,7 @@ lj_celltile_force(const ct_params P) {
               asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
               return v;
             };
-            for (; grp < ngroups; grp += WPG) {
+            for (; grp < ngroups; grp += NCONS) {
               const int r = grp * R + gix;
               const bool valid = r < ns;
               int4 m = make_int4(0, (int)u0, 0, 0);
@@ -568,7 +558,7 @@ lj_celltile_force(const ct_params P) {
               asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
               asm volatile("ld.shared.f64 %0, [%1];" : "=d"(z) : "r"(az));
             };
-            for (; quad < nquads; quad += WPG) {
+            for (; quad < nquads; quad += NCONS) {
               const int r = quad * 4 + gi;
               const bool valid = r < ns;
               int4 m = make_int4(0, (int)u0, 0, 0);
@@ -617,8 +607,7 @@ lj_celltile_force(const ct_params P) {
       __syncwarp();
       if (P.dbg && had_quad) t_work += clock64() - tw1;
       if (lane == 0) mbar_arrive(&tempty[tslot]);  // this warp is through with the tile
-      tslot += NG;                                 // the group's next tile
-      if (tslot >= rl) { tslot -= rl; tphase ^= 1; }
+      if (++tslot == rl) { tslot = 0; tphase ^= 1; }
     }
   }
   if (P.dbg && lane == 0) {
@@ -628,27 +617,24 @@ lj_celltile_force(const ct_params P) {
 }
 
 // ring sizes for a CTA with `budget` bytes of dynamic shared memory.  A tile holds five y-rows and
-// one list slot; with NG groups NG consecutive tiles are in work at once (NG + 4 y-rows, NG list
-// slots) and the producers should be a few tiles ahead of them.  At a unit boundary the last tile
-// of the old unit and the first tile of the new one hold ten y-rows between them.
-static bool ring_sizes(size_t budget, size_t ys, size_t ls, int ng, int& ry, int& rl) {
+// one list slot; at a unit boundary the last tile of the old unit and the first tile of the new one
+// hold ten y-rows between them, so fewer than ten y slots drain the pipeline at every boundary.
+// Prefer >= 10 y slots, then balance the look-ahead of the two rings.
+static bool ring_sizes(size_t budget, size_t ys, size_t ls, int& ry, int& rl) {
   int best = -1;
   ry = rl = 0;
   for (int l = kCtMaxL; l >= kTileMinLSlots; l--) {
     if ((size_t)l * ls + kTileMinYSlots * ys > budget) continue;
     int y = (int)((budget - (size_t)l * ls) / ys);
     if (y > kCtMaxY) y = kCtMaxY;
-    // look-ahead in tiles beyond the ng in work, as the y ring and the list ring allow it
-    const int ahead_y = y - 4 - ng, ahead_l = l - ng;
-    int score = ahead_y < ahead_l ? ahead_y : ahead_l;
-    if (score < 1) continue;
-    if (y >= 9 + ng && l >= 2 + ng) score += 100;
+    int score = (y - 5 < l - 1) ? y - 5 : l - 1;
+    if (y >= 10 && l >= 3) score += 100;
     if (score > best) { best = score; ry = y; rl = l; }
   }
   return best >= 0;
 }
 
-template <int LAYOUT, bool MX, int NCONS, int NB, int WPG>
+template <int LAYOUT, bool MX, int NCONS, int NB>
 int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
                     cudaStream_t st, int ry, int rl) {
   const lj_tile_geom& g = ctx->tl_g;
@@ -656,7 +642,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   {  // diagnostics: cap the ring sizes
     const int ry_env = lj_diag_int("LJ_TILE_RY"), rl_env = lj_diag_int("LJ_TILE_RL");
     if (ry_env >= kTileMinYSlots && ry_env < ry) ry = ry_env;
-    if (rl_env >= kTileMinLSlots && rl_env >= NCONS / WPG && rl_env < rl) rl = rl_env;
+    if (rl_env >= kTileMinLSlots && rl_env < rl) rl = rl_env;
   }
   const int seg_env = lj_diag_int("LJ_TILE_SEG");
   // columns without a single list entry (the ghost layers of a decomposed run) are skipped
@@ -698,13 +684,13 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   }
 #endif
   const size_t smem = (size_t)ry * ys + (size_t)rl * ls;
-  auto kern = lj_celltile_force<LAYOUT, MX, NCONS, NB, WPG>;
+  auto kern = lj_celltile_force<LAYOUT, MX, NCONS, NB>;
   LJ_FUNC_SMEM(ctx, kern, smem);
   const int nunits = ncols * nseg;
   const int grid = nunits < NB * ctx->sm_count ? nunits : NB * ctx->sm_count;
   if (lj_diag_set("LJ_TILE_DEBUG"))
-    fprintf(stderr, "[lj] cell-tile force: %d consumer warps in groups of %d, %d units (%d columns x %d segments of %d), "
-            "y ring %d x %zu B, list ring %d x %zu B, smem %zu B\n", NCONS, WPG, nunits, ncols, nseg, seg_len, ry, ys, rl,
+    fprintf(stderr, "[lj] cell-tile force: %d consumer warps, %d units (%d columns x %d segments of %d), "
+            "y ring %d x %zu B, list ring %d x %zu B, smem %zu B\n", NCONS, nunits, ncols, nseg, seg_len, ry, ys, rl,
             ls, smem);
   kern<<<(unsigned)grid, (NCONS + 2) * 32, smem, st>>>(P);
   LJ_LAUNCHED(ctx);
@@ -741,34 +727,25 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   return LJ_OK;
 }
 
-// consumer-warp layout: NCONS warps in groups of 4 when the rings hold the groups' tiles plus some
-// look-ahead, else one group (every warp on every tile, the round-1 pipeline)
+// 16 consumer warps + 2 producer warps in one CTA per SM; other layouts in diagnostic builds only
 template <int LAYOUT, bool MX>
 int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
                       cudaStream_t st) {
   const lj_tile_geom& g = ctx->tl_g;
   const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
   int ry = 0, rl = 0;
-  const int nc = lj_diag_int("LJ_TILE_CONSUMERS"), wpg = lj_diag_int("LJ_TILE_WPG");
 #if LJ_DIAG
+  const int nc = lj_diag_int("LJ_TILE_CONSUMERS");
   if (nc == 8) {  // two CTAs per SM (measured slower: two pipelines, twice the producers)
     const size_t half = (size_t)(227 * 1024) / 2 - 9 * 1024;
-    LJ_REQUIRE(ctx, ring_sizes(half, ys, ls, 1, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
-    return launch_celltile<LAYOUT, MX, 8, 2, 8>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+    LJ_REQUIRE(ctx, ring_sizes(half, ys, ls, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
+    return launch_celltile<LAYOUT, MX, 8, 2>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
   }
-  if (nc == 24 && wpg != 24 && ring_sizes(kTileSmemBudget, ys, ls, 6, ry, rl))
-    return launch_celltile<LAYOUT, MX, 24, 1, 4>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
-  if (nc == 24 && ring_sizes(kTileSmemBudget, ys, ls, 1, ry, rl))
-    return launch_celltile<LAYOUT, MX, 24, 1, 24>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
-  if (nc == 20 && ring_sizes(kTileSmemBudget, ys, ls, 5, ry, rl))
-    return launch_celltile<LAYOUT, MX, 20, 1, 4>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
-  if (wpg == 8 && ring_sizes(kTileSmemBudget, ys, ls, 2, ry, rl))
-    return launch_celltile<LAYOUT, MX, 16, 1, 8>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  if (nc == 24 && ring_sizes(kTileSmemBudget, ys, ls, ry, rl))
+    return launch_celltile<LAYOUT, MX, 24, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
 #endif
-  if (wpg != 16 && ring_sizes(kTileSmemBudget, ys, ls, 4, ry, rl))
-    return launch_celltile<LAYOUT, MX, 16, 1, 4>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
-  LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, 1, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
-  return launch_celltile<LAYOUT, MX, 16, 1, 16>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
+  return launch_celltile<LAYOUT, MX, 16, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
 }
 
 }  // namespace

@@ -301,13 +301,12 @@ int launch_cluster(lj_ctx* ctx, const lj_force_args* a, int64_t c0, int64_t c1, 
                    long long cl2_bits, cudaStream_t st) {
   const size_t smem = (size_t)2 * kClCapInts * sizeof(uint32_t);
   auto kern = lj_gather_cluster<LAYOUT>;
-  static bool configured = false;
-  static int per_sm = 1;
-  if (!configured) {
-    LJ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // shared-memory opt-in and occupancy are per DEVICE: cached in the context, not in the process
+  LJ_FUNC_SMEM(ctx, kern, smem);
+  int& per_sm = ctx->func_occ[reinterpret_cast<const void*>(kern)];
+  if (per_sm < 1) {
     LJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kClThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    configured = true;
   }
   const int64_t ntiles = (c1 - c0 + kClTile - 1) / kClTile;
   int64_t grid = (int64_t)ctx->sm_count * per_sm;

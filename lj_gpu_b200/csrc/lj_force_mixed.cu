@@ -263,6 +263,7 @@ int lj_force_mixed_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64
     case LJ_AOS_D3: k_to_fixed<LJ_AOS_D3><<<cb, 256, 0, st>>>(a->q, pn, a->plane_stride, fp, q32); break;
     case LJ_AOS_D4: k_to_fixed<LJ_AOS_D4><<<cb, 256, 0, st>>>(a->q, pn, a->plane_stride, fp, q32); break;
     case LJ_AOS_F4: k_to_fixed<LJ_AOS_F4><<<cb, 256, 0, st>>>(a->q, pn, a->plane_stride, fp, q32); break;
+    case LJ_AOS_F3: k_to_fixed<LJ_AOS_F3><<<cb, 256, 0, st>>>(a->q, pn, a->plane_stride, fp, q32); break;
     default: k_to_fixed<LJ_SOA_D><<<cb, 256, 0, st>>>(a->q, pn, a->plane_stride, fp, q32); break;
   }
   LJ_LAUNCHED(ctx);
@@ -279,6 +280,9 @@ int lj_force_mixed_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64
         break;
       case LJ_AOS_F4:
         lj_gather_cluster_mixed<LJ_AOS_F4><<<blocks, 128, 0, st>>>(a->q, q32, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2f, a->cl2, fp, ctx->cl_list, ctx->cl_ptr);
+        break;
+      case LJ_AOS_F3:
+        lj_gather_cluster_mixed<LJ_AOS_F3><<<blocks, 128, 0, st>>>(a->q, q32, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2f, a->cl2, fp, ctx->cl_list, ctx->cl_ptr);
         break;
       default:
         lj_gather_cluster_mixed<LJ_SOA_D><<<blocks, 128, 0, st>>>(a->q, q32, a->p, ctx->cl_r0, ctx->cl_r1, c0, c1, a->plane_stride, c24, c48, cl2f, a->cl2, fp, ctx->cl_list, ctx->cl_ptr);
@@ -304,6 +308,10 @@ int lj_force_mixed_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64
     case LJ_AOS_F4:
       ok = a->pointer64 ? launch_mixed_g<LJ_AOS_F4, true>(g, a, q32, fp, r0, r1, tb, st)
                         : launch_mixed_g<LJ_AOS_F4, false>(g, a, q32, fp, r0, r1, tb, st);
+      break;
+    case LJ_AOS_F3:
+      ok = a->pointer64 ? launch_mixed_g<LJ_AOS_F3, true>(g, a, q32, fp, r0, r1, tb, st)
+                        : launch_mixed_g<LJ_AOS_F3, false>(g, a, q32, fp, r0, r1, tb, st);
       break;
   }
   LJ_REQUIRE(ctx, ok, "lj_force_step: no mixed kernel for this configuration");

@@ -197,13 +197,12 @@ int launch_tile(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, dou
                 long long cl2_bits, cudaStream_t st) {
   const size_t smem = (size_t)2 * kCapInts * sizeof(int32_t);
   auto kern = lj_gather_tile<G, LAYOUT, PTR64>;
-  static bool configured = false;
-  static int per_sm = 1;
-  if (!configured) {
-    LJ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // shared-memory opt-in and occupancy are per DEVICE: cached in the context, not in the process
+  LJ_FUNC_SMEM(ctx, kern, smem);
+  int& per_sm = ctx->func_occ[reinterpret_cast<const void*>(kern)];
+  if (per_sm < 1) {
     LJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    configured = true;
   }
   const int64_t ntiles = (r1 - r0 + kTileRows - 1) / kTileRows;
   int64_t grid = (int64_t)ctx->sm_count * per_sm;  // persistent: one wave, tiles strided

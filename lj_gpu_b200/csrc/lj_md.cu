@@ -96,6 +96,7 @@ extern "C" {
 
 int lj_drift(lj_ctx* ctx, void* q, const void* p, int64_t pn, int32_t layout, int64_t plane_stride,
              double dt, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (pn <= 0) return LJ_OK;
   LJ_REQUIRE(ctx, q && p, "lj_drift: null array");
@@ -113,6 +114,7 @@ int lj_drift(lj_ctx* ctx, void* q, const void* p, int64_t pn, int32_t layout, in
 
 int lj_max_displacement2(lj_ctx* ctx, const void* q, const void* q_ref, int64_t pn, int32_t layout,
                          int64_t plane_stride, double* out_host, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, out_host != nullptr, "lj_max_displacement2: null output");
   *out_host = 0.0;
@@ -138,6 +140,7 @@ int lj_max_displacement2(lj_ctx* ctx, const void* q, const void* q_ref, int64_t 
 
 int lj_energy(lj_ctx* ctx, const lj_force_args* a, double* kinetic_out, double* potential_out,
               void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, a && kinetic_out && potential_out, "lj_energy: null argument");
   *kinetic_out = *potential_out = 0.0;

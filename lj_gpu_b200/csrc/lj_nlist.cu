@@ -932,6 +932,7 @@ int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t p
     case LJ_AOS_D3: k_bbox<LJ_AOS_D3><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
     case LJ_AOS_D4: k_bbox<LJ_AOS_D4><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
     case LJ_AOS_F4: k_bbox<LJ_AOS_F4><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
+    case LJ_AOS_F3: k_bbox<LJ_AOS_F3><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
     default: k_bbox<LJ_SOA_D><<<nb, 256, 0, st>>>(q, pn, plane, bb); break;
   }
   LJ_LAUNCHED(ctx);
@@ -991,6 +992,7 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, 
   const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
   const uint32_t* nop_u = reinterpret_cast<const uint32_t*>(a->number_of_partners);
   ctx->tl_valid = false;  // the cell-sort scratch and any mirror derived from it are rebuilt below
+  ctx->graph_loop = -1;   // ... and a cached CUDA graph may replay the kernel that ran on the old mirror
   // any list these arrays were mirrored by is stale from here on
   if (ctx->cl_valid && (ctx->cl_id_list == a->sorted_list || ctx->cl_id_nop == a->number_of_partners ||
                         ctx->cl_id_ptr == a->pointer))
@@ -1287,6 +1289,7 @@ int lj_sort_rows_launch(lj_ctx* ctx, int32_t* list, const int32_t* nop, const vo
 
 extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number_of_pairs_out,
                              void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, a != nullptr, "lj_build_list: null args");
   LJ_REQUIRE(ctx, a->pn >= 0 && a->pn < 2147483647LL, "lj_build_list: particle_number out of range");
@@ -1302,7 +1305,7 @@ extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number
   if (a->layout == LJ_SOA_D)
     LJ_REQUIRE(ctx, a->plane_stride >= a->pn, "lj_build_list: SoA plane_stride < particle_number");
   int rc;
-  const bool tiles = (a->flags & LJ_LIST_TILES) && !a->half && a->layout != LJ_AOS_F4;
+  const bool tiles = (a->flags & LJ_LIST_TILES) && !a->half && a->layout != LJ_AOS_F4 && a->layout != LJ_AOS_F3;
   bool deferred = tiles;  // let the cell-tile fill pass write sorted_list too, if the engine allows
   switch (a->layout) {
     case LJ_AOS_D3: rc = build_list_impl<LJ_AOS_D3>(ctx, a, st, &deferred); break;
@@ -1314,6 +1317,10 @@ extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number
     case LJ_AOS_F4:
       LJ_REQUIRE(ctx, (uintptr_t)a->q % 16 == 0, "lj_build_list: float4 array must be 16-byte aligned");
       rc = build_list_impl<LJ_AOS_F4>(ctx, a, st, &deferred);
+      break;
+    case LJ_AOS_F3:
+      LJ_REQUIRE(ctx, (uintptr_t)a->q % 4 == 0, "lj_build_list: float3 array must be 4-byte aligned");
+      rc = build_list_impl<LJ_AOS_F3>(ctx, a, st, &deferred);
       break;
     default: return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_build_list", "unknown layout");
   }
@@ -1342,6 +1349,7 @@ extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number
 
 extern "C" int lj_list_result(lj_ctx* ctx, int64_t* number_of_pairs_out, int32_t* max_partners_out,
                               void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, ctx->totals != nullptr, "lj_list_result: no list has been built on this context");
   cudaStream_t st = lj_stream(ctx, stream);
@@ -1360,6 +1368,7 @@ extern "C" int lj_list_result(lj_ctx* ctx, int64_t* number_of_pairs_out, int32_t
 extern "C" int lj_build_ell(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* nop,
                             const void* pointer, int32_t pointer64, int64_t pn, int32_t* tl,
                             int64_t capacity_entries, int32_t* max_partners_out, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, pn >= 0, "lj_build_ell: negative particle_number");
   cudaStream_t st = lj_stream(ctx, stream);
@@ -1385,9 +1394,55 @@ extern "C" int lj_build_ell(lj_ctx* ctx, const int32_t* sorted_list, const int32
   return LJ_OK;
 }
 
+// CSR -> row-major padded table (one thread per table entry, zero padding)
+template <bool PTR64>
+__global__ void __launch_bounds__(256)
+k_csr_to_ellrows(const int32_t* __restrict__ list, const int32_t* __restrict__ nop, const void* __restrict__ pointer,
+                 int64_t pn, int width, int32_t* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pn * width) return;
+  const int64_t i = t / width;
+  const int k = (int)(t - i * width);
+  out[t] = k < nop[i] ? list[row_offset<PTR64>(pointer, i) + k] : 0;
+}
+
+extern "C" int lj_build_ell_rows(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* nop,
+                                 const void* pointer, int32_t pointer64, int64_t pn, int32_t width,
+                                 int32_t* out, int64_t capacity_entries, int32_t* max_partners_out,
+                                 void* stream) {
+  LJ_ENTER(ctx);
+  LJ_REQUIRE(ctx, pn >= 0 && width >= 0, "lj_build_ell_rows: negative size");
+  cudaStream_t st = lj_stream(ctx, stream);
+  if (pn == 0) { if (max_partners_out) *max_partners_out = 0; return LJ_OK; }
+  LJ_REQUIRE(ctx, sorted_list && nop && pointer && out, "lj_build_ell_rows: null array");
+  int rc = lj_scratch_reserve(ctx, 1, st);
+  if (rc) return rc;
+  int* mx = &ctx->totals->max_np;
+  LJ_CUDA(ctx, cudaMemsetAsync(mx, 0, sizeof(int), st));
+  k_max_np<<<4 * ctx->sm_count, 256, 0, st>>>(nop, pn, mx);
+  LJ_LAUNCHED(ctx);
+  LJ_CUDA(ctx, cudaMemcpyAsync(&ctx->totals_host->max_np, mx, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  const int max_np = ctx->totals_host->max_np;
+  if (max_partners_out) *max_partners_out = max_np;
+  // the reference's fixed NUM_NEIGH = 60 (cuda/force_cuda.cu:15) is smaller than its own longest row
+  // (78 at rho = 0.5): its rows overlap.  Here a width that does not hold the longest row is an error.
+  if (width < max_np)
+    return lj_set_error(ctx, LJ_ERR_CAPACITY, "lj_build_ell_rows", "width < max_partners: rows would overlap");
+  if ((int64_t)width * pn > capacity_entries)
+    return lj_set_error(ctx, LJ_ERR_CAPACITY, "lj_build_ell_rows", "sorted_list2d capacity < width*pn");
+  if (width == 0) return LJ_OK;
+  const unsigned blocks = (unsigned)blocks_for((int64_t)width * pn, 256);
+  if (pointer64) k_csr_to_ellrows<true><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, width, out);
+  else k_csr_to_ellrows<false><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, width, out);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
 extern "C" int lj_shuffle_rows(lj_ctx* ctx, int32_t* sorted_list, const int32_t* nop,
                                const void* pointer, int32_t pointer64, int64_t pn, uint32_t seed,
                                void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (pn <= 0) return LJ_OK;
   LJ_REQUIRE(ctx, sorted_list && nop && pointer, "lj_shuffle_rows: null array");
@@ -1395,6 +1450,7 @@ extern "C" int lj_shuffle_rows(lj_ctx* ctx, int32_t* sorted_list, const int32_t*
   // consumed in its shuffled order
   if (ctx->cl_id_list == sorted_list) ctx->cl_valid = false;
   if (ctx->tl_id_list == sorted_list) ctx->tl_valid = false;
+  ctx->graph_loop = -1;  // a cached CUDA graph may have captured the kernel that ran on the mirror
   cudaStream_t st = lj_stream(ctx, stream);
   const unsigned blocks = (unsigned)blocks_for(pn, 256);
   if (pointer64) k_shuffle_rows<true><<<blocks, 256, 0, st>>>(sorted_list, nop, pointer, pn, seed);
@@ -1406,6 +1462,7 @@ extern "C" int lj_shuffle_rows(lj_ctx* ctx, int32_t* sorted_list, const int32_t*
 extern "C" int lj_validate_list(lj_ctx* ctx, const int32_t* sorted_list, const int32_t* nop,
                                 const void* pointer, int32_t pointer64, int64_t pn,
                                 int64_t number_of_pairs, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (pn <= 0) return LJ_OK;
   LJ_REQUIRE(ctx, sorted_list && nop && pointer, "lj_validate_list: null array");

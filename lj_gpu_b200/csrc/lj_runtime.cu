@@ -114,6 +114,7 @@ int lj_ctx_destroy(lj_ctx* ctx) {
 }
 
 int lj_sync(lj_ctx* ctx, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (stream) {
     LJ_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
@@ -126,9 +127,11 @@ int lj_sync(lj_ctx* ctx, void* stream) {
 }
 
 int lj_list_invalidate(lj_ctx* ctx) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   ctx->cl_valid = false;
   ctx->tl_valid = false;
+  ctx->graph_loop = -1;  // a cached CUDA graph may have captured the kernel that ran on the mirror
   return LJ_OK;
 }
 
@@ -139,6 +142,7 @@ int lj_device_sm_count(lj_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 // ------------------------------------------------------------------ memory layer ------
 int lj_dev_alloc(lj_ctx* ctx, size_t bytes, void** out, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx || !out) return LJ_ERR_BAD_ARG;
   *out = nullptr;
   if (bytes == 0) return LJ_OK;
@@ -147,12 +151,14 @@ int lj_dev_alloc(lj_ctx* ctx, size_t bytes, void** out, void* stream) {
 }
 
 int lj_dev_free(lj_ctx* ctx, void* ptr, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (ptr) LJ_CUDA(ctx, cudaFreeAsync(ptr, lj_stream(ctx, stream)));
   return LJ_OK;
 }
 
 int lj_buf_allocate(lj_ctx* ctx, size_t bytes, lj_buf* out, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx || !out) return LJ_ERR_BAD_ARG;
   out->host = out->dev = nullptr;
   out->bytes = bytes;
@@ -168,6 +174,7 @@ int lj_buf_allocate(lj_ctx* ctx, size_t bytes, lj_buf* out, void* stream) {
 }
 
 int lj_buf_deallocate(lj_ctx* ctx, lj_buf* buf, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx || !buf) return LJ_ERR_BAD_ARG;
   if (buf->dev) LJ_CUDA(ctx, cudaFreeAsync(buf->dev, lj_stream(ctx, stream)));
   if (buf->host) {
@@ -181,6 +188,7 @@ int lj_buf_deallocate(lj_ctx* ctx, lj_buf* buf, void* stream) {
 }
 
 int lj_buf_host2dev(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx || !buf) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, beg + count <= buf->bytes, "lj_buf_host2dev: range exceeds the buffer");
   if (count == 0) return LJ_OK;
@@ -190,6 +198,7 @@ int lj_buf_host2dev(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, vo
 }
 
 int lj_buf_dev2host(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx || !buf) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, beg + count <= buf->bytes, "lj_buf_dev2host: range exceeds the buffer");
   if (count == 0) return LJ_OK;
@@ -200,6 +209,7 @@ int lj_buf_dev2host(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, vo
 
 int lj_buf_set_val32(lj_ctx* ctx, const lj_buf* buf, size_t beg, size_t count, uint32_t value,
                      void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx || !buf) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, (beg + count) * 4 <= buf->bytes, "lj_buf_set_val32: range exceeds the buffer");
   if (count == 0) return LJ_OK;
@@ -220,6 +230,7 @@ static int ring_init(lj_ctx* ctx) {
 }
 
 int lj_upload(lj_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (bytes == 0) return LJ_OK;
   LJ_REQUIRE(ctx, dev_dst && host_src, "lj_upload: null pointer");
@@ -247,6 +258,7 @@ int lj_upload(lj_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes, vo
 }
 
 int lj_download(lj_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (bytes == 0) return LJ_OK;
   LJ_REQUIRE(ctx, host_dst && dev_src, "lj_download: null pointer");
@@ -281,11 +293,13 @@ int lj_download(lj_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, 
 
 // ------------------------------------------------------------------ force entry points -
 int lj_force_step(lj_ctx* ctx, const lj_force_args* args, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   return lj_force_launch(ctx, args, lj_stream(ctx, stream));
 }
 
 int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int use_graph, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, args != nullptr && loop >= 0, "lj_force_loop: bad arguments");
   cudaStream_t st = lj_stream(ctx, stream);
@@ -381,6 +395,7 @@ static int soa6_gather(lj_ctx* ctx, double* dst, const double* x, const double* 
 
 int lj_force_loop_soa6(lj_ctx* ctx, const double* qx, const double* qy, const double* qz, double* px,
                        double* py, double* pz, const lj_force_args* fa, int loop, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, fa && qx && qy && qz && px && py && pz && loop >= 0, "lj_force_loop_soa6: bad arguments");
   LJ_REQUIRE(ctx, fa->pn >= 0, "lj_force_loop_soa6: negative particle_number");
@@ -411,6 +426,7 @@ int lj_force_loop_soa6(lj_ctx* ctx, const double* qx, const double* qy, const do
 
 int lj_build_list_soa6(lj_ctx* ctx, const double* qx, const double* qy, const double* qz,
                        const lj_list_args* la, int64_t* number_of_pairs_out, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, la && qx && qy && qz, "lj_build_list_soa6: bad arguments");
   LJ_REQUIRE(ctx, la->pn >= 0 && la->pn < 2147483647LL, "lj_build_list_soa6: particle_number out of range");
@@ -433,10 +449,11 @@ int lj_build_list_soa6(lj_ctx* ctx, const double* qx, const double* qy, const do
 
 // ------------------------------------------------------------------ measure() ---------
 static size_t vec_bytes(int layout) {
-  return layout == LJ_AOS_D4 ? 32 : layout == LJ_AOS_D3 ? 24 : layout == LJ_AOS_F4 ? 16 : 8;
+  return layout == LJ_AOS_D4 ? 32 : layout == LJ_AOS_D3 ? 24 : layout == LJ_AOS_F4 ? 16 : layout == LJ_AOS_F3 ? 12 : 8;
 }
 
 int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   LJ_REQUIRE(ctx, m && m->q_host && m->p_host && m->pn > 0 && m->loop >= 0, "lj_measure: bad arguments");
   LJ_REQUIRE(ctx, m->layout == LJ_AOS_D3 || m->layout == LJ_AOS_D4 || m->layout == LJ_SOA_D,
@@ -446,6 +463,9 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
   const size_t qbytes = m->layout == LJ_SOA_D ? (size_t)m->plane_stride * 3 * 8 : (size_t)pn * vec_bytes(m->layout);
   if (m->layout == LJ_SOA_D) LJ_REQUIRE(ctx, m->plane_stride >= pn, "lj_measure: plane_stride < pn");
   const bool own_list = m->list_host == nullptr;
+  // validated before the first allocation: LJ_REQUIRE returns, it does not release anything
+  LJ_REQUIRE(ctx, own_list || (m->number_of_partners_host && m->pointer_host && m->number_of_pairs_in >= 0),
+             "lj_measure: incomplete host list");
   const double t_all0 = now_s();
   m->h2d_bytes = m->d2h_bytes = 0;
   m->list_builds = 0;
@@ -490,8 +510,6 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
       M_TRY(lj_list_result(ctx, &npairs, &max_np, st));
       m->list_builds = 1;
     } else {
-      LJ_REQUIRE(ctx, m->number_of_partners_host && m->pointer_host && m->number_of_pairs_in >= 0,
-                 "lj_measure: incomplete host list");
       npairs = m->number_of_pairs_in;
       capacity = npairs;
       M_TRY(lj_dev_alloc(ctx, sizeof(int32_t) * (size_t)(capacity ? capacity : 1), (void**)&list, st));
@@ -547,6 +565,7 @@ done:
 
 // ------------------------------------------------------------------ multi-GPU helpers --
 int lj_ipc_alloc(lj_ctx* ctx, size_t bytes, void** out) {
+  LJ_ENTER(ctx);
   if (!ctx || !out) return LJ_ERR_BAD_ARG;
   *out = nullptr;
   LJ_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 16));
@@ -554,12 +573,14 @@ int lj_ipc_alloc(lj_ctx* ctx, size_t bytes, void** out) {
 }
 
 int lj_ipc_free(lj_ctx* ctx, void* ptr) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (ptr) LJ_CUDA(ctx, cudaFree(ptr));
   return LJ_OK;
 }
 
 int lj_ipc_export(lj_ctx* ctx, void* dev_ptr, uint8_t handle_out[64]) {
+  LJ_ENTER(ctx);
   if (!ctx || !dev_ptr || !handle_out) return LJ_ERR_BAD_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t h;
@@ -569,6 +590,7 @@ int lj_ipc_export(lj_ctx* ctx, void* dev_ptr, uint8_t handle_out[64]) {
 }
 
 int lj_ipc_open(lj_ctx* ctx, const uint8_t handle[64], void** peer_ptr_out) {
+  LJ_ENTER(ctx);
   if (!ctx || !handle || !peer_ptr_out) return LJ_ERR_BAD_ARG;
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, 64);
@@ -577,12 +599,14 @@ int lj_ipc_open(lj_ctx* ctx, const uint8_t handle[64], void** peer_ptr_out) {
 }
 
 int lj_ipc_close(lj_ctx* ctx, void* peer_ptr) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (peer_ptr) LJ_CUDA(ctx, cudaIpcCloseMemHandle(peer_ptr));
   return LJ_OK;
 }
 
 int lj_halo_pull(lj_ctx* ctx, void* local_dst, const void* peer_src, size_t bytes, void* stream) {
+  LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (bytes == 0) return LJ_OK;
   LJ_REQUIRE(ctx, local_dst && peer_src, "lj_halo_pull: null pointer");

@@ -94,6 +94,12 @@ def make_slab(rank: int, world: int, density: float, L: float, search_len: float
         raise ValueError("more ranks (%d) than lattice layers (%d)" % (world, n))
     bounds = [(n * r) // world for r in range(world + 1)]
     halo = int(np.ceil((search_len + 0.5 * s + jitter) / s))
+    thinnest = min(bounds[r + 1] - bounds[r] for r in range(world))
+    if world > 1 and thinnest < halo:
+        # the ghosts of a slab thinner than the halo live on rank +-2: the one-hop exchange below
+        # would send rows it does not own
+        raise ValueError("slab of %d lattice layers is thinner than the halo (%d layers): use fewer ranks "
+                         "(<= %d) for this system" % (thinnest, halo, max(1, n // halo)))
     return Slab(rank, world, n, bounds[rank], bounds[rank + 1], halo, 4 * n * n)
 
 

@@ -66,13 +66,13 @@ def test_struct_layout_matches_the_header(tmp_path):
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lj_b200.h"\n'
                    'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(lj_force_args),'
                    'sizeof(lj_list_args), sizeof(lj_measure_args), sizeof(lj_buf),'
-                   'offsetof(lj_force_args, list_entries), offsetof(lj_list_args, row_end),'
+                   'offsetof(lj_force_args, ell_width), offsetof(lj_list_args, row_end),'
                    'offsetof(lj_measure_args, d2h_bytes));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [C.sizeof(_capi.LjForceArgs), C.sizeof(_capi.LjListArgs), C.sizeof(_capi.LjMeasureArgs),
-            C.sizeof(_capi.LjBuf), _capi.LjForceArgs.list_entries.offset, _capi.LjListArgs.row_end.offset,
+            C.sizeof(_capi.LjBuf), _capi.LjForceArgs.ell_width.offset, _capi.LjListArgs.row_end.offset,
             _capi.LjMeasureArgs.d2h_bytes.offset]
     assert got == want
 

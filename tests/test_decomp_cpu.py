@@ -17,10 +17,13 @@ DENSITY, L, STEPS = 0.8, 17.3, 3
 
 
 def test_slab_bookkeeping():
-    for world in (1, 2, 3, 4, 8):
+    # a slab thinner than the halo would need ghosts from rank +-2: refused, not silently wrong
+    with pytest.raises(ValueError):
+        decomp.make_slab(0, 8, DENSITY, 40.0)           # 23 layers / 8 ranks = 2-3 layers < halo of 3
+    for world, box in ((1, 40.0), (2, 40.0), (3, 40.0), (4, 40.0), (8, 60.0)):
         s = decomp.lattice_spacing(DENSITY)
-        n = int(40.0 / s)
-        slabs = [decomp.make_slab(r, world, DENSITY, 40.0) for r in range(world)]
+        n = int(box / s)
+        slabs = [decomp.make_slab(r, world, DENSITY, box) for r in range(world)]
         assert slabs[0].lo == 0 and slabs[-1].hi == 4 * n ** 3
         for a, b in zip(slabs, slabs[1:]):
             assert a.hi == b.lo                      # contiguous, disjoint, complete

@@ -854,8 +854,11 @@ def test_celltile_moving_particles_rebuild_and_row_ranges(ctx, torch, sysS):
             ctx.rebuild(qr, plr)
             ctx.rebuild(qd, pl, tiles=True)
     assert torch.equal(qd, qr) and torch.equal(pd, pr)
-    # a rebuild without the flag leaves no mirror: explicit request fails, AUTO falls back
+    # rebuild() reuses the flags the list was built with (the mirror is rebuilt with the list) ...
     ctx.rebuild(qd, pl)
+    ctx.force_step(qd, pd, pl, variant="celltile")
+    # ... a rebuild with the flag switched off leaves no mirror: explicit request fails, AUTO falls back
+    ctx.rebuild(qd, pl, tiles=False)
     with pytest.raises(LJError):
         ctx.force_step(qd, pd, pl, variant="celltile")
     ctx.force_step(qd, pd, pl)
@@ -896,3 +899,77 @@ def test_celltile_large_system_matches_per_row_kernel(ctx, torch):
     ka = torch.sort(rows * pn + plain.sorted_list[:plain.number_of_pairs].long()).values
     kb = torch.sort(rows * pn + pl.sorted_list[:pl.number_of_pairs].long()).values
     assert torch.equal(ka, kb)
+
+
+# ------------------------------------------------------------------------ SURVEY 8 leftovers (round 2)
+def test_newton3_on_the_half_ell_table(ctx, torch, sysA, oracle):
+    """force_kernel_memopt2_with_aar / memopt3_with_aar (cuda/kernel.cuh:344-423): thread per i on the
+    HALF column-major ELL table, reaction on j by atomics.  Checker: the oracle's force_sorted on the
+    same half list (= cpu_ref/force_soa.cpp:163-195)."""
+    s = sysA
+    for layout in ("aos4", "aos3", "soa"):
+        qd, pd = s.device_arrays(torch, layout)
+        pn = s.pn if layout == "soa" else None
+        pl = ctx.makepair(qd, half=True, layout=layout, pn=pn, sort_rows=True)
+        tl = ctx.make_transposed_pairlist(pl)
+        tl_o, max_np = oracle.transpose_list(s.half[2], s.half[0], s.half[1])
+        assert pl.max_partners == max_np
+        assert np.array_equal(tl.cpu().numpy()[:max_np * s.pn], tl_o[:max_np * s.pn])
+        ctx.force_loop(qd, pd, pl, loop=100, ell=True, layout=layout, pn=pn)   # half list -> Newton-3
+        assert s.err(pd, layout) < TOL_FP64
+        if layout == "aos4":
+            assert torch.all(pd[:, 3] == 77.5)
+
+
+def test_row_major_padded_ell(ctx, torch, sysA, sysS):
+    """make_sorted_list2d() (cuda/force_cuda.cu:242-253) with a width that holds the longest row: the
+    table equals the CSR rows zero padded, the gather on it reproduces the oracle, and the reference's
+    own width (NUM_NEIGH = 60 < max_partners = 78 at rho = 0.5) is refused instead of overlapping."""
+    from lj_gpu_b200 import LJError, _capi
+    s = sysA
+    qd, pd = s.device_arrays(torch, "aos4")
+    pl = ctx.makepair(qd, sort_rows=True)
+    assert pl.max_partners == 78
+    with pytest.raises(LJError) as e:
+        ctx.make_sorted_list2d(pl, width=60)
+    assert e.value.status == _capi.LJ_ERR_CAPACITY
+    t2 = ctx.make_sorted_list2d(pl).cpu().numpy().reshape(s.pn, pl.max_partners)
+    nop, ptr, lst = s.full
+    for i in (0, 1, s.pn // 2, s.pn - 1):
+        assert np.array_equal(t2[i, :nop[i]], lst[ptr[i]:ptr[i] + nop[i]]) and np.all(t2[i, nop[i]:] == 0)
+    assert int((t2 != 0).sum()) <= len(lst)
+    for group in (1, 8, 32):
+        pd.zero_()
+        ctx.force_loop(qd, pd, pl, loop=100, ell_rows=True, group=group)
+        assert s.err(pd, "aos4") < TOL_FP64, group
+    # wider than needed, other layouts
+    for layout in ("aos3", "soa"):
+        q2, p2 = sysS.device_arrays(torch, layout)
+        pn = sysS.pn if layout == "soa" else None
+        pl2 = ctx.makepair(q2, layout=layout, pn=pn)
+        ctx.make_sorted_list2d(pl2, width=pl2.max_partners + 5)
+        ctx.force_loop(q2, p2, pl2, loop=sysS.steps, ell_rows=True, layout=layout, pn=pn)
+        assert sysS.err(p2, layout) < TOL_FP64
+
+
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_float3_layout_mixed(ctx, torch, sysA, sysB, oracle, which):
+    """The reference's q_f3 / p_f3 buffers (cuda/force_cuda.cu:24): packed float3 in and out.
+    Checker = the FP64 oracle on the SAME float-valued positions (as for float4)."""
+    s = sysA if which == "A" else sysB
+    qf = np.ascontiguousarray(s.q.astype(np.float32))
+    q64 = np.ascontiguousarray(qf.astype(np.float64))
+    nop_o, ptr_o, lst_o = oracle.makepair(q64, full=True)
+    p_o = np.zeros_like(q64)
+    oracle.force_gather(q64, p_o, nop_o, ptr_o, lst_o, steps=100, static_q=True)
+    qd = torch.from_numpy(qf).cuda()
+    assert qd.shape[1] == 3 and qd.dtype == torch.float32
+    pd = torch.zeros_like(qd)
+    pl = ctx.makepair(qd)                                          # list build straight from float3
+    nop, ptr, lst = list_to_host(pl)
+    assert np.array_equal(nop, nop_o) and np.array_equal(s.lo.sort_rows(nop, ptr, lst), lst_o)
+    ctx.force_loop(qd, pd, pl, loop=100, precision="mixed")
+    assert np.abs(pd.cpu().numpy() - p_o).max() / np.abs(p_o).max() < TOL_MIXED
+    from lj_gpu_b200 import LJError
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl, precision="fp64")              # float3 is a mixed-precision layout

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 KNOBS = ("LJ_TILE_WPG", "LJ_TILE_CONSUMERS", "LJ_TILE_RY", "LJ_TILE_RL", "LJ_TILE_SEG", "LJ_TILE_MODE",
-         "LJ_TILE_DBG", "LJ_TILE_DEBUG", "LJ_TILE_ROWS")
+         "LJ_TILE_ROWS")
 
 
 def main():
