@@ -182,7 +182,7 @@ def run_cuda(args):
     if world > 1:
         from lj_gpu_b200 import decomp
         return decomp.bench_decomposed(args, METRIC, UNIT, REBUILD_EVERY, ClockSampler, measured_peak_gbs,
-                                       algorithmic_bytes)
+                                       algorithmic_bytes, cpu_reference_sample)
     torch.cuda.set_device(local)
     ctx = LJContext(local)
     stream = torch.cuda.current_stream()

@@ -165,6 +165,14 @@ typedef struct lj_force_args {
 } lj_force_args;
 
 LJ_API int lj_force_step(lj_ctx* ctx, const lj_force_args* args, void* stream);
+/* The same step in two parts, for callers that overlap a ghost exchange with the force work
+ * (z-slab decomposition): the list must have been built for a row range [row_begin,row_end) of
+ * "owned" particles with LJ_LIST_TILES.  LJ_PART_INTERIOR runs the tiles none of whose stencil cell
+ * layers held, at build time, a particle outside the row range -- they only read positions of owned
+ * particles; LJ_PART_BOUNDARY runs the others and first refreshes the library's copy of the
+ * positions outside the row range (the ghosts).  INTERIOR then BOUNDARY = one lj_force_step. */
+enum { LJ_PART_ALL = 0, LJ_PART_INTERIOR = 1, LJ_PART_BOUNDARY = 2 };
+LJ_API int lj_force_step_part(lj_ctx* ctx, const lj_force_args* args, int32_t part, void* stream);
 /* `loop` back-to-back steps, the body of measure() (cuda/force_cuda.cu:333-335).  With
  * use_graph != 0 the steps are captured once into a CUDA graph and replayed. */
 LJ_API int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int use_graph, void* stream);
@@ -365,6 +373,27 @@ LJ_API int lj_ipc_close(lj_ctx* ctx, void* peer_ptr);
 /* Halo pull: copy `bytes` (multiple of 16) from a peer-mapped pointer into local memory
  * with a grid of 16-byte P2P loads over NVLink. */
 LJ_API int lj_halo_pull(lj_ctx* ctx, void* local_dst, const void* peer_src, size_t bytes, void* stream);
+
+/* Ordering between GPUs without host round trips: 32-bit step counters in peer-visible memory
+ * (lj_ipc_alloc'ed, or any device memory a peer can address).  lj_flag_set stores `value` once all
+ * earlier work of `stream` is done (system-scope release); lj_flag_wait holds `stream` until the flag
+ * is >= at_least.  lj_halo_pull_sync copies one or two segments in one launch; each segment first
+ * waits for *wait_flag >= wait_value (NULL: no wait; typically the owner's "q of step k is final")
+ * and finally stores done_value into *done_flag (NULL: none; typically a counter in the OWNER's
+ * memory, which the owner waits for before it overwrites q).  A wait only ever depends on an
+ * earlier step of the other rank, so two ranks cannot wait for each other. */
+typedef struct lj_halo_seg {
+  void* local_dst;
+  const void* peer_src;
+  size_t bytes;                 /* multiple of 16 */
+  const int32_t* wait_flag;
+  int32_t wait_value;
+  int32_t done_value;
+  int32_t* done_flag;
+} lj_halo_seg;
+LJ_API int lj_flag_set(lj_ctx* ctx, int32_t* flag, int32_t value, void* stream);
+LJ_API int lj_flag_wait(lj_ctx* ctx, const int32_t* flag, int32_t at_least, void* stream);
+LJ_API int lj_halo_pull_sync(lj_ctx* ctx, const lj_halo_seg* segs, int32_t nsegs, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ LJ_LIST_CSR, LJ_LIST_ELL, LJ_LIST_ELL_ROWS = 0, 1, 2
 LJ_VARIANT_AUTO, LJ_VARIANT_SUBWARP, LJ_VARIANT_TILE_TMA, LJ_VARIANT_NEWTON3, LJ_VARIANT_CLUSTER, \
     LJ_VARIANT_CELLTILE = range(6)
 LJ_PREC_FP64, LJ_PREC_MIXED = 0, 1
+LJ_PART_ALL, LJ_PART_INTERIOR, LJ_PART_BOUNDARY = 0, 1, 2
 LJ_LIST_SORT_ROWS = 1
 LJ_LIST_CLUSTERS = 2
 LJ_LIST_TILES = 8
@@ -42,6 +43,12 @@ class LjForceArgs(C.Structure):
         ("plane_stride", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
         ("list_entries", C.c_int64), ("ell_width", C.c_int64),
     ]
+
+
+class LjHaloSeg(C.Structure):
+    _fields_ = [("local_dst", C.c_void_p), ("peer_src", C.c_void_p), ("bytes", C.c_size_t),
+                ("wait_flag", C.c_void_p), ("wait_value", C.c_int32), ("done_value", C.c_int32),
+                ("done_flag", C.c_void_p)]
 
 
 class LjListArgs(C.Structure):
@@ -90,6 +97,7 @@ PROTOTYPES = {
     "lj_upload": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "lj_download": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "lj_force_step": (C.c_int, [_vp, C.POINTER(LjForceArgs), _vp]),
+    "lj_force_step_part": (C.c_int, [_vp, C.POINTER(LjForceArgs), _i32, _vp]),
     "lj_force_loop": (C.c_int, [_vp, C.POINTER(LjForceArgs), C.c_int, C.c_int, _vp]),
     "lj_build_list": (C.c_int, [_vp, C.POINTER(LjListArgs), C.POINTER(_i64), _vp]),
     "lj_force_loop_soa6": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(LjForceArgs), C.c_int, _vp]),
@@ -115,6 +123,9 @@ PROTOTYPES = {
     "lj_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "lj_ipc_close": (C.c_int, [_vp, _vp]),
     "lj_halo_pull": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "lj_flag_set": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "lj_flag_wait": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "lj_halo_pull_sync": (C.c_int, [_vp, C.POINTER(LjHaloSeg), _i32, _vp]),
 }
 
 _lib = None

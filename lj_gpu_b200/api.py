@@ -425,10 +425,16 @@ class LJContext:
                                                 px.data_ptr(), py.data_ptr(), pz.data_ptr(), C.byref(a), loop,
                                                 self._stream(stream)))
 
-    def force_step(self, q, p, pl: PairList, stream=None, **kw):
-        """One kernel launch of measure() (cuda/force_cuda.cu:334): p += dt * F(q), in place."""
+    def force_step(self, q, p, pl: PairList, stream=None, part=None, **kw):
+        """One kernel launch of measure() (cuda/force_cuda.cu:334): p += dt * F(q), in place.
+        part="interior" | "boundary": lj_force_step_part on the cell-tile mirror (the tiles that do /
+        do not depend only on positions inside the list's row range)."""
         a = self.force_args(q, p, pl, **kw)
-        self._check(self.lib.lj_force_step(self.h, C.byref(a), self._stream(stream)))
+        if part is None:
+            self._check(self.lib.lj_force_step(self.h, C.byref(a), self._stream(stream)))
+        else:
+            code = {"interior": capi.LJ_PART_INTERIOR, "boundary": capi.LJ_PART_BOUNDARY, "all": capi.LJ_PART_ALL}[part]
+            self._check(self.lib.lj_force_step_part(self.h, C.byref(a), code, self._stream(stream)))
 
     def force_loop(self, q, p, pl: PairList, loop: int = LOOP, use_graph: bool = False, stream=None,
                    **kw):
@@ -554,6 +560,21 @@ class LJContext:
 
     def ipc_close(self, ptr: int):
         self._check(self.lib.lj_ipc_close(self.h, ptr))
+
+    def flag_set(self, flag_ptr: int, value: int, stream=None):
+        self._check(self.lib.lj_flag_set(self.h, flag_ptr, value, self._stream(stream)))
+
+    def flag_wait(self, flag_ptr: int, at_least: int, stream=None):
+        self._check(self.lib.lj_flag_wait(self.h, flag_ptr, at_least, self._stream(stream)))
+
+    def halo_pull_sync(self, segs, stream=None):
+        """segs: [(dst_ptr, src_ptr, nbytes, wait_flag_ptr|0, wait_value, done_flag_ptr|0, done_value)], one or two."""
+        arr = (capi.LjHaloSeg * len(segs))()
+        for k, (d, sp, n, wf, wv, df, dv) in enumerate(segs):
+            arr[k].local_dst, arr[k].peer_src, arr[k].bytes = d, sp, n
+            arr[k].wait_flag, arr[k].wait_value = (wf or None), wv
+            arr[k].done_flag, arr[k].done_value = (df or None), dv
+        self._check(self.lib.lj_halo_pull_sync(self.h, arr, len(segs), self._stream(stream)))
 
     def halo_pull(self, dst_ptr: int, peer_ptr: int, nbytes: int, stream=None):
         self._check(self.lib.lj_halo_pull(self.h, dst_ptr, peer_ptr, nbytes, self._stream(stream)))

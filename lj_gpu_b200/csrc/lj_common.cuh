@@ -40,7 +40,7 @@ struct lj_tile_geom {
   int max_units;   // largest list segment of one tile, in units of 8 entries
   int pad;         // the force kernel's unit counter lives here
   int ncols_active;  // columns (tx, cz) with at least one list entry; the others (ghost layers of a
-  int pad2;          // decomposed run) are skipped by the force kernel
+  int pad2;          // decomposed run) are skipped by the force kernel.  pad2: columns selected by a part launch
   unsigned long long total_units;  // whole mirror list, units of 8 entries
 };
 
@@ -109,6 +109,9 @@ struct lj_ctx {
   uint4* tl_ttab = nullptr;              // [ntiles][2] tile table
   int32_t* tl_cols = nullptr;            // [ncols_active] the active columns, ascending
   int64_t tl_cols_cap = 0;
+  int32_t* tl_zflag = nullptr;           // [nz] cell layers holding a particle outside the row range (part launches)
+  int32_t* tl_cols_sel = nullptr;        // columns selected by the last part launch (count in tl_geom->pad2)
+  int64_t tl_sel_cap = 0;
   int4* tl_meta = nullptr;               // [pn] {entries, first unit, original index, 0} of row s
   int64_t tl_pn_cap = 0, tl_cells_cap = 0, tl_list_cap = 0, tl_tab_cap = 0;  // particles, cells, units, tiles
   bool tl_valid = false;
@@ -127,6 +130,7 @@ struct lj_ctx {
   std::unordered_map<const void*, size_t> func_smem;  // kernel -> opted-in dynamic shared memory
   std::unordered_map<const void*, int> func_occ;      // kernel -> resident CTAs per SM (occupancy query)
 
+  unsigned int* pull_counter = nullptr;  // lj_halo_pull_sync: blocks of the running copy that have finished
   long long* diag_buf = nullptr;  // LJ_DIAG builds only: per-warp cycle counters of the cell-tile kernel
   int diag_dumps = 0;
 
@@ -207,15 +211,15 @@ static inline cudaStream_t lj_stream(lj_ctx* ctx, void* s) { (void)ctx; return (
 
 // internal entry points shared between translation units
 int lj_scratch_reserve(lj_ctx* ctx, int64_t pn, cudaStream_t st);
-int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st);
+int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st, int part = 0);
 int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t plane,
                    lj_list_totals* reset_totals, cudaStream_t st);
 // cell-tile mirror (lj_nlist.cu builds it, lj_force_celltile.cu consumes it)
-int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st);
+int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st, int part);
 bool lj_celltile_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1);
 bool lj_celltile_worthwhile(const lj_ctx* ctx);
 int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
-                             long long cl2_bits, cudaStream_t st);
+                             long long cl2_bits, cudaStream_t st, int part);
 // shared memory of the force kernel: a ring of y-row slots (cap_y packed double3 records each) and
 // a ring of list slots (a tile's list segment + 16 B of metadata per row)
 constexpr size_t kTileSmemBudget = 227 * 1024 - 8 * 1024;  // minus the kernel's static shared memory

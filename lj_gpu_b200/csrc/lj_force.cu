@@ -518,7 +518,7 @@ bool lj_cluster_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, in
 int lj_force_cluster_launch(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, double c24,
                             double c48, long long cl2_bits, cudaStream_t st);
 
-int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
+int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st, int part) {
   LJ_REQUIRE(ctx, a != nullptr, "lj_force_step: null args");
   LJ_REQUIRE(ctx, a->pn >= 0, "lj_force_step: negative particle_number");
   if (a->pn == 0) return LJ_OK;
@@ -586,9 +586,15 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
     LJ_REQUIRE(ctx, lj_celltile_usable(ctx, a, r0, r1),
                "lj_force_step: no cell-tile mirror for these arrays (build with LJ_LIST_TILES; CSR, "
                "double positions, same row range)");
+  if (part != 0) {  // lj_force_step_part: INTERIOR / BOUNDARY tiles of the mirror
+    LJ_REQUIRE(ctx, part == LJ_PART_INTERIOR || part == LJ_PART_BOUNDARY, "lj_force_step_part: unknown part");
+    LJ_REQUIRE(ctx, (a->variant == LJ_VARIANT_CELLTILE || a->variant == LJ_VARIANT_AUTO) && lj_celltile_usable(ctx, a, r0, r1),
+               "lj_force_step_part: needs the cell-tile mirror of these arrays and this row range (LJ_LIST_TILES)");
+    return lj_force_celltile_launch(ctx, a, c24, c48, cl2_bits, st, part);
+  }
   if ((a->variant == LJ_VARIANT_CELLTILE || (a->variant == LJ_VARIANT_AUTO && lj_celltile_worthwhile(ctx))) &&
       lj_celltile_usable(ctx, a, r0, r1))
-    return lj_force_celltile_launch(ctx, a, c24, c48, cl2_bits, st);
+    return lj_force_celltile_launch(ctx, a, c24, c48, cl2_bits, st, 0);
   if (a->precision == LJ_PREC_MIXED) {
     LJ_REQUIRE(ctx, !n3 && a->list_layout == LJ_LIST_CSR, "lj_force_step: mixed precision is gather/CSR only");
     return lj_force_mixed_launch(ctx, a, r0, r1, g, tb, st);

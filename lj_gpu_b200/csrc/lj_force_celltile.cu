@@ -97,6 +97,7 @@ struct ct_params {
   const uint2* ytab; const uint4* ttab; const int4* meta; const uint16_t* list;
   int ntx, ny, ncols;    // tiles per pencil, cells in y, ACTIVE columns (all of them: ntx * nz)
   const int32_t* cols;   // the active columns, or NULL when every column is active
+  const int* ncols_dev;  // part launches: the number of selected columns is only known on the device
   int seg_len, nseg;     // a unit = one column x [seg*seg_len, min(ny, (seg+1)*seg_len))
   int cap_y, cap_units, cap_rows;
   int ry, rl;            // ring sizes: y-row slots, tile slots (list + metadata + barriers)
@@ -170,7 +171,8 @@ lj_celltile_force(const ct_params P) {
     yrel[threadIdx.x] = -1;
   }
   __syncthreads();
-  const int nunits = P.ncols * P.nseg;
+  const int ncols = P.ncols_dev ? *P.ncols_dev : P.ncols;  // (written by the permute kernel that ran before)
+  const int nunits = ncols * P.nseg;
 
   if (warp >= NCONS) {
     // ------------------------------------------------------- two producer warps, by role ---
@@ -220,7 +222,7 @@ lj_celltile_force(const ct_params P) {
     // table rows of unit u -> staging buffer b: y-rows max(y0-2,0) .. min(y1+1,ny-1) (warp Y),
     // tiles y0 .. y1-1 (warp L)
     auto stage_tables = [&](int u, int b) {  // returns the unit's column (tx, cz)
-      const int ci = u % P.ncols, seg = u / P.ncols;
+      const int ci = u % ncols, seg = u / ncols;
       const int col = P.cols ? __ldg(P.cols + ci) : ci;
       const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
       const int ylo = max(y0 - 2, 0), yhi = min(y1 + 1, P.ny - 1);
@@ -246,7 +248,7 @@ lj_celltile_force(const ct_params P) {
     if (u < nunits) col_cur = stage_tables(u, 0);
     for (; u < nunits; nu++) {
       const int u_next = next_unit(nu + 1);
-      const int seg = u / P.ncols;
+      const int seg = u / ncols;
       const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
       const int ntile = y1 - y0;
       const int tb = nu & 1;
@@ -636,7 +638,7 @@ static bool ring_sizes(size_t budget, size_t ys, size_t ls, int& ry, int& rl) {
 
 template <int LAYOUT, bool MX, int NCONS, int NB>
 int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
-                    cudaStream_t st, int ry, int rl) {
+                    cudaStream_t st, int ry, int rl, int part) {
   const lj_tile_geom& g = ctx->tl_g;
   const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
   {  // diagnostics: cap the ring sizes
@@ -672,6 +674,11 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   P.ytab = ctx->tl_tab; P.ttab = ctx->tl_ttab; P.meta = ctx->tl_meta; P.list = ctx->tl_list;
   P.ntx = g.ntx; P.ny = g.ny; P.ncols = ncols; P.seg_len = seg_len; P.nseg = nseg;
   P.cols = all_cols ? nullptr : ctx->tl_cols;
+  P.ncols_dev = nullptr;
+  if (part != 0) {  // the permute kernel compacted the selected columns; their number stays on the device
+    P.cols = ctx->tl_cols_sel;
+    P.ncols_dev = &ctx->tl_geom->pad2;
+  }
   P.cap_y = lj_celltile_cap_y(g); P.cap_units = g.max_units; P.cap_rows = g.max_rows;
   P.ry = ry; P.rl = rl; P.lslot_bytes = (int)ls;
   P.mode = lj_diag_int("LJ_TILE_MODE");
@@ -686,7 +693,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   const size_t smem = (size_t)ry * ys + (size_t)rl * ls;
   auto kern = lj_celltile_force<LAYOUT, MX, NCONS, NB>;
   LJ_FUNC_SMEM(ctx, kern, smem);
-  const int nunits = ncols * nseg;
+  const int nunits = ncols * nseg;  // part launches: an upper bound, CTAs without a unit leave at once
   const int grid = nunits < NB * ctx->sm_count ? nunits : NB * ctx->sm_count;
   if (lj_diag_set("LJ_TILE_DEBUG"))
     fprintf(stderr, "[lj] cell-tile force: %d consumer warps, %d units (%d columns x %d segments of %d), "
@@ -730,7 +737,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
 // 16 consumer warps + 2 producer warps in one CTA per SM; other layouts in diagnostic builds only
 template <int LAYOUT, bool MX>
 int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
-                      cudaStream_t st) {
+                      cudaStream_t st, int part) {
   const lj_tile_geom& g = ctx->tl_g;
   const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
   int ry = 0, rl = 0;
@@ -739,13 +746,13 @@ int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c4
   if (nc == 8) {  // two CTAs per SM (measured slower: two pipelines, twice the producers)
     const size_t half = (size_t)(227 * 1024) / 2 - 9 * 1024;
     LJ_REQUIRE(ctx, ring_sizes(half, ys, ls, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
-    return launch_celltile<LAYOUT, MX, 8, 2>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+    return launch_celltile<LAYOUT, MX, 8, 2>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
   }
   if (nc == 24 && ring_sizes(kTileSmemBudget, ys, ls, ry, rl))
-    return launch_celltile<LAYOUT, MX, 24, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+    return launch_celltile<LAYOUT, MX, 24, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
 #endif
   LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
-  return launch_celltile<LAYOUT, MX, 16, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl);
+  return launch_celltile<LAYOUT, MX, 16, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
 }
 
 }  // namespace
@@ -766,20 +773,20 @@ bool lj_celltile_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, i
 }
 
 int lj_force_celltile_launch(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
-                             long long cl2_bits, cudaStream_t st) {
-  int rc = lj_celltile_permute(ctx, a, st);
+                             long long cl2_bits, cudaStream_t st, int part) {
+  int rc = lj_celltile_permute(ctx, a, st, part);
   if (rc) return rc;
   const bool mx = a->precision == LJ_PREC_MIXED;
   switch (a->layout) {
     case LJ_AOS_D4:
-      return mx ? dispatch_celltile<LJ_AOS_D4, true>(ctx, a, c24, c48, cl2_bits, st)
-                : dispatch_celltile<LJ_AOS_D4, false>(ctx, a, c24, c48, cl2_bits, st);
+      return mx ? dispatch_celltile<LJ_AOS_D4, true>(ctx, a, c24, c48, cl2_bits, st, part)
+                : dispatch_celltile<LJ_AOS_D4, false>(ctx, a, c24, c48, cl2_bits, st, part);
     case LJ_AOS_D3:
-      return mx ? dispatch_celltile<LJ_AOS_D3, true>(ctx, a, c24, c48, cl2_bits, st)
-                : dispatch_celltile<LJ_AOS_D3, false>(ctx, a, c24, c48, cl2_bits, st);
+      return mx ? dispatch_celltile<LJ_AOS_D3, true>(ctx, a, c24, c48, cl2_bits, st, part)
+                : dispatch_celltile<LJ_AOS_D3, false>(ctx, a, c24, c48, cl2_bits, st, part);
     case LJ_SOA_D:
-      return mx ? dispatch_celltile<LJ_SOA_D, true>(ctx, a, c24, c48, cl2_bits, st)
-                : dispatch_celltile<LJ_SOA_D, false>(ctx, a, c24, c48, cl2_bits, st);
+      return mx ? dispatch_celltile<LJ_SOA_D, true>(ctx, a, c24, c48, cl2_bits, st, part)
+                : dispatch_celltile<LJ_SOA_D, false>(ctx, a, c24, c48, cl2_bits, st, part);
   }
   return lj_set_error(ctx, LJ_ERR_BAD_ARG, "lj_force_step", "layout");
 }

@@ -859,15 +859,45 @@ k_tile_fill(int64_t pn, const grid_ext* __restrict__ ge, const lj_tile_geom* __r
   }
 }
 
+// Column selection of a PART launch (lj_force_step_part): the active columns (tx, cz) whose five
+// stencil cell layers cz-2 .. cz+2 held no particle outside the list's row range at build time
+// (INTERIOR: their rows depend on positions inside the row range only -- in a z-slab run, on no
+// ghost), or the others (BOUNDARY).  Run by block 0 of the permute kernel that precedes the force
+// kernel; the order of the compacted list does not matter (units are dealt dynamically).
+struct tile_part { int part; int64_t r0, r1; const int32_t* cols; int ncols_all; const int32_t* zflag; int32_t* cols_sel; };
+
+__device__ __forceinline__ void tile_select_columns(const tile_part& tp, const lj_tile_geom* __restrict__ tg,
+                                                     lj_tile_geom* __restrict__ tg_out) {
+  __shared__ int n_sel;
+  if (threadIdx.x == 0) n_sel = 0;
+  __syncthreads();
+  const int ntx = tg->ntx, nz = tg->nz;
+  const bool all_cols = tg->ncols_active <= 0 || tg->ncols_active >= ntx * nz;
+  const int ncols = all_cols ? ntx * nz : tg->ncols_active;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    const int col = all_cols ? c : tp.cols[c];
+    const int cz = col / ntx;
+    bool touched = false;
+    for (int z = max(cz - 2, 0); z <= min(cz + 2, nz - 1); z++) touched |= tp.zflag[z] != 0;
+    if ((tp.part == 1) == !touched) tp.cols_sel[atomicAdd(&n_sel, 1)] = col;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) tg_out->pad2 = n_sel;  // read by the force kernel that follows
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(256)
 k_tile_permute(const void* __restrict__ q, int64_t plane, const int32_t* __restrict__ order,
-               int64_t pn, double2* __restrict__ qxy, double* __restrict__ qz, int* __restrict__ unit_counter) {
+               int64_t pn, double2* __restrict__ qxy, double* __restrict__ qz, lj_tile_geom* __restrict__ tg,
+               const tile_part tp) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) *unit_counter = 0;  // the force kernel that follows deals its work units from here
+  if (s == 0) tg->pad = 0;  // the force kernel that follows deals its work units from here
+  if (tp.part != 0 && blockIdx.x == 0) tile_select_columns(tp, tg, tg);
   if (s >= pn) return;
+  const int o = order[s];
+  if (tp.part != 0 && ((o >= tp.r0 && o < tp.r1) != (tp.part == 1))) return;  // INTERIOR: rows of the range; BOUNDARY: the others
   double x, y, z;
-  load_pos<LAYOUT>(q, order[s], plane, x, y, z);
+  load_pos<LAYOUT>(q, o, plane, x, y, z);
   qxy[s] = make_double2(x, y);  // two planes: the force kernel reads {x,y} with LDS.128, z with LDS.64
   qz[s] = z;
 }
@@ -877,15 +907,27 @@ k_tile_permute(const void* __restrict__ q, int64_t plane, const int32_t* __restr
 template <int LAYOUT>
 __global__ void __launch_bounds__(256)
 k_tile_permute_fx(const void* __restrict__ q, int64_t plane, const int32_t* __restrict__ order,
-                  int64_t pn, double scale, int4* __restrict__ qfx, int* __restrict__ unit_counter) {
+                  int64_t pn, double scale, int4* __restrict__ qfx, lj_tile_geom* __restrict__ tg,
+                  const tile_part tp) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) *unit_counter = 0;
+  if (s == 0) tg->pad = 0;
+  if (tp.part != 0 && blockIdx.x == 0) tile_select_columns(tp, tg, tg);
   if (s >= pn) return;
   const int o = order[s];
+  if (tp.part != 0 && ((o >= tp.r0 && o < tp.r1) != (tp.part == 1))) return;
   double x, y, z;
   load_pos<LAYOUT>(q, o, plane, x, y, z);
   qfx[s] = make_int4((int)(uint32_t)__double2ll_rn(x * scale), (int)(uint32_t)__double2ll_rn(y * scale),
                      (int)(uint32_t)__double2ll_rn(z * scale), o);
+}
+
+// cell layers (z index) that hold a particle outside the list's row range [r0, r1)
+__global__ void __launch_bounds__(256)
+k_tile_zflag(int64_t pn, int64_t r0, int64_t r1, const int32_t* __restrict__ cell_of,
+             const lj_tile_geom* __restrict__ tg, int32_t* __restrict__ zflag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn || (i >= r0 && i < r1)) return;
+  zflag[cell_of[i] / (tg->nx * tg->ny)] = 1;
 }
 
 int64_t blocks_for(int64_t n, int tb) { return (n + tb - 1) / tb; }
@@ -1212,6 +1254,16 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
     if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cols, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
     ctx->tl_cols_cap = ncols_all;
   }
+  if (ncols_all > ctx->tl_sel_cap) {  // column selection of part launches: z-layer flags, compacted columns
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_zflag, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cols_sel, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    ctx->tl_sel_cap = ncols_all;
+  }
+  LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_zflag, 0, sizeof(int32_t) * (size_t)ncols_all, st));
+  if (r0 > 0 || r1 < pn) {
+    k_tile_zflag<<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(pn, r0, r1, ctx->cell_of, ctx->tl_geom, ctx->tl_zflag);
+    LJ_LAUNCHED(ctx);
+  }
   LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_cols, 0, sizeof(int32_t) * (size_t)ncols_all, st));
   k_tile_table<<<(unsigned)blocks_for(g.ntiles, 128), 128, 0, st>>>(ctx->tl_cell_start, ctx->tl_off,
                                                                      ctx->tl_geom, ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols);
@@ -1254,9 +1306,15 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
   return LJ_OK;
 }
 
-// positions of this step in cell order (the force kernel's TMA source)
-int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
+// positions of this step in cell order (the force kernel's TMA source).  part 0: every particle;
+// 1 / 2 (lj_force_step_part): only the particles inside / outside the mirror's row range, and
+// block 0 compacts the columns the force kernel that follows will walk (tile_select_columns).
+int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st, int part) {
   const unsigned blocks = (unsigned)blocks_for(a->pn, 256);
+  tile_part tp{};
+  tp.part = part; tp.r0 = ctx->tl_r0; tp.r1 = ctx->tl_r1;
+  tp.cols = ctx->tl_cols; tp.ncols_all = ctx->tl_g.ntx * ctx->tl_g.nz;
+  tp.zflag = ctx->tl_zflag; tp.cols_sel = ctx->tl_cols_sel;
   if (a->precision == LJ_PREC_MIXED) {
     if (ctx->tl_qfx_cap < a->pn) {
       if (ctx->tl_qfx) LJ_CUDA(ctx, cudaFreeAsync(ctx->tl_qfx, st));
@@ -1268,17 +1326,17 @@ int lj_celltile_permute(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st) {
     }
     const double scale = lj_fx_frame_for(a->cl2).scale;
     switch (a->layout) {
-      case LJ_AOS_D3: k_tile_permute_fx<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, &ctx->tl_geom->pad); break;
-      case LJ_AOS_D4: k_tile_permute_fx<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, &ctx->tl_geom->pad); break;
-      default: k_tile_permute_fx<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, &ctx->tl_geom->pad); break;
+      case LJ_AOS_D3: k_tile_permute_fx<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, ctx->tl_geom, tp); break;
+      case LJ_AOS_D4: k_tile_permute_fx<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, ctx->tl_geom, tp); break;
+      default: k_tile_permute_fx<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, scale, ctx->tl_qfx, ctx->tl_geom, tp); break;
     }
     LJ_LAUNCHED(ctx);
     return LJ_OK;
   }
   switch (a->layout) {
-    case LJ_AOS_D3: k_tile_permute<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, &ctx->tl_geom->pad); break;
-    case LJ_AOS_D4: k_tile_permute<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, &ctx->tl_geom->pad); break;
-    default: k_tile_permute<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, &ctx->tl_geom->pad); break;
+    case LJ_AOS_D3: k_tile_permute<LJ_AOS_D3><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, ctx->tl_geom, tp); break;
+    case LJ_AOS_D4: k_tile_permute<LJ_AOS_D4><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, ctx->tl_geom, tp); break;
+    default: k_tile_permute<LJ_SOA_D><<<blocks, 256, 0, st>>>(a->q, a->plane_stride, ctx->tl_order, a->pn, reinterpret_cast<double2*>(ctx->tl_qs), ctx->tl_qz, ctx->tl_geom, tp); break;
   }
   LJ_LAUNCHED(ctx);
   return LJ_OK;

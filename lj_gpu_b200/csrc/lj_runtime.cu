@@ -298,6 +298,11 @@ int lj_force_step(lj_ctx* ctx, const lj_force_args* args, void* stream) {
   return lj_force_launch(ctx, args, lj_stream(ctx, stream));
 }
 
+int lj_force_step_part(lj_ctx* ctx, const lj_force_args* args, int part, void* stream) {
+  LJ_ENTER(ctx);
+  return lj_force_launch(ctx, args, lj_stream(ctx, stream), part);
+}
+
 int lj_force_loop(lj_ctx* ctx, const lj_force_args* args, int loop, int use_graph, void* stream) {
   LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
@@ -602,6 +607,101 @@ int lj_ipc_close(lj_ctx* ctx, void* peer_ptr) {
   LJ_ENTER(ctx);
   if (!ctx) return LJ_ERR_BAD_ARG;
   if (peer_ptr) LJ_CUDA(ctx, cudaIpcCloseMemHandle(peer_ptr));
+  return LJ_OK;
+}
+
+// ---- cross-GPU ordering without host round trips: 32-bit counters in peer-visible memory -------
+// A rank publishes "my q of step k is final" by storing k into a flag its neighbours have mapped
+// (lj_flag_set), a neighbour's pull waits for it on the device (k_copy16_sync), and reports "I have
+// read your q of step k" by storing k into a flag in the OWNER's memory, which the owner waits for
+// (lj_flag_wait) before it overwrites q.  System-scope release/acquire; each wait only depends on
+// work of an earlier step of the other rank, so the two streams cannot wait for each other.
+__global__ void k_flag_set(int* flag, int value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__device__ __forceinline__ void flag_spin(const int* flag, int at_least) {
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v < at_least) __nanosleep(200);
+  } while (v < at_least);
+}
+__global__ void k_flag_wait(const int* flag, int at_least) { flag_spin(flag, at_least); }
+// up to two segments (ghosts from the slab below and from the slab above) in ONE launch: the blocks
+// are split between them, each segment waits on and reports through its own flags
+struct copy_segs { lj_halo_seg s[2]; int n; };
+__global__ void __launch_bounds__(256)
+k_copy16_sync(const copy_segs segs, unsigned int* blocks_done) {
+  const int which = (segs.n == 2 && blockIdx.x >= gridDim.x / 2) ? 1 : 0;
+  const unsigned first = which ? gridDim.x / 2 : 0u;
+  const unsigned nblk = segs.n == 2 ? (which ? gridDim.x - gridDim.x / 2 : gridDim.x / 2) : gridDim.x;
+  const lj_halo_seg sg = segs.s[which];
+  if (sg.wait_flag) {
+    if (threadIdx.x == 0) flag_spin(sg.wait_flag, sg.wait_value);
+    __syncthreads();
+  }
+  int4* __restrict__ dst = reinterpret_cast<int4*>(sg.local_dst);
+  const int4* __restrict__ src = reinterpret_cast<const int4*>(sg.peer_src);
+  const size_t n16 = sg.bytes / 16;
+  for (size_t i = (size_t)(blockIdx.x - first) * blockDim.x + threadIdx.x; i < n16; i += (size_t)nblk * blockDim.x) {
+    int4 v;  // straight from the owner's memory: no stale copy in this GPU's L1
+    asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
+    dst[i] = v;
+  }
+  if (sg.done_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(blocks_done + which, 1u) == nblk - 1) {  // the last block reports for the whole segment
+        blocks_done[which] = 0;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(sg.done_flag), "r"(sg.done_value) : "memory");
+      }
+    }
+  }
+}
+
+int lj_flag_set(lj_ctx* ctx, int32_t* flag, int32_t value, void* stream) {
+  LJ_ENTER(ctx);
+  LJ_REQUIRE(ctx, flag != nullptr, "lj_flag_set: null flag");
+  k_flag_set<<<1, 1, 0, lj_stream(ctx, stream)>>>(flag, value);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+int lj_flag_wait(lj_ctx* ctx, const int32_t* flag, int32_t at_least, void* stream) {
+  LJ_ENTER(ctx);
+  LJ_REQUIRE(ctx, flag != nullptr, "lj_flag_wait: null flag");
+  k_flag_wait<<<1, 1, 0, lj_stream(ctx, stream)>>>(flag, at_least);
+  LJ_LAUNCHED(ctx);
+  return LJ_OK;
+}
+
+int lj_halo_pull_sync(lj_ctx* ctx, const lj_halo_seg* segs, int32_t nsegs, void* stream) {
+  LJ_ENTER(ctx);
+  LJ_REQUIRE(ctx, segs != nullptr && nsegs >= 1 && nsegs <= 2, "lj_halo_pull_sync: one or two segments");
+  copy_segs cs{};
+  cs.n = nsegs;
+  size_t most = 0;
+  for (int k = 0; k < nsegs; k++) {
+    cs.s[k] = segs[k];
+    LJ_REQUIRE(ctx, segs[k].bytes == 0 || (segs[k].local_dst && segs[k].peer_src), "lj_halo_pull_sync: null pointer");
+    LJ_REQUIRE(ctx, segs[k].bytes % 16 == 0 && (uintptr_t)segs[k].local_dst % 16 == 0 && (uintptr_t)segs[k].peer_src % 16 == 0,
+               "lj_halo_pull_sync: pointers and sizes must be multiples of 16 bytes");
+    if (segs[k].bytes > most) most = segs[k].bytes;
+  }
+  cudaStream_t st = lj_stream(ctx, stream);
+  if (!ctx->pull_counter) {
+    LJ_CUDA(ctx, cudaMalloc((void**)&ctx->pull_counter, 2 * sizeof(unsigned int)));
+    LJ_CUDA(ctx, cudaMemset(ctx->pull_counter, 0, 2 * sizeof(unsigned int)));
+  }
+  // a CTA per SM is enough to saturate an NVLink direction and leaves room for the interior force
+  // kernel running concurrently; two segments share the grid
+  size_t blocks = (most / 16 + 255) / 256 * (size_t)nsegs;
+  if (blocks > (size_t)ctx->sm_count) blocks = (size_t)ctx->sm_count;
+  if (blocks < (size_t)nsegs) blocks = (size_t)nsegs;
+  k_copy16_sync<<<(unsigned)blocks, 256, 0, st>>>(cs, ctx->pull_counter);
+  LJ_LAUNCHED(ctx);
   return LJ_OK;
 }
 

@@ -145,6 +145,19 @@ def exchange_halo(q_local, plan, dist, async_op: bool = False):
 # GPU execution (one process per GPU, torchrun)
 # ------------------------------------------------------------------------------------------
 class DecomposedSystem:
+    """One rank (= one process, one GPU) of the z-slab decomposition.
+
+    Per step:   publish()  "my q of step k is final"           (compute stream, lj_flag_set)
+                halo()     pull the neighbours' boundary layers (comm stream; each pull WAITS on the
+                           device for the owner's flag of step k and then tells the owner it is done)
+                force      interior tiles / rows while the halo flies, boundary tiles / rows after
+                           its event (lj_force_step_part on the cell-tile mirror, row ranges on the
+                           per-row kernels)
+    and before q is overwritten (drift):  wait_pulled()  both neighbours have read step k.
+    """
+
+    READY, PULLED_BY_BELOW, PULLED_BY_ABOVE = 0, 1, 2   # int32 slots of a rank's flag block
+
     def __init__(self, density: float, L: float, halo_mode: str = "nccl", search_len: float = 3.3,
                  tiles: bool = False):
         import torch
@@ -166,22 +179,27 @@ class DecomposedSystem:
         ql = local_positions(self.slab, q_all)
         del q_all
         q4 = np.zeros((ql.shape[0], 4)); q4[:, :3] = ql
-        if halo_mode == "p2p":  # the neighbours map this array through CUDA IPC
+        del ql
+        if halo_mode == "p2p":  # the neighbours map this array and the flag block through CUDA IPC
             self.q = self.ctx.ipc_tensor(q4.shape, torch.float64)
             self.q.copy_(torch.from_numpy(q4))
+            self.flags = self.ctx.ipc_tensor((4,), torch.int32)
+            self.flags.zero_()
         else:
             self.q = torch.from_numpy(q4).cuda()
+            self.flags = None
+        del q4
         self.p = torch.zeros_like(self.q)
         self.compute = torch.cuda.current_stream()
         self.comm = torch.cuda.Stream()
-        # tiles: also build the cell-tile mirror for the owned rows; the halo-then-force schedule
-        # (one launch over rows [0, n_own)) then runs the shared-memory kernel, the overlapped
-        # schedule (row sub-ranges) the per-row kernel
+        self.stepno = 0
+        # tiles: also build the cell-tile mirror for the owned rows: both schedules then run the
+        # shared-memory kernel (the overlapped one as lj_force_step_part INTERIOR / BOUNDARY)
         self.tiles = tiles
         self.pl = self.ctx.makepair(self.q, rows=(0, self.slab.n_own), search_len=search_len, tiles=tiles)
         self.search_len = search_len
         self.pairs_local = self.pl.number_of_pairs
-        self.peer_ptr = {}
+        self.peer_ptr, self.peer_flags = {}, {}
         if halo_mode == "p2p":
             ok = 1
             try:
@@ -193,16 +211,36 @@ class DecomposedSystem:
             if int(flag.item()) == 0:
                 self.halo_mode = "nccl"
 
-    # -- CUDA IPC: map the neighbours' q arrays ------------------------------------------
+    # -- CUDA IPC: map the neighbours' q arrays and flag blocks ------------------------------
     def _open_peers(self):
-        dist, torch = self.dist, self.torch
-        handle = self.ctx.ipc_export(self.q)  # q starts its own cudaMalloc block: offset 0
+        dist = self.dist
+        mine = (self.ctx.ipc_export(self.q), self.ctx.ipc_export(self.flags))  # each starts its own cudaMalloc block
         handles = [None] * self.world
-        dist.all_gather_object(handles, handle)
+        dist.all_gather_object(handles, mine)
         for peer in (self.rank - 1, self.rank + 1):
             if 0 <= peer < self.world:
-                self.peer_ptr[peer] = self.ctx.ipc_open(handles[peer])
+                self.peer_ptr[peer] = self.ctx.ipc_open(handles[peer][0])
+                self.peer_flags[peer] = self.ctx.ipc_open(handles[peer][1])
         dist.barrier()
+
+    def publish(self):
+        """q is final for the step that starts now (compute stream order)."""
+        self.stepno += 1
+        if self.halo_mode == "p2p":
+            self.ctx.flag_set(self.flags.data_ptr() + 4 * self.READY, self.stepno, stream=self.compute)
+        # my own exchange of this step must not start before my previous step is through with the ghost
+        # rows it is about to overwrite (and, NCCL, before my q is final for the sends)
+        self.q_final = self.torch.cuda.Event()
+        self.q_final.record(self.compute)
+
+    def wait_pulled(self):
+        """Hold the compute stream until both neighbours have read this step's q (call before q changes)."""
+        if self.halo_mode != "p2p":
+            return   # NCCL send/recv pairs are ordered by the collective itself
+        if self.rank > 0:
+            self.ctx.flag_wait(self.flags.data_ptr() + 4 * self.PULLED_BY_BELOW, self.stepno, stream=self.compute)
+        if self.rank < self.world - 1:
+            self.ctx.flag_wait(self.flags.data_ptr() + 4 * self.PULLED_BY_ABOVE, self.stepno, stream=self.compute)
 
     def halo(self, wait_event=None):
         """Start one ghost-position exchange on the comm stream; returns an event."""
@@ -210,26 +248,40 @@ class DecomposedSystem:
         with torch.cuda.stream(self.comm):
             if wait_event is not None:
                 self.comm.wait_event(wait_event)
+            if getattr(self, "q_final", None) is not None:
+                self.comm.wait_event(self.q_final)
             if self.halo_mode == "p2p":
                 row = self.q.shape[1] * 8
+                segs = []
                 for peer, kind, b, e in self.plan:
                     if kind != "recv" or e <= b:
                         continue
                     ps = self.slabs[peer]
-                    # my ghosts from below are the peer's top owned rows, from above its bottom rows
+                    # my ghosts from below are the peer's top owned rows, from above its bottom rows;
+                    # seen from the peer I am its neighbour above / below
                     src_b = ps.n_own - (e - b) if peer < self.rank else 0
-                    self.ctx.halo_pull(self.q.data_ptr() + b * row, self.peer_ptr[peer] + src_b * row,
-                                       (e - b) * row, stream=self.comm)
+                    done = self.PULLED_BY_ABOVE if peer < self.rank else self.PULLED_BY_BELOW
+                    segs.append((self.q.data_ptr() + b * row, self.peer_ptr[peer] + src_b * row, (e - b) * row,
+                                 self.peer_flags[peer] + 4 * self.READY, self.stepno,
+                                 self.peer_flags[peer] + 4 * done, self.stepno))
+                if segs:
+                    self.ctx.halo_pull_sync(segs, stream=self.comm)
             else:
                 exchange_halo(self.q, self.plan, self.dist)
             ev = torch.cuda.Event()
             ev.record(self.comm)
         return ev
 
-    def step(self, overlap: bool = True, **fkw):
-        """One force step: halo exchange overlapped with the interior rows."""
+    def force(self, ev, overlap: bool = True, **fkw):
+        """The force step of this rank around the halo event `ev`."""
         ctx, s = self.ctx, self.slab
-        ev = self.halo()
+        rows = (0, s.n_own)
+        if overlap and self.tiles and fkw.get("variant", "auto") in ("auto", "celltile"):
+            # cell-tile kernel in two parts: tiles that read no ghost run while the halo is in flight
+            ctx.force_step(self.q, self.p, self.pl, rows=rows, part="interior", **fkw)
+            self.compute.wait_event(ev)
+            ctx.force_step(self.q, self.p, self.pl, rows=rows, part="boundary", **fkw)
+            return
         ib, ie = s.interior_rows()
         if overlap and ie > ib:
             ctx.force_step(self.q, self.p, self.pl, rows=(ib, ie), **fkw)
@@ -239,78 +291,81 @@ class DecomposedSystem:
                     ctx.force_step(self.q, self.p, self.pl, rows=(b, e), **fkw)
         else:
             self.compute.wait_event(ev)
-            ctx.force_step(self.q, self.p, self.pl, rows=(0, s.n_own), **fkw)
+            ctx.force_step(self.q, self.p, self.pl, rows=rows, **fkw)
+
+    def step(self, overlap: bool = True, rebuild: bool = False, **fkw):
+        """One force step: halo exchange overlapped with the work that needs no ghost.  With
+        rebuild the list is rebuilt from this step's positions first (needs the ghosts: no overlap)."""
+        self.publish()
+        ev = self.halo()
+        if rebuild:
+            self.compute.wait_event(ev)
+            self.rebuild()
+            self.force(ev, overlap=False, **fkw)
+        else:
+            self.force(ev, overlap=overlap, **fkw)
+
+    def drift(self, dt: float):
+        """q += p dt for the OWNED particles, once both neighbours have read this step's q."""
+        self.wait_pulled()
+        self.ctx.drift(self.q, self.p, dt=dt, pn=self.slab.n_own, stream=self.compute)
 
     def rebuild(self):
         self.ctx.rebuild(self.q, self.pl, search_len=self.search_len, rows=(0, self.slab.n_own),
                          tiles=self.tiles)
 
     def run(self, steps: int, rebuild_every: int, first_step: int = 0, overlap: bool = True, **fkw):
+        """Static positions (the reference benchmark): `steps` force steps, list rebuilt every
+        `rebuild_every` steps (the rebuilt list is the same list: the cadence measures its cost)."""
         for k in range(first_step, first_step + steps):
-            if rebuild_every and k % rebuild_every == 0:
-                self.rebuild()
-            self.step(overlap=overlap, **fkw)
+            self.step(overlap=overlap, rebuild=bool(rebuild_every and k % rebuild_every == 0), **fkw)
 
-    def gather_p(self) -> np.ndarray | None:
-        """Owned momenta of every rank concatenated on rank 0 (tests / checks only)."""
-        dist, torch = self.dist, self.torch
-        mine = self.p[:self.slab.n_own, :3].contiguous().cpu()
+    def run_md(self, steps: int, dt: float, rebuild_every: int, overlap: bool = True, **fkw):
+        """Moving particles: kick (force step) + drift of the owned particles, fixed rebuild cadence."""
+        for k in range(steps):
+            self.step(overlap=overlap, rebuild=bool(k > 0 and rebuild_every and k % rebuild_every == 0), dt=dt, **fkw)
+            self.drift(dt)
+
+    def gather(self, what: str = "p") -> np.ndarray | None:
+        """Owned momenta (or positions) of every rank concatenated on rank 0 (tests / checks only)."""
+        dist = self.dist
+        src = self.p if what == "p" else self.q
+        mine = src[:self.slab.n_own, :3].contiguous().cpu()
         out = [None] * self.world if self.rank == 0 else None
         dist.gather_object(mine.numpy(), out, dst=0)
         return np.concatenate(out, axis=0) if self.rank == 0 else None
 
+    def gather_p(self) -> np.ndarray | None:
+        return self.gather("p")
 
-def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_peak_gbs, algorithmic_bytes):
-    """bench.py body for N > 1 (torchrun): weak scaling, ~1M particles per GPU."""
-    import torch
-    import torch.distributed as dist
 
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rank, world = dist.get_rank(), dist.get_world_size()
-    density = args.density
-    s = lattice_spacing(density)
-    # cubic lattice with ~1.0e6 * world particles and a layer count divisible by world
-    n = int(round((250047.0 * world) ** (1.0 / 3.0)))
-    n = max(world, (n + world - 1) // world * world)
-    if os.environ.get("LJ_BENCH_CELLS"):  # e.g. 320 at rho=0.8: BASELINE config 5 (N=131,072,000)
-        n = int(os.environ["LJ_BENCH_CELLS"])
-    L = (n + 0.05) * s
-    halo_mode = os.environ.get("LJ_HALO", "p2p")
-    tiles = args.variant in ("auto", "celltile") and args.prec == "fp64"
-    system = DecomposedSystem(density, L, halo_mode=halo_mode, tiles=tiles)
-    halo_mode = system.halo_mode
-    fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
-               threads_per_block=args.threads_per_block)
-    K, W = args.steps, max(args.warmup, 3)
+def _timed(torch, dist, fn, reps):
+    """mean ms per call over `reps` calls, device timed, MAX over ranks"""
+    torch.cuda.synchronize(); dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / reps], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _measure_system(system, K, W, rebuild_every, fkw, ClockSampler=None):
+    """Warm up, pick the schedule (both are timed, untimed region), then time EXACTLY K steps of the
+    cadence between two events; max over ranks.  Returns a dict of raw numbers (every rank)."""
+    torch, dist = system.torch, system.dist
     system.run(W, rebuild_every, **fkw)
     torch.cuda.synchronize(); dist.barrier()
-
-    def timed(fn, reps):
-        torch.cuda.synchronize(); dist.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record(); torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b) / reps], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-    # schedule choice (untimed): interior/boundary split with the halo in flight, or halo first
-    # and one launch; thin slabs and a 25-60 us halo can favour the latter
-    for ov in (False, True):   # first launches load kernels (the serial schedule runs the cell-tile kernel)
+    for ov in (False, True):   # first launches load kernels
         system.step(overlap=ov, **fkw)
         system.step(overlap=ov, **fkw)
-    ms_serial = timed(lambda: system.step(overlap=False, **fkw), 20)
-    ms_overlap = timed(lambda: system.step(overlap=True, **fkw), 20)
-    use_overlap = ms_overlap < ms_serial
-    if use_overlap and system.tiles:
-        # the overlapped schedule works on row sub-ranges, which the per-row kernels serve: do not pay
-        # for a mirror nobody reads
-        system.tiles = False
-        system.rebuild()
-    sampler = ClockSampler(local) if rank == 0 else None
+    reps = 10
+    ms_serial = _timed(torch, dist, lambda: system.step(overlap=False, **fkw), reps)
+    ms_overlap = _timed(torch, dist, lambda: system.step(overlap=True, **fkw), reps)
+    use_overlap = ms_overlap <= ms_serial
+    sampler = ClockSampler(system.local) if (ClockSampler and system.rank == 0) else None
     if sampler:
         sampler.start(); time.sleep(0.3)
     l0 = system.ctx.launches
@@ -326,32 +381,127 @@ def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_p
     launches = system.ctx.launches - l0
     pairs = torch.tensor([system.pl.number_of_pairs], dtype=torch.int64, device="cuda")
     dist.all_reduce(pairs)
-    ms_halo = timed(lambda: torch.cuda.current_stream().wait_event(system.halo()), 20)
+    # the pieces: the force step alone (no halo wait beyond the schedule's), one list rebuild, the halo alone
+    ms_force = _timed(torch, dist, lambda: system.step(overlap=use_overlap, **fkw), reps)
+    ms_build = _timed(torch, dist, system.rebuild, 3)
+    ms_halo = _timed(torch, dist, lambda: torch.cuda.current_stream().wait_event(system.halo()), reps)
     clocks = sampler.finish() if sampler else None
+    return dict(ms_total=float(ms.item()), pairs=int(pairs.item()), launches=int(launches), ms_serial=ms_serial,
+                ms_overlap=ms_overlap, use_overlap=use_overlap, ms_force=ms_force, ms_build=ms_build, ms_halo=ms_halo,
+                clocks=clocks)
+
+
+def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_peak_gbs, algorithmic_bytes,
+                     cpu_reference_sample=None):
+    """bench.py body for N > 1 (torchrun).  Main line: BASELINE config 5 -- FCC rho = 0.8, 320 cells per
+    side, N = 131,072,000 -- split into N z-slabs: STRONG scaling (the total work is fixed).  Side
+    block: the weak-scaling run of round 1 (~1.0e6 particles per GPU at the bench density)."""
+    import torch
+    import torch.distributed as dist
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    halo_mode = os.environ.get("LJ_HALO", "p2p")
+    tiles = args.variant in ("auto", "celltile")
+    if tiles and args.prec == "mixed":
+        tiles = "wide"
+    fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
+               threads_per_block=args.threads_per_block)
+    K, W = args.steps, max(args.warmup, 3)
+    peak, peak_src = measured_peak_gbs()
+
+    # ---------------- main: config 5, strong scaling
+    density5 = 0.8
+    cells5 = int(os.environ.get("LJ_BENCH_CELLS", "320"))     # 320 -> N = 131,072,000
+    L5 = (cells5 + 0.05) * lattice_spacing(density5)
+    t0 = time.perf_counter()
+    system = DecomposedSystem(density5, L5, halo_mode=halo_mode, tiles=tiles)
+    setup_s = time.perf_counter() - t0
+    # e2e: the resident arrays come from pinned HOST buffers and the momenta go back to the host; both
+    # copies are timed on the device and charged to the K steps (the reference's measure(): upload,
+    # LOOP launches, download)
+    qh = system.q.cpu().pin_memory()
+    ph = torch.zeros_like(qh).pin_memory()
+    ms_h2d = _timed(torch, dist, lambda: (system.q.copy_(qh, non_blocking=True), system.p.copy_(ph, non_blocking=True)), 1)
+    r = _measure_system(system, K, W, rebuild_every, fkw, ClockSampler)
+    ms_d2h = _timed(torch, dist, lambda: ph.copy_(system.p, non_blocking=True), 1)
+    checksum = float(ph[:system.slab.n_own, :3].sum())
+    n_local, n_own = system.slab.n_local, system.slab.n_own
+    pairs_local = system.pl.number_of_pairs
+    # per-rank roofline of the force step: this rank's algorithmic bytes / its step time
+    bytes_rank = algorithmic_bytes(n_own, pairs_local) + (n_local - n_own) * 32   # + the ghosts it reads
+    ghost_bytes = int((system.slab.n_lo + system.slab.n_hi) * 32)
+    sched = "overlap" if r["use_overlap"] else "halo-then-force"
+    halo_used = system.halo_mode
+    slab_layers = system.slab.z1 - system.slab.z0
+    pn5 = system.pn_global
+    del system, qh, ph
+    torch.cuda.empty_cache()
+
+    # ---------------- side: weak scaling, ~1.0e6 particles per GPU (round 1's SCALE workload)
+    weak = None
+    if not os.environ.get("LJ_BENCH_NO_WEAK"):
+        s = lattice_spacing(args.density)
+        n = int(round((250047.0 * world) ** (1.0 / 3.0)))
+        n = max(world, (n + world - 1) // world * world)
+        try:
+            wsys = DecomposedSystem(args.density, (n + 0.05) * s, halo_mode=halo_mode, tiles=tiles)
+            wr = _measure_system(wsys, min(K, 100), 5, rebuild_every, fkw)
+            weak = {"workload": "FCC rho=%.1f, %d cells/side, N=%d (~1.0e6 per GPU), %d directed pairs" % (
+                        args.density, n, wsys.pn_global, wr["pairs"]),
+                    "value": wr["pairs"] * min(K, 100) / (wr["ms_total"] * 1e-3), "unit": unit,
+                    "ms_per_step": wr["ms_total"] / min(K, 100), "scaling": "weak",
+                    "schedule": "overlap" if wr["use_overlap"] else "halo-then-force",
+                    "ms_step_overlap": wr["ms_overlap"], "ms_step_serial": wr["ms_serial"],
+                    "ms_halo_alone": wr["ms_halo"], "list_build_ms": wr["ms_build"]}
+            del wsys
+        except Exception as e:  # noqa: BLE001 -- the side block must not take the headline down
+            weak = {"error": str(e)}
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        P = int(pairs.item())
-        ms_total = float(ms.item())
+        P, ms_total = r["pairs"], r["ms_total"]
         out = {
             "metric": metric, "value": P * K / (ms_total * 1e-3), "unit": unit, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.prec == "fp64" else "f32-mixed", "data": "synthetic",
-            "config": {"workload": "synthetic FCC lattice N=%d (%d cells/side) rho=%.1f cutoff=3.0 search=3.3, "
-                                   "%d z-slabs, %d directed pairs, on-GPU list rebuild every %d steps, ghost "
-                                   "positions exchanged every step (%s)" % (
-                                       system.pn_global, n, density, world, P, rebuild_every, halo_mode),
-                       "parallelism": "z-slab x%d" % world, "halo_layers": system.slab.halo,
-                       "l2": "inputs larger than L2", "rebuild_every": rebuild_every},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "halo": {"mode": halo_mode, "schedule": "overlap" if use_overlap else "halo-then-force",
-                     "ms_step_overlap": ms_overlap, "ms_step_serial": ms_serial,
-                     "ms_halo_alone": ms_halo,
-                     "ghost_bytes_per_step_per_rank": int((system.slab.n_lo + system.slab.n_hi) * 32)},
-            "e2e": {"value": P * K / (ms_total * 1e-3), "unit": unit, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0,
-                    "note": "decomposed runs keep q,p resident; the host-buffer plugin call is the N=1 line"},
+            "config": {"workload": "BASELINE config 5: synthetic FCC lattice N=%d (%d cells/side) rho=%.1f cutoff=3.0 "
+                                   "search=3.3, %d z-slabs of %d lattice layers, %d directed pairs, on-GPU list rebuild "
+                                   "every %d steps, ghost positions exchanged every step (%s)" % (
+                                       pn5, cells5, density5, world, slab_layers, P, rebuild_every, halo_used),
+                       "parallelism": "z-slab x%d" % world, "l2": "inputs larger than L2",
+                       "rebuild_every": rebuild_every, "setup_seconds_generator_and_first_build": setup_s},
+            "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "halo": {"mode": halo_used, "schedule": sched, "ms_step_overlap": r["ms_overlap"],
+                     "ms_step_serial": r["ms_serial"], "ms_halo_alone": r["ms_halo"],
+                     "ghost_bytes_per_step_per_rank": ghost_bytes,
+                     "ordering": "device-side step counters (lj_flag_set / lj_halo_pull_sync / lj_flag_wait)"
+                                 if halo_used == "p2p" else "NCCL send/recv"},
+            "roofline": {"bound": "hbm", "achieved": bytes_rank / (r["ms_force"] * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": bytes_rank / (r["ms_force"] * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "per": "rank 0 (its slab: %d owned + %d ghost particles, %d pairs)" % (
+                             n_own, n_local - n_own, pairs_local),
+                         "kernel": "force step of one rank incl. its halo wait (k_tile_permute + lj_celltile_force x2 parts)",
+                         "algorithmic_bytes_per_launch": bytes_rank, "ms_per_launch": r["ms_force"],
+                         "list_build_ms": r["ms_build"],
+                         "amortised_step_ms": r["ms_force"] + r["ms_build"] / rebuild_every},
+            "e2e": {"value": P * K / ((ms_total + ms_h2d + ms_d2h) * 1e-3), "unit": unit,
+                    "h2d_bytes_per_step": 2 * n_local * 32 / K, "d2h_bytes_per_step": n_local * 32 / K,
+                    "ms_h2d_once": ms_h2d, "ms_d2h_once": ms_d2h, "p_checksum_rank0": checksum,
+                    "call": "per rank: pinned host q,p -> H2D once, K decomposed steps (rebuild every %d), D2H p once; "
+                            "bytes per rank, charged to the K steps" % rebuild_every},
+            "weak_scaling_1M_per_gpu": weak,
         }
+        if cpu_reference_sample is not None and not getattr(args, "no_cpu", False):
+            try:
+                c = cpu_reference_sample(20)
+                t = c["t_force"] + c["t_list"]
+                out["cpu_baseline"] = {"value": 2 * c["pairs_half"] * c["steps"] / t, "unit": unit, "cores": c["cores"],
+                                       "kind": c["kind"], "sample": c["what"],
+                                       "force_only_pairs_per_s": 2 * c["pairs_half"] * c["steps"] / c["t_force"]}
+            except Exception as e:  # noqa: BLE001
+                out["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()

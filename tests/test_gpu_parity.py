@@ -973,3 +973,46 @@ def test_float3_layout_mixed(ctx, torch, sysA, sysB, oracle, which):
     from lj_gpu_b200 import LJError
     with pytest.raises(LJError):
         ctx.force_step(qd, pd, pl, precision="fp64")              # float3 is a mixed-precision layout
+
+
+def test_force_step_parts_interior_plus_boundary_equal_one_step(ctx, torch, sysS):
+    """lj_force_step_part: INTERIOR tiles read only positions inside the list's row range (garbage in
+    the other positions does not reach them), BOUNDARY refreshes those positions and runs the rest;
+    together they are exactly one lj_force_step."""
+    from lj_gpu_b200 import LJError
+    s = sysS
+    qd, pd = s.device_arrays(torch, "aos4")
+    own = (s.pn // 2) // 4 * 4
+    pl = ctx.makepair(qd, tiles=True, rows=(0, own))
+    ref = torch.zeros_like(pd)
+    ctx.force_loop(qd, ref, pl, loop=3, variant="celltile", rows=(0, own))
+    good = qd.clone()
+    pd.zero_()
+    touched_by_interior = None
+    for _ in range(3):
+        qd[own:, :3] = 1.0e5                                  # "ghosts not here yet"
+        before = pd.clone()
+        ctx.force_step(qd, pd, pl, variant="celltile", rows=(0, own), part="interior")
+        touched_by_interior = (pd != before).any(dim=1)
+        qd.copy_(good)                                         # "the halo has arrived"
+        ctx.force_step(qd, pd, pl, variant="celltile", rows=(0, own), part="boundary")
+    assert torch.equal(pd, ref)
+    n_int = int(touched_by_interior.sum().item())
+    assert 0 < n_int < own                                     # both parts had rows
+    assert np.abs(pd.cpu().numpy()[:own, :3] - s.p[:own] * (3 / s.steps)).max() / s.scale < TOL_FP64
+    # mixed precision goes through the same two parts
+    pm, pr = torch.zeros_like(pd), torch.zeros_like(pd)
+    ctx.force_step(qd, pr, pl, variant="celltile", rows=(0, own), precision="mixed")
+    ctx.force_step(qd, pm, pl, variant="celltile", rows=(0, own), precision="mixed", part="interior")
+    ctx.force_step(qd, pm, pl, variant="celltile", rows=(0, own), precision="mixed", part="boundary")
+    assert torch.equal(pm, pr)
+    # a whole-system list has no boundary tiles; no mirror -> an error, not a silent fallback
+    full = ctx.makepair(qd, tiles=True)
+    pa, pb = torch.zeros_like(pd), torch.zeros_like(pd)
+    ctx.force_step(qd, pa, full, variant="celltile")
+    ctx.force_step(qd, pb, full, variant="celltile", part="interior")
+    ctx.force_step(qd, pb, full, variant="celltile", part="boundary")
+    assert torch.equal(pa, pb)
+    plain = ctx.makepair(qd)
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, plain, part="interior")
