@@ -100,6 +100,33 @@ def algorithmic_bytes(pn, pairs, s_vec=32, ptr_bytes=4):
     return 4 * pairs + pn * (s_vec + 2 * s_vec + 4 + ptr_bytes)
 
 
+def kernel_source_sha():
+    """sha256 over the sources of the dominant kernel: ties an ncu capture to the code it was taken from"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("lj_force_celltile.cu", "lj_celltile.cuh", "lj_tile.cuh", "lj_common.cuh"):
+        with open(os.path.join(ROOT, "lj_gpu_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def roofline_traffic(prec):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    `ncu --set full` capture -- only if that capture was taken from the kernel sources of this tree
+    (profiles/roofline_traffic.json records their hash and the commit); a stale capture is dropped."""
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        tj = json.load(open(tpath))
+        entry = tj["mixed_kernel"] if prec == "mixed" else tj
+        if tj.get("kernel_source_sha") != kernel_source_sha():
+            return None, "dropped: profiles/roofline_traffic.json was captured at %s from other kernel sources (%s != %s)" % (
+                tj.get("git_head", "?"), tj.get("kernel_source_sha", "none"), kernel_source_sha())
+        return entry.get("dram_bytes_per_launch"), "%s, captured at commit %s (%s)" % (
+            entry.get("kernel"), tj.get("git_head"), tj.get("source"))
+    except Exception as e:  # noqa: BLE001
+        return None, "no capture: %s" % e
+
+
 # ----------------------------------------------------------------------------- reference arm
 def cpu_reference_sample(steps_force=20, L=50.0):
     """The real reference on the host: one makepair()+sortpair() and `steps_force` x
@@ -134,6 +161,71 @@ def cpu_reference_sample(steps_force=20, L=50.0):
                 steps=steps_force, cores=1,
                 what="oracle/lj_oracle.c brute-force makepair once + %d x force_sorted, rho=1.0 L=50 "
                      "N=%d, 1 thread" % (steps_force, len(q)))
+
+
+def cpu_restatement_config_c(q, nop, ptr, lst):
+    """SURVEY 8(d) / BASELINE.md 4.4: the CPU RESTATEMENT (oracle/lj_oracle.c -- NOT the reference, which
+    cannot run at this size: static N = 400000, O(N^2) makepair) on the bench's own config: one full-list
+    gather step on 1 core and on all host cores (OpenMP), and its O(N) cell-list build on 1 core."""
+    import numpy as np
+    from oracle import ljoracle as lo
+    o = lo.Oracle()
+    nthreads = os.cpu_count() or 1
+    out = {"kind": "port", "what": "oracle/lj_oracle.c full-list gather (cuda/kernel.cuh:36-65 arithmetic) + O(N) cell-list "
+                                   "makepair on the bench config N=%d, labelled NOT the reference" % len(q), "nproc": nthreads}
+    P = len(lst)
+    p = np.zeros_like(q)
+    for cores in (1, nthreads):
+        o.set_num_threads(cores)
+        o.force_gather(q, p, nop, ptr, lst, steps=1)          # warm
+        t0 = time.perf_counter()
+        o.force_gather(q, p, nop, ptr, lst, steps=2)
+        t = (time.perf_counter() - t0) / 2
+        out["force_step_s_%s" % ("1core" if cores == 1 else "allcores")] = t
+        out["force_pairs_per_s_%s" % ("1core" if cores == 1 else "allcores")] = P / t
+    o.set_num_threads(1)
+    t0 = time.perf_counter()
+    o.makepair(q, full=True, cap=P + 1024)
+    out["list_build_s_1core"] = time.perf_counter() - t0
+    amort = out["force_step_s_allcores"] + out["list_build_s_1core"] / REBUILD_EVERY
+    out["amortised_pairs_per_s_allcores_force_1core_build"] = P / amort
+    o.set_num_threads(nthreads)
+    return out
+
+
+def repo_on_reference_configs(ctx, torch, np, init_fcc, stream):
+    """This repository's kernels on the reference's own two configurations (A: rho=0.5, B: rho=1.0,
+    L=50), on lists whose rows were shuffled like the reference's random_shfl(): seconds per LOOP=100
+    steps, kernel only -- the number cuda/force_cuda.cu:341 prints."""
+    rows = []
+    for rho in (0.5, 1.0):
+        q = init_fcc(rho, 50.0)
+        q4 = np.zeros((len(q), 4)); q4[:, :3] = q
+        qd = torch.from_numpy(q4).cuda(); pd = torch.zeros_like(qd)
+        best = None
+        for name, build, fkw in (("per-row gather, 8 lanes per row (shuffled rows)", dict(), dict(variant="subwarp", group=8)),
+                                 ("warp per row = warp_unroll mapping (shuffled rows)", dict(), dict(variant="warp", group=32)),
+                                 ("cell-tile mirror (library-built list)", dict(tiles=True), dict(variant="celltile"))):
+            pl = ctx.makepair(qd, **build)
+            if not build:
+                ctx.random_shfl(pl, seed=10)
+            for graph in (False, True):
+                ctx.force_loop(qd, pd, pl, loop=100, use_graph=graph, **fkw)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(5):
+                    ctx.force_loop(qd, pd, pl, loop=100, use_graph=graph, **fkw)
+                a1.record(stream)
+                torch.cuda.synchronize()
+                sec = a0.elapsed_time(a1) / 5 * 1e-3
+                if best is None or sec < best["seconds_per_100_steps"]:
+                    best = {"kernel": name, "cuda_graph": graph, "seconds_per_100_steps": sec,
+                            "pairs_per_s": pl.number_of_pairs * 100 / sec}
+            del pl
+        rows.append({"density": rho, "N": len(q), **best})
+        del qd, pd
+    return rows
 
 
 def run_reference(args):
@@ -201,6 +293,10 @@ def run_cuda(args):
         use_tiles = "wide"   # LJ_LIST_TILES_WIDE: the tile size the mixed kernel prefers
     pl = ctx.makepair(qd, pointer64=False, clusters=use_cl, tiles=use_tiles)
     P = pl.number_of_pairs
+    list_host = None
+    if not args.no_cpu:   # the CPU restatement leg runs on the SAME list (row order is unspecified by contract)
+        list_host = (pl.number_of_partners.cpu().numpy(), pl.pointer.cpu().numpy().astype(np.int64),
+                     pl.sorted_list[:P].cpu().numpy())
     fkw = dict(variant=args.variant, group=args.group, precision=args.prec,
                threads_per_block=args.threads_per_block)
 
@@ -324,19 +420,66 @@ def run_cuda(args):
     except Exception as e:  # noqa: BLE001 -- the side measurement must not take the headline down
         ref_cfg = {"error": str(e)}
 
+    # ---- the reference's OWN CUDA kernels recompiled for sm_100 (baseline/_ref), on this GPU, next to this
+    #      repository's kernels on the same two configurations
+    ref_gpu = None
+    if not args.no_ref_gpu:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import run_reference_gpu as rrg
+            ref_gpu = rrg.reference_gpu((0.5, 1.0), timeout=300.0)
+            mine = repo_on_reference_configs(ctx, torch, np, init_fcc, stream)
+            for row in ref_gpu["rows"]:
+                for m_ in mine:
+                    if m_["density"] == row.get("density") and "best_seconds_per_100_steps" in row:
+                        row["this_repo"] = m_
+                        row["this_repo_faster_than_best_reference_kernel"] = \
+                            m_["seconds_per_100_steps"] < row["best_seconds_per_100_steps"]
+                        row["speedup_vs_best_reference_kernel"] = row["best_seconds_per_100_steps"] / m_["seconds_per_100_steps"]
+        except Exception as e:  # noqa: BLE001 -- the side measurement must not take the headline down
+            ref_gpu = {"error": str(e)}
+
+    # ---- BASELINE config 5 on ONE GPU (N = 131,072,000): the denominator of the strong-scaling runs
+    cfg5 = None
+    if not args.no_config5:
+        try:
+            del qd, pd, pl
+            torch.cuda.empty_cache()
+            from lj_gpu_b200.decomp import lattice_spacing
+            t0 = time.perf_counter()
+            q5 = init_fcc(0.8, (320 + 0.05) * lattice_spacing(0.8))
+            n5 = len(q5)
+            q54 = np.zeros((n5, 4)); q54[:, :3] = q5
+            del q5
+            q5d = torch.from_numpy(q54).cuda(); del q54
+            p5d = torch.zeros_like(q5d)
+            pl5 = ctx.makepair(q5d, pointer64=True, tiles=True)
+            setup = time.perf_counter() - t0
+            ctx.force_loop(q5d, p5d, pl5, loop=2, **fkw)
+            torch.cuda.synchronize()
+            c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            c0.record(stream)
+            ctx.force_loop(q5d, p5d, pl5, loop=10, **fkw)
+            c1.record(stream)
+            ctx.rebuild(q5d, pl5)
+            c2.record(stream)
+            torch.cuda.synchronize()
+            f5, b5 = c0.elapsed_time(c1) / 10, c1.elapsed_time(c2)
+            cfg5 = {"workload": "BASELINE config 5 on one GPU: FCC rho=0.8, 320 cells/side, N=%d, %d directed pairs, int64 pointer[]" % (n5, pl5.number_of_pairs),
+                    "ms_per_force_step": f5, "list_build_ms": b5, "amortised_step_ms": f5 + b5 / REBUILD_EVERY,
+                    "pairs_per_s_amortised": pl5.number_of_pairs / ((f5 + b5 / REBUILD_EVERY) * 1e-3),
+                    "roofline_frac_force": algorithmic_bytes(n5, pl5.number_of_pairs, 32, 8) / (f5 * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                    "setup_seconds_generator_and_first_build": setup,
+                    "note": "strong-scaling efficiency of `bench.py --gpus N` = this amortised_step_ms / (N * its ms_per_step)"}
+            del q5d, p5d, pl5
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            cfg5 = {"error": str(e)}
+
     peak, peak_src = measured_peak_gbs()
     bytes_force = algorithmic_bytes(pn, P)
     achieved = bytes_force / (ms_force * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_launch")
-            if args.prec == "mixed":  # the mixed kernel has its own capture
-                traffic = tj.get("mixed_kernel", {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = roofline_traffic(args.prec)
 
     out = {
         "metric": METRIC, "value": P * K / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K,
@@ -356,7 +499,8 @@ def run_cuda(args):
                 "call": "lj_measure(): pinned host q,p -> H2D -> GPU list build -> K steps (rebuild "
                         "every 20) -> D2H p", "p_checksum": checksum},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "kernel": ("force step (k_tile_permute + lj_celltile_force, %s)" % args.prec if use_tiles
                                 else "force step (lj_gather_*)"),
                      "algorithmic_bytes_per_launch": bytes_force,
@@ -371,6 +515,8 @@ def run_cuda(args):
         mixed["pairs_per_s_amortised"] = P / (mixed["amortised_step_ms"] * 1e-3)
     out["mixed_precision"] = mixed
     out["reference_config"] = ref_cfg
+    out["reference_gpu"] = ref_gpu
+    out["config5_single_gpu"] = cfg5
     if not args.no_cpu:
         r = cpu_reference_sample(20)
         t = r["t_force"] + r["t_list"]
@@ -379,6 +525,10 @@ def run_cuda(args):
             "kind": r["kind"], "sample": r["what"],
             "force_only_pairs_per_s": 2 * r["pairs_half"] * r["steps"] / r["t_force"],
             "ms_per_force_step": 1e3 * r["t_force"] / r["steps"], "s_per_list_build": r["t_list"]}
+        try:   # the restatement on the bench's own configuration (1 core and all cores)
+            out["cpu_baseline"]["restatement_config_c"] = cpu_restatement_config_c(q, *list_host)
+        except Exception as e:  # noqa: BLE001
+            out["cpu_baseline"]["restatement_config_c"] = {"error": str(e)}
     print(json.dumps(out), flush=True)
     ctx.close()
 
@@ -396,6 +546,8 @@ def main():
     ap.add_argument("--prec", default="fp64", choices=["fp64", "mixed"])
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference_gpu block (baseline/_ref binaries)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config5_single_gpu side block (N=131M on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -196,7 +196,10 @@ class DecomposedSystem:
         # tiles: also build the cell-tile mirror for the owned rows: both schedules then run the
         # shared-memory kernel (the overlapped one as lj_force_step_part INTERIOR / BOUNDARY)
         self.tiles = tiles
-        self.pl = self.ctx.makepair(self.q, rows=(0, self.slab.n_own), search_len=search_len, tiles=tiles)
+        # int32 pointer[] holds 2^32 - 1 list entries: 64-bit offsets for slabs beyond ~14 M particles
+        # (the reference's int32 offsets overflow at BASELINE config 4 already)
+        self.pl = self.ctx.makepair(self.q, rows=(0, self.slab.n_own), search_len=search_len, tiles=tiles,
+                                    pointer64=self.slab.n_own * 160 > 2 ** 31)
         self.search_len = search_len
         self.pairs_local = self.pl.number_of_pairs
         self.peer_ptr, self.peer_flags = {}, {}
