@@ -698,7 +698,7 @@ k_tile_meta(int64_t pn, const int32_t* __restrict__ order, const int32_t* __rest
 __global__ void __launch_bounds__(128)
 k_tile_table(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ off,
              lj_tile_geom* __restrict__ tg, uint2* __restrict__ ytab, uint4* __restrict__ ttab,
-             int32_t* __restrict__ col_flag) {
+             int32_t* __restrict__ col_flag, int phase) {  // phase 0: y-row table only, 1: tile table only, 2: both
   const lj_tile_geom g = *tg;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.ntiles) return;
@@ -710,17 +710,20 @@ k_tile_table(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict
   for (int dz = 0; dz < kTileYPencils; dz++) {
     uint32_t st, len;
     tile_pencil_range(cell_start, g.nx, g.ny, g.nz, cy, cz, rxa, rxb, dz, st, len);
-    ytab[(size_t)t * kTileYTab + dz] = make_uint2(st, base);
+    if (phase != 1) ytab[(size_t)t * kTileYTab + dz] = make_uint2(st, base);
     if (dz == 2) { st2 = st; pb2 = base; }
     base += len;
   }
-  ytab[(size_t)t * kTileYTab + 5] = make_uint2(0u, base);
+  if (phase != 1) {
+    ytab[(size_t)t * kTileYTab + 5] = make_uint2(0u, base);
+    atomicMax(&tg->max_yrow, (int)base);
+  }
+  if (phase == 0) return;
   const int rowc = (cz * g.ny + cy) * g.nx;
   const uint32_t s0 = cell_start[rowc + xa], s1 = cell_start[rowc + xb + 1];
   ttab[(size_t)t * kTileTTab] = make_uint4(s0, s1 - s0, off[s0], off[s1] - off[s0]);
   ttab[(size_t)t * kTileTTab + 1] = make_uint4(pb2 + (s0 - st2), 0u, 0u, 0u);  // + 2 * cap_y at run time
   atomicMax(&tg->max_rows, (int)(s1 - s0));
-  atomicMax(&tg->max_yrow, (int)base);
   atomicMax(&tg->max_units, (int)(off[s1] - off[s0]));
   if (off[s1] != off[s0]) col_flag[t / g.ny] = 1;  // column (cz * ntx + tx) has work
 }
@@ -930,6 +933,310 @@ k_tile_zflag(int64_t pn, int64_t r0, int64_t r1, const int32_t* __restrict__ cel
   zflag[cell_of[i] / (tg->nx * tg->ny)] = 1;
 }
 
+// ====================================================================== tile engine ======
+// ONE search per build (round 2).  Round 1 searched twice: k_search_cluster counted (0.75 ms at
+// N = 1M) and k_tile_fill searched again to write the list and its mirror (1.68 ms).  Here the
+// COUNT pass runs per tile with the tile's 25-pencil region staged in shared memory, and records
+// for every row and pencil WHICH candidates hit as a 64-bit mask (bit b = record b of the row's
+// window = the five x-cells around its own cell).  After the scans, k_tile_replay walks the masks
+// and writes both lists without looking at a single position.  Membership is decided by the same
+// tests as k_search (FP32 on origin-shifted coordinates, the exact FP64 fma chain inside the error
+// band), rows are emitted in the same order as k_tile_fill did (pencil dz-major, cell order within).
+constexpr int kTeThreads = 192;  // six warps: 48 rows per round of row pairs (tiles hold ~40, ~56 wide)
+constexpr int kTeLanes = 8;      // lanes per row (pair), four per warp
+constexpr int kTeRowCap = 256;   // replay: entries of a row staged in shared memory (longer rows are written directly)
+
+struct te_pencil { uint32_t st, base, len; int rowc; };  // cell-order start, region-local index of its first record,
+                                                          // records, first cell of the (y,z) row (-1: outside the grid)
+
+// pencil p = dz * 5 + dy of tile t = (tx, cy, cz), from the y-row table (the y-rows cy-2 .. cy+2 of a column
+// are the table rows t-2 .. t+2); window tables: xoff[p][k] = first record (relative to the pencil's first
+// record) of region x-cell k, k = 0 .. ncx
+__device__ __forceinline__ void te_setup(const lj_tile_geom& g, int t, uint32_t cap_y, const uint32_t* __restrict__ cell_start,
+                                         const uint2* __restrict__ ytab, te_pencil* __restrict__ pen, int* __restrict__ xoff,
+                                         int ncx1, int& ncx, uint32_t& s0, uint32_t& ns) {
+  const int cy = t % g.ny, tx = (t / g.ny) % g.ntx, cz = t / (g.ny * g.ntx);
+  int xa, xb, rxa, rxb;
+  tile_x_extent(tx * g.tc, g.tc, g.nx, xa, xb, rxa, rxb);
+  ncx = rxb - rxa + 1;
+  if (threadIdx.x < 25) {
+    const int p = threadIdx.x, dz = p / 5, dy = p % 5;
+    const int Y = cy + dy - 2, z = cz + dz - 2;
+    te_pencil e;
+    e.st = 0; e.base = 0; e.len = 0;
+    e.rowc = (Y < 0 || Y >= g.ny || z < 0 || z >= g.nz) ? -1 : (z * g.ny + Y) * g.nx;
+    if (Y >= 0 && Y < g.ny) {
+      const uint2* row = ytab + (size_t)(t + dy - 2) * kTileYTab;
+      const uint2 a = row[dz], nx = row[dz + 1];   // entry 5 = {0, length of the y-row}
+      e.st = a.x; e.base = (uint32_t)dy * cap_y + a.y; e.len = nx.y - a.y;
+    }
+    pen[p] = e;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 25 * ncx1; idx += blockDim.x) {
+    const int p = idx / ncx1, k = idx - p * ncx1;
+    const te_pencil e = pen[p];
+    xoff[idx] = (e.rowc >= 0 && k <= ncx) ? (int)(cell_start[e.rowc + rxa + k] - e.st) : 0;
+  }
+  const int rowc = (cz * g.ny + cy) * g.nx;
+  s0 = cell_start[rowc + xa];
+  ns = cell_start[rowc + xb + 1] - s0;
+  __syncthreads();
+}
+
+// region x-cell of the tile row with offset `rel` into the centre pencil
+__device__ __forceinline__ int te_row_cell(const int* __restrict__ xoff_c, int ncx, uint32_t rel) {
+  int kx = 0;
+  while (kx + 1 < ncx && (uint32_t)xoff_c[kx + 1] <= rel) kx++;
+  return kx;
+}
+
+// COUNT pass.  One CTA per tile.  Eight lanes work on a PAIR of consecutive rows (a, b): each lane
+// loads a candidate record once and tests it against both rows (they sit in the same or in
+// neighbouring cells, so they share one window: the x-cells min(kx) - 2 .. max(kx) + 2).  The loop
+// body is branch-free: a candidate with r2 < lo is a hit (the row's own record is removed afterwards:
+// any other record that close is a neighbour), candidates inside the FP32 error band [lo, hi) of the
+// search radius are collected in a bit field and decided exactly after the loop (about one in 5000).
+// Mask layout: byte lg of mask[s][p] belongs to lane lg, its bit `it` = window record it * 8 + lg.
+// Outputs per row (cell-order slot s): the 25 masks, tl_order[s], tl_cnt[s], tl_units[s] and the
+// public number_of_partners[i].  status bit 16: a window holds more than 64 records (cells too
+// crowded for the masks) -- the caller falls back to the round-1 engine.
+__global__ void __launch_bounds__(kTeThreads)
+k_tile_count(int64_t pn, int64_t r0, int64_t r1, const grid_ext* __restrict__ ge, const lj_tile_geom* __restrict__ tgp,
+             const uint32_t* __restrict__ cell_start, const uint2* __restrict__ ytab,
+             const double4* __restrict__ sorted_pos, const float4* __restrict__ sorted_pos32, double sl2,
+             int ncx1, int32_t* __restrict__ nop, int32_t* __restrict__ tl_order, int32_t* __restrict__ tl_cnt,
+             uint32_t* __restrict__ tl_units, unsigned char* __restrict__ masks, lj_list_totals* __restrict__ tot) {
+  extern __shared__ __align__(16) unsigned char te_smem[];
+  const lj_tile_geom g = *tgp;
+  const uint32_t cap_y = (uint32_t)((g.max_yrow + 8 + 1) & ~1);
+  float4* reg = reinterpret_cast<float4*>(te_smem);
+  te_pencil* pen = reinterpret_cast<te_pencil*>(reg + 5 * cap_y);
+  int* xoff = reinterpret_cast<int*>(pen + 25);
+  __shared__ int blk_max;
+  if (threadIdx.x == 0) blk_max = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) tl_units[pn] = 0u;  // sentinel: the scan then yields off[pn] = total
+  int ncx;
+  uint32_t s0, ns;
+  te_setup(g, blockIdx.x, cap_y, cell_start, ytab, pen, xoff, ncx1, ncx, s0, ns);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (ns == 0) return;  // (uniform) an empty tile
+  // stage the region: warp w copies pencils w, w + 6, ...; a lane has ~10 independent loads in flight
+  for (int p = warp; p < 25; p += kTeThreads / 32) {
+    const te_pencil e = pen[p];
+    float4* dst = reg + e.base;
+    for (uint32_t k = lane; k < e.len; k += 32) dst[k] = sorted_pos32[e.st + k];
+  }
+  __syncthreads();
+  const float margin = ge->margin, sl2f = ge->sl2f;
+  const float lo_f = sl2f - margin, hi_f = sl2f + margin;
+  const int lg = lane % kTeLanes, gi = lane / kTeLanes;
+  const unsigned gmask = 0xffu << (gi * kTeLanes);
+  const te_pencil pc = pen[12];  // the centre pencil holds the tile's rows
+  const int* xoff_c = xoff + 12 * ncx1;
+  int my_max = 0;
+  for (uint32_t rb = warp * 8; rb < ns; rb += (kTeThreads / 32) * 8) {
+    const uint32_t ra = rb + 2 * gi, rbb = ra + 1;
+    const bool va = ra < ns, vb = rbb < ns;
+    const uint32_t sa = s0 + (va ? ra : 0u), sb = s0 + (vb ? rbb : (va ? ra : 0u));
+    const uint32_t rela = sa - pc.st, relb = sb - pc.st;
+    const float4 ma = reg[pc.base + rela], mb = reg[pc.base + relb];
+    const int ia = __float_as_int(ma.w), ib = __float_as_int(mb.w);
+    const bool in_a = va && ia >= r0 && ia < r1, in_b = vb && ib >= r0 && ib < r1;
+    const int kxa = te_row_cell(xoff_c, ncx, rela), kxb = te_row_cell(xoff_c, ncx, relb);
+    const int k_lo = max(min(kxa, kxb) - 2, 0), k_hi = min(max(kxa, kxb) + 2, ncx - 1);
+    const int* xlo = xoff + k_lo;
+    const int* xhi = xoff + k_hi + 1;
+    unsigned char* mpa = masks + (size_t)sa * 200 + lg;   // 25 masks of 8 bytes per row
+    unsigned char* mpb = masks + (size_t)sb * 200 + lg;
+    // the rows' own records (centre pencil): window record -> (lane, bit)
+    const int wc = xlo[12 * ncx1];
+    const int selfa = (int)rela - wc, selfb = (int)relb - wc;
+    int cnta = 0, cntb = 0;
+#pragma unroll 1
+    for (int p = 0; p < 25; p++) {
+      const te_pencil e = pen[p];
+      const int w0 = xlo[p * ncx1];
+      int nw = ((in_a || in_b) && e.rowc >= 0) ? xhi[p * ncx1] - w0 : 0;
+      if (nw > 64) { if (lg == 0) atomicOr(&tot->overflow, 16); nw = 64; }
+      const int iters = __reduce_max_sync(0xffffffffu, (nw + kTeLanes - 1) / kTeLanes);
+      const float4* __restrict__ cand = reg + (e.base + (uint32_t)w0 + (uint32_t)lg);
+      unsigned ha = 0, hb = 0, band = 0;  // band: bit it = row a, bit 8 + it = row b
+      unsigned bit = 1u;
+      int left = nw - lg;  // this lane's candidates: idx = lg, lg + 8, ... < nw
+#pragma unroll 1
+      for (int it = 0; it < iters; it++, bit <<= 1, left -= kTeLanes) {
+        const float4 c = cand[left > 0 ? it * kTeLanes : 0];
+        const unsigned b1 = left > 0 ? bit : 0u;
+        const float ax = ma.x - c.x, ay = ma.y - c.y, az = ma.z - c.z;
+        const float bx = mb.x - c.x, by = mb.y - c.y, bz = mb.z - c.z;
+        const float r2a = fmaf(az, az, fmaf(ay, ay, ax * ax));
+        const float r2b = fmaf(bz, bz, fmaf(by, by, bx * bx));
+        if (r2a < lo_f) ha |= b1;
+        if (r2b < lo_f) hb |= b1;
+        if (r2a >= lo_f && r2a < hi_f) band |= b1;
+        if (r2b >= lo_f && r2b < hi_f) band |= b1 << 8;
+      }
+      if (p == 12) {  // a row is not its own neighbour
+        if ((selfa & 7) == lg) ha &= ~(1u << (selfa >> 3));
+        if ((selfb & 7) == lg) hb &= ~(1u << (selfb >> 3));
+      }
+      if (!in_a) { ha = 0; band &= ~0xffu; }
+      if (!in_b) { hb = 0; band &= 0xffu; }
+      if (__any_sync(0xffffffffu, band != 0)) {  // rare: the exact FP64 test
+        while (band) {
+          const int k = __ffs((int)band) - 1;
+          band &= band - 1;
+          const int it = k & 7;
+          const uint32_t m = e.st + (uint32_t)(w0 + it * kTeLanes + lg), sr = k < 8 ? sa : sb;
+          const double4 cj = sorted_pos[m], md = sorted_pos[sr];
+          const double dx = md.x - cj.x, dy = md.y - cj.y, dz = md.z - cj.z;
+          if (m != sr && fma(dz, dz, fma(dy, dy, dx * dx)) < sl2) { if (k < 8) ha |= 1u << it; else hb |= 1u << it; }
+        }
+      }
+      cnta += __popc(ha);
+      cntb += __popc(hb);
+      if (in_a) mpa[p * 8] = (unsigned char)ha;
+      if (in_b) mpb[p * 8] = (unsigned char)hb;
+    }
+#pragma unroll
+    for (int d = 1; d < kTeLanes; d <<= 1) {
+      cnta += __shfl_xor_sync(gmask, cnta, d, kTeLanes);
+      cntb += __shfl_xor_sync(gmask, cntb, d, kTeLanes);
+    }
+    if (lg == 0 && va) {
+      tl_order[sa] = ia; tl_cnt[sa] = cnta; tl_units[sa] = (uint32_t)(cnta + 7) >> 3; nop[ia] = cnta;
+      my_max = max(my_max, cnta);
+    }
+    if (lg == 1 && vb) {
+      tl_order[sb] = ib; tl_cnt[sb] = cntb; tl_units[sb] = (uint32_t)(cntb + 7) >> 3; nop[ib] = cntb;
+      my_max = max(my_max, cntb);
+    }
+  }
+  if (my_max > 0) atomicMax(&blk_max, my_max);
+  __syncthreads();
+  if (threadIdx.x == 0 && blk_max > *(volatile int*)&tot->max_np) atomicMax(&tot->max_np, blk_max);
+}
+
+// 8 x 8 bit-matrix transpose (Hacker's Delight 7-3): mask bit lg * 8 + it -> bit it * 8 + lg = window record
+__device__ __forceinline__ unsigned long long te_transpose8(unsigned long long x) {
+  unsigned long long t;
+  t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull; x = x ^ t ^ (t << 7);
+  t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
+  t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
+  return x;
+}
+
+// REPLAY pass: masks -> mirror entries (16-bit region-local indices) and the public list (original
+// indices), both at the offsets the scans produced.  No positions are read.  A row's entries are
+// expanded into shared memory (each lane its pencils, scattered) and written out by the row's eight
+// lanes in runs of eight consecutive entries: 16 contiguous bytes of the mirror, 32 of the list.
+template <bool PTR64>
+__global__ void __launch_bounds__(kTeThreads)
+k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* __restrict__ cell_start,
+              const uint2* __restrict__ ytab, int ncx1, const int32_t* __restrict__ tl_order,
+              const int32_t* __restrict__ tl_cnt, const uint32_t* __restrict__ tl_off,
+              const unsigned long long* __restrict__ masks, uint16_t* __restrict__ tl_list,
+              const void* __restrict__ pointer, int32_t* __restrict__ list, int64_t capacity,
+              lj_list_totals* __restrict__ tot) {
+  extern __shared__ __align__(16) unsigned char te_smem[];
+  const lj_tile_geom g = *tgp;
+  const uint32_t cap_y = (uint32_t)((g.max_yrow + 8 + 1) & ~1);
+  te_pencil* pen = reinterpret_cast<te_pencil*>(te_smem);
+  int* xoff = reinterpret_cast<int*>(pen + 25);
+  // per row group: kTeRowCap x {cell-order index of j (4 B)} then kTeRowCap x {region-local index (2 B)}
+  unsigned char* stage = reinterpret_cast<unsigned char*>(xoff + 25 * ncx1);
+  int ncx;
+  uint32_t s0, ns;
+  te_setup(g, blockIdx.x, cap_y, cell_start, ytab, pen, xoff, ncx1, ncx, s0, ns);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lg = lane % kTeLanes, gi = lane / kTeLanes;
+  const unsigned gmask = 0xffu << (gi * kTeLanes);
+  const te_pencil pc = pen[12];
+  const int* xoff_c = xoff + 12 * ncx1;
+  const uint16_t dummy = (uint16_t)(cap_y - 1);  // last record of the dy = 0 ring slot: far-away point
+  uint32_t* sm_m = reinterpret_cast<uint32_t*>(stage + (size_t)(warp * 4 + gi) * kTeRowCap * 6);
+  uint16_t* sm_l = reinterpret_cast<uint16_t*>(sm_m + kTeRowCap);
+  for (uint32_t rb = warp * 4; rb < ns; rb += (kTeThreads / 32) * 4) {
+    const uint32_t r = rb + gi;
+    const bool valid = r < ns;
+    const uint32_t s = s0 + (valid ? r : 0u);
+    const int want = valid ? tl_cnt[s] : 0;
+    if (want == 0) continue;  // (whole groups: the eight lanes of a row agree)
+    // the window of the COUNT pass: shared with the other row of the pair (2k, 2k + 1)
+    const uint32_t rp = (r ^ 1u) < ns ? (r ^ 1u) : r;
+    const int kx = te_row_cell(xoff_c, ncx, s - pc.st);
+    const int kxp = te_row_cell(xoff_c, ncx, s0 + rp - pc.st);
+    const int* xlo = xoff + max(min(kx, kxp) - 2, 0);
+    const size_t base = (size_t)tl_off[s] * 8;
+    const int i = tl_order[s];
+    const int64_t pbase = row_offset<PTR64>(pointer, i);
+    bool pub = true;
+    if (pbase + want > capacity) {
+      if (lg == 0) atomicOr(&tot->overflow, 1);
+      pub = false;
+    }
+    const bool staged = want <= kTeRowCap;
+    // lane lg owns pencils lg, lg + 8, lg + 16 (and 24 for lg = 0); entries are emitted in pencil order
+    unsigned long long mk[4];
+    int before = 0;  // entries of all earlier pencils
+    int off[4];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      const int p = q4 * kTeLanes + lg;
+      mk[q4] = p < 25 ? te_transpose8(masks[(size_t)s * 25 + p]) : 0ull;
+      const int c = __popcll(mk[q4]);
+      int inc = c;  // inclusive scan over the eight lanes of the row
+#pragma unroll
+      for (int d = 1; d < kTeLanes; d <<= 1) {
+        const int v = __shfl_up_sync(gmask, inc, d, kTeLanes);
+        if (lg >= d) inc += v;
+      }
+      off[q4] = before + inc - c;
+      before += __shfl_sync(gmask, inc, kTeLanes - 1, kTeLanes);
+    }
+    if (before != want) { if (lg == 0) atomicOr(&tot->overflow, 8); continue; }  // cannot happen
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      const int p = q4 * kTeLanes + lg;
+      if (p >= 25) continue;
+      const te_pencil e = pen[p];
+      const int w0 = xlo[p * ncx1];
+      const uint32_t lbase = e.base + (uint32_t)w0, mbase = e.st + (uint32_t)w0;
+      int o = off[q4];
+      // the two 32-bit halves separately: windows rarely hold more than 32 records, and 32-bit
+      // find-first-set / clear-lowest are one instruction each where the 64-bit forms are four
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        unsigned m = half ? (unsigned)(mk[q4] >> 32) : (unsigned)mk[q4];
+        const uint32_t lb = lbase + 32u * half, mb = mbase + 32u * half;
+        while (m) {
+          const int b = __ffs((int)m) - 1;
+          m &= m - 1;
+          if (staged) { sm_m[o] = mb + b; sm_l[o] = (uint16_t)(lb + b); }
+          else {
+            tl_list[base + o] = (uint16_t)(lb + b);
+            if (pub) list[pbase + o] = tl_order[mb + b];
+          }
+          o++;
+        }
+      }
+    }
+    const int padded = ((want + 7) >> 3) << 3;
+    if (staged) {
+      __syncwarp(gmask);
+      for (int k = lg; k < padded; k += kTeLanes) {
+        const bool real = k < want;
+        tl_list[base + k] = real ? sm_l[k] : dummy;
+        if (pub && real) list[pbase + k] = tl_order[sm_m[k]];
+      }
+      __syncwarp(gmask);
+    } else {
+      for (int k = want + lg; k < padded; k += kTeLanes) tl_list[base + k] = dummy;
+    }
+  }
+}
+
 int64_t blocks_for(int64_t n, int tb) { return (n + tb - 1) / tb; }
 
 }  // namespace
@@ -987,8 +1294,10 @@ static int cluster_fill(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, boo
 
 // *deferred (in: the caller would like to run the FILL pass itself; out: it has to): the COUNT pass
 // and the scans are done, sorted_list is still unwritten.
+// bounding box -> cell grid (on the device) -> counting sort of the particles by cell -> positions
+// in cell order (double4 for the exact test, origin-shifted float4 for the pre-filter)
 template <int LAYOUT>
-static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool* deferred) {
+static int bin_particles(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) {
   const int64_t pn = a->pn;
   int rc = lj_scratch_reserve(ctx, pn, st);
   if (rc) return rc;
@@ -997,9 +1306,6 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, 
   float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
   const int* ncell_dev = &ge->ncell1;  // histogram + sentinel
   const int64_t cells = ctx->scratch_cells;
-  int64_t r0 = a->row_begin, r1 = a->row_end;
-  if (r0 == 0 && r1 == 0) r1 = pn;
-
   rc = lj_bbox_launch(ctx, a->q, LAYOUT, pn, a->plane_stride, ctx->totals, st);
   if (rc) return rc;
   k_grid_setup<<<1, 1, 0, st>>>(bb, a->search_len, cells, ge);
@@ -1025,6 +1331,22 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, 
       a->q, pn, a->plane_stride, ge, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->sorted_tmp,
       ctx->sorted_pos, sorted_pos32);
   LJ_LAUNCHED(ctx);
+  ctx->tl_valid = false;  // the cell-sort scratch and any mirror derived from it are rebuilt from here
+  ctx->graph_loop = -1;   // ... and a cached CUDA graph may replay the kernel that ran on the old mirror
+  return LJ_OK;
+}
+
+// *deferred (in: the caller would like to run the FILL pass itself; out: it has to): the COUNT pass
+// and the scans are done, sorted_list is still unwritten.  binned: bin_particles() has already run.
+template <int LAYOUT>
+static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool* deferred, bool binned = false) {
+  const int64_t pn = a->pn;
+  int rc = LJ_OK;
+  if (!binned && (rc = bin_particles<LAYOUT>(ctx, a, st))) return rc;
+  grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
+  float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
+  int64_t r0 = a->row_begin, r1 = a->row_end;
+  if (r0 == 0 && r1 == 0) r1 = pn;
 
   const double sl2 = a->search_len * a->search_len;
   if (r0 > 0 || r1 < pn) {  // rows outside the range stay empty
@@ -1033,8 +1355,6 @@ static int build_list_impl(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, 
   }
   const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
   const uint32_t* nop_u = reinterpret_cast<const uint32_t*>(a->number_of_partners);
-  ctx->tl_valid = false;  // the cell-sort scratch and any mirror derived from it are rebuilt below
-  ctx->graph_loop = -1;   // ... and a cached CUDA graph may replay the kernel that ran on the old mirror
   // any list these arrays were mirrored by is stale from here on
   if (ctx->cl_valid && (ctx->cl_id_list == a->sorted_list || ctx->cl_id_nop == a->number_of_partners ||
                         ctx->cl_id_ptr == a->pointer))
@@ -1266,7 +1586,7 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
   }
   LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_cols, 0, sizeof(int32_t) * (size_t)ncols_all, st));
   k_tile_table<<<(unsigned)blocks_for(g.ntiles, 128), 128, 0, st>>>(ctx->tl_cell_start, ctx->tl_off,
-                                                                     ctx->tl_geom, ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols);
+                                                                     ctx->tl_geom, ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols, 2);
   LJ_LAUNCHED(ctx);
   k_tile_cols<<<1, 32, 0, st>>>(ncols_all, ctx->tl_cols, ctx->tl_geom);
   LJ_LAUNCHED(ctx);
@@ -1297,6 +1617,183 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
   // too dense for 16-bit indices or for the shared-memory rings: no mirror, the per-row kernels serve
   if (5 * lj_celltile_cap_y(g) >= 65536 ||
       kTileMinYSlots * lj_celltile_yslot_bytes(g) + kTileMinLSlots * lj_celltile_lslot_bytes(g) > kTileSmemBudget)
+    return LJ_OK;
+  ctx->tl_g = g;
+  ctx->tl_valid = true;
+  ctx->tl_id_list = a->sorted_list; ctx->tl_id_nop = a->number_of_partners; ctx->tl_id_ptr = a->pointer;
+  ctx->tl_pn = pn; ctx->tl_r0 = r0; ctx->tl_r1 = r1;
+  ctx->graph_loop = -1;  // the geometry is baked into the launch parameters
+  return LJ_OK;
+}
+
+// ------------------------------------------------------------------ tile engine: host
+// lj_build_list with LJ_LIST_TILES on a full list: binning -> tile geometry -> k_tile_count (the ONE
+// search, masks) -> scans (pointer[], mirror offsets) -> tables -> k_tile_replay (both lists).
+// *done = false: the engine does not apply to this system (cells too crowded for the 64-bit window
+// masks, a region that does not fit in shared memory, mask scratch too large, > 2^32 mirror units);
+// the binning has been done, the caller continues with the round-1 engine.
+template <int LAYOUT>
+static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool* done) {
+  *done = false;
+  const int64_t pn = a->pn;
+  int64_t r0 = a->row_begin, r1 = a->row_end;
+  if (r0 == 0 && r1 == 0) r1 = pn;
+  int rc = bin_particles<LAYOUT>(ctx, a, st);
+  if (rc) return rc;
+  const size_t mask_bytes = sizeof(unsigned long long) * 25 * (size_t)pn;
+  if (mask_bytes > ((size_t)16 << 30)) return LJ_OK;
+  grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
+  float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
+  if (ctx->cl_valid && (ctx->cl_id_list == a->sorted_list || ctx->cl_id_nop == a->number_of_partners ||
+                        ctx->cl_id_ptr == a->pointer))
+    ctx->cl_valid = false;
+  if (!ctx->tl_geom) {
+    LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->tl_geom, sizeof(lj_tile_geom), ctx->pool, st));
+    LJ_CUDA(ctx, cudaHostAlloc((void**)&ctx->tl_geom_host, sizeof(lj_tile_geom), cudaHostAllocDefault));
+  }
+  if (pn > ctx->tl_pn_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_order, sizeof(int32_t) * pn, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cnt, sizeof(int32_t) * pn, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_units, sizeof(uint32_t) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_off, sizeof(uint32_t) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_meta, sizeof(int4) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_qs, 24 * (size_t)(pn + 2), st))) return rc;
+    LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_qs, 0, 24 * (size_t)(pn + 2), st));
+    ctx->tl_qz = ctx->tl_qs + 2 * (size_t)(pn + 2);
+    ctx->tl_pn_cap = pn;
+  }
+  const int rows_env = lj_diag_int("LJ_TILE_ROWS");
+  const int target_rows = rows_env > 0 ? rows_env : (a->flags & LJ_LIST_TILES_WIDE) ? 56 : 40;
+  k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
+  LJ_LAUNCHED(ctx);
+  // read-back 1: the grid and the tile count (size the tables and the launches)
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_geom_host, ctx->tl_geom, sizeof(lj_tile_geom), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  lj_tile_geom g = *ctx->tl_geom_host;
+  if (g.ntiles <= 0) return LJ_OK;
+  const int64_t ncell1 = (int64_t)g.nx * g.ny * g.nz + 1;
+  if (ncell1 > ctx->tl_cells_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cell_start, sizeof(uint32_t) * ncell1, st))) return rc;
+    ctx->tl_cells_cap = ncell1;
+  }
+  if (g.ntiles > ctx->tl_tab_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_tab, sizeof(uint2) * kTileYTab * (size_t)g.ntiles, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_ttab, sizeof(uint4) * kTileTTab * (size_t)g.ntiles, st))) return rc;
+    ctx->tl_tab_cap = g.ntiles;
+  }
+  const int ncols_all = g.ntx * g.nz;
+  if (ncols_all > ctx->tl_cols_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cols, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    ctx->tl_cols_cap = ncols_all;
+  }
+  if (ncols_all > ctx->tl_sel_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_zflag, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cols_sel, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    ctx->tl_sel_cap = ncols_all;
+  }
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_cell_start, ctx->cell_start, sizeof(uint32_t) * ncell1,
+                               cudaMemcpyDeviceToDevice, st));
+  k_tile_table<<<(unsigned)blocks_for(g.ntiles, 128), 128, 0, st>>>(ctx->tl_cell_start, ctx->tl_off, ctx->tl_geom,
+                                                                     ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols, 0);
+  LJ_LAUNCHED(ctx);
+  // read-back 2: the longest y-row (sizes the shared memory of the count kernel)
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_geom_host, ctx->tl_geom, sizeof(lj_tile_geom), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  g = *ctx->tl_geom_host;
+  const int cap_y = lj_celltile_cap_y(g);
+  const int ncx1 = g.tc + 5;  // x-cells of a region + 1
+  const size_t smem_tab = 25 * sizeof(te_pencil) + sizeof(int) * 25 * (size_t)ncx1;
+  const size_t smem_count = (size_t)5 * cap_y * sizeof(float4) + smem_tab;
+  if (5 * cap_y >= 65536 || smem_count > (size_t)200 * 1024) return LJ_OK;
+  unsigned long long* masks = nullptr;
+  LJ_CUDA(ctx, cudaMallocAsync((void**)&masks, mask_bytes, ctx->pool, st));
+  LJ_FUNC_SMEM(ctx, k_tile_count, smem_count);
+  const double sl2 = a->search_len * a->search_len;
+  k_tile_count<<<(unsigned)g.ntiles, kTeThreads, smem_count, st>>>(
+      pn, r0, r1, ge, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ctx->sorted_pos, sorted_pos32, sl2, ncx1,
+      a->number_of_partners, ctx->tl_order, ctx->tl_cnt, ctx->tl_units, reinterpret_cast<unsigned char*>(masks), ctx->totals);
+  LJ_LAUNCHED(ctx);
+  // pointer[] = exclusive scan of number_of_partners (64-bit carry), mirror offsets = scan of the padded units
+  const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
+  const uint32_t* nop_u = reinterpret_cast<const uint32_t*>(a->number_of_partners);
+  k_scan_reduce<<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp);
+  LJ_LAUNCHED(ctx);
+  k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, row_tiles, &ctx->totals->total);
+  LJ_LAUNCHED(ctx);
+  if (a->pointer64)
+    k_scan_down<long long><<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp,
+                                                                reinterpret_cast<long long*>(a->pointer));
+  else
+    k_scan_down<uint32_t><<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp,
+                                                               reinterpret_cast<uint32_t*>(a->pointer));
+  LJ_LAUNCHED(ctx);
+  k_finish_totals<<<1, 1, 0, st>>>(ctx->totals, a->capacity, a->pointer64);
+  LJ_LAUNCHED(ctx);
+  ctx->last_capacity = a->capacity;
+  const unsigned utiles = (unsigned)blocks_for(pn + 1, kScanTile);
+  k_scan_reduce<<<utiles, kScanThreads, 0, st>>>(ctx->tl_units, pn + 1, nullptr, ctx->scan_tmp);
+  LJ_LAUNCHED(ctx);
+  k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, utiles, &ctx->tl_geom->total_units);
+  LJ_LAUNCHED(ctx);
+  k_scan_down<uint32_t><<<utiles, kScanThreads, 0, st>>>(ctx->tl_units, pn + 1, nullptr, ctx->scan_tmp, ctx->tl_off);
+  LJ_LAUNCHED(ctx);
+  k_tile_meta<<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(pn, ctx->tl_order, ctx->tl_cnt, ctx->tl_off, ctx->tl_meta);
+  LJ_LAUNCHED(ctx);
+  // tile table, active columns, z-layer flags: need the offsets, not the list itself
+  LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_zflag, 0, sizeof(int32_t) * (size_t)ncols_all, st));
+  if (r0 > 0 || r1 < pn) {
+    k_tile_zflag<<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(pn, r0, r1, ctx->cell_of, ctx->tl_geom, ctx->tl_zflag);
+    LJ_LAUNCHED(ctx);
+  }
+  LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_cols, 0, sizeof(int32_t) * (size_t)ncols_all, st));
+  k_tile_table<<<(unsigned)blocks_for(g.ntiles, 128), 128, 0, st>>>(ctx->tl_cell_start, ctx->tl_off, ctx->tl_geom,
+                                                                     ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols, 1);
+  LJ_LAUNCHED(ctx);
+  k_tile_cols<<<1, 32, 0, st>>>(ncols_all, ctx->tl_cols, ctx->tl_geom);
+  LJ_LAUNCHED(ctx);
+  // read-back 3: totals (capacity / offset overflow, crowded cells) and the size of the mirror
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_geom_host, ctx->tl_geom, sizeof(lj_tile_geom), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  g = *ctx->tl_geom_host;
+  const int ovf = ctx->totals_host->overflow;
+  if ((ovf & 16) || g.total_units >= 0xffffffffull) {  // not for this engine: the round-1 engine redoes the counts
+    LJ_CUDA(ctx, cudaFreeAsync(masks, st));
+    LJ_CUDA(ctx, cudaMemsetAsync(ctx->totals, 0, sizeof(lj_list_totals), st));  // its flags start clean
+    return LJ_OK;
+  }
+  *done = true;
+  if (ovf) {  // capacity or 32-bit offset overflow: reported by lj_list_result, nothing to fill
+    LJ_CUDA(ctx, cudaFreeAsync(masks, st));
+    return LJ_OK;
+  }
+  if ((int64_t)g.total_units + 2 > ctx->tl_list_cap) {
+    const int64_t cap = (int64_t)g.total_units + (int64_t)g.total_units / 32 + 1024;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_list, 16 * (size_t)cap, st))) return rc;
+    ctx->tl_list_cap = cap;
+  }
+  const size_t smem_replay = smem_tab + (size_t)(kTeThreads / kTeLanes) * kTeRowCap * 6;
+  LJ_FUNC_SMEM(ctx, k_tile_replay<true>, smem_replay);
+  LJ_FUNC_SMEM(ctx, k_tile_replay<false>, smem_replay);
+  if (a->pointer64)
+    k_tile_replay<true><<<(unsigned)g.ntiles, kTeThreads, smem_replay, st>>>(
+        pn, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ncx1, ctx->tl_order, ctx->tl_cnt, ctx->tl_off, masks, ctx->tl_list,
+        a->pointer, a->sorted_list, a->capacity, ctx->totals);
+  else
+    k_tile_replay<false><<<(unsigned)g.ntiles, kTeThreads, smem_replay, st>>>(
+        pn, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ncx1, ctx->tl_order, ctx->tl_cnt, ctx->tl_off, masks, ctx->tl_list,
+        a->pointer, a->sorted_list, a->capacity, ctx->totals);
+  LJ_LAUNCHED(ctx);
+  LJ_CUDA(ctx, cudaFreeAsync(masks, st));
+  // read-back 4 is not needed: the geometry is final since read-back 3 (k_tile_cols included); the
+  // replay can only raise bit 8 (masks disagree with the counts), which lj_list_result reports
+  if (lj_diag_set("LJ_TILE_DEBUG"))
+    fprintf(stderr, "[lj] cell-tile mirror (tile engine): grid %dx%dx%d, %d cells per tile, %d tiles, max rows %d, y-row %d, "
+            "list units %d, y slot %zu B, list slot %zu B, %llu units total\n", g.nx, g.ny, g.nz, g.tc,
+            g.ntiles, g.max_rows, g.max_yrow, g.max_units, lj_celltile_yslot_bytes(g),
+            lj_celltile_lslot_bytes(g), g.total_units);
+  // too dense for the shared-memory rings of the force kernel: the lists are complete, there is no mirror
+  if (kTileMinYSlots * lj_celltile_yslot_bytes(g) + kTileMinLSlots * lj_celltile_lslot_bytes(g) > kTileSmemBudget)
     return LJ_OK;
   ctx->tl_g = g;
   ctx->tl_valid = true;
@@ -1365,13 +1862,40 @@ extern "C" int lj_build_list(lj_ctx* ctx, const lj_list_args* a, int64_t* number
   int rc;
   const bool tiles = (a->flags & LJ_LIST_TILES) && !a->half && a->layout != LJ_AOS_F4 && a->layout != LJ_AOS_F3;
   bool deferred = tiles;  // let the cell-tile fill pass write sorted_list too, if the engine allows
+  // the tile engine (one search per build) serves the plain LJ_LIST_TILES build; when it does not apply it
+  // leaves the binning done and the round-1 engine takes over
+  bool binned = false;
+  if (tiles && !(a->flags & (LJ_LIST_CLUSTERS | LJ_LIST_PER_PARTICLE_SEARCH)) && !lj_diag_set("LJ_TILE_OLD_ENGINE")) {
+    bool done = false;
+    switch (a->layout) {
+      case LJ_AOS_D3: rc = build_list_tiles<LJ_AOS_D3>(ctx, a, st, &done); break;
+      case LJ_AOS_D4:
+        LJ_REQUIRE(ctx, (uintptr_t)a->q % 32 == 0, "lj_build_list: double4 array must be 32-byte aligned");
+        rc = build_list_tiles<LJ_AOS_D4>(ctx, a, st, &done);
+        break;
+      default: rc = build_list_tiles<LJ_SOA_D>(ctx, a, st, &done); break;
+    }
+    if (rc) return rc;
+    if (done) {
+      if (a->flags & LJ_LIST_SORT_ROWS) {
+        // sorting the public rows would leave the mirror in another order: still the same set per row,
+        // and the mirror only ever is consumed by the cell-tile kernel
+        rc = lj_sort_rows_launch(ctx, a->sorted_list, a->number_of_partners, a->pointer, a->pointer64,
+                                 a->pn, a->capacity, st);
+        if (rc) return rc;
+      }
+      if (number_of_pairs_out) return lj_list_result(ctx, number_of_pairs_out, nullptr, stream);
+      return LJ_OK;
+    }
+    binned = true;
+  }
   switch (a->layout) {
-    case LJ_AOS_D3: rc = build_list_impl<LJ_AOS_D3>(ctx, a, st, &deferred); break;
+    case LJ_AOS_D3: rc = build_list_impl<LJ_AOS_D3>(ctx, a, st, &deferred, binned); break;
     case LJ_AOS_D4:
       LJ_REQUIRE(ctx, (uintptr_t)a->q % 32 == 0, "lj_build_list: double4 array must be 32-byte aligned");
-      rc = build_list_impl<LJ_AOS_D4>(ctx, a, st, &deferred);
+      rc = build_list_impl<LJ_AOS_D4>(ctx, a, st, &deferred, binned);
       break;
-    case LJ_SOA_D: rc = build_list_impl<LJ_SOA_D>(ctx, a, st, &deferred); break;
+    case LJ_SOA_D: rc = build_list_impl<LJ_SOA_D>(ctx, a, st, &deferred, binned); break;
     case LJ_AOS_F4:
       LJ_REQUIRE(ctx, (uintptr_t)a->q % 16 == 0, "lj_build_list: float4 array must be 16-byte aligned");
       rc = build_list_impl<LJ_AOS_F4>(ctx, a, st, &deferred);
@@ -1416,6 +1940,8 @@ extern "C" int lj_list_result(lj_ctx* ctx, int64_t* number_of_pairs_out, int32_t
   LJ_CUDA(ctx, cudaStreamSynchronize(st));
   if (number_of_pairs_out) *number_of_pairs_out = (int64_t)ctx->totals_host->total;
   if (max_partners_out) *max_partners_out = ctx->totals_host->max_np;
+  if (ctx->totals_host->overflow & 8)
+    return lj_set_error(ctx, LJ_ERR_INVALID_LIST, "lj_build_list", "cell-tile mirror disagrees with the CSR list");
   if (ctx->totals_host->overflow & 2)
     return lj_set_error(ctx, LJ_ERR_OVERFLOW32, "lj_build_list", "list offsets exceed 32 bits: pass pointer64=1");
   if (ctx->totals_host->overflow & 1)
