@@ -162,6 +162,11 @@ typedef struct lj_force_args {
                                         0 = unknown.  Lets LJ_VARIANT_TILE_TMA round its bulk
                                         copies up to 16 bytes without reading past the array */
   int64_t ell_width;                 /* LJ_LIST_ELL_ROWS: entries per row of the padded table   */
+  uint64_t mirror_token;             /* lj_list_mirror_token() of the mirror the caller vouches for: the
+                                        cell-tile / cluster mirrors are used only when this matches the
+                                        context's current mirror AND the arrays are the ones it was built
+                                        from.  0 (a caller that knows nothing of mirrors, or one that has
+                                        written other contents into the same arrays) = per-row kernels.  */
 } lj_force_args;
 
 LJ_API int lj_force_step(lj_ctx* ctx, const lj_force_args* args, void* stream);
@@ -232,6 +237,22 @@ typedef struct lj_list_args {
  * lj_list_result(). */
 LJ_API int lj_build_list(lj_ctx* ctx, const lj_list_args* args, int64_t* number_of_pairs_out,
                   void* stream);
+/* Build the cell-tile mirror for a CSR list the CALLER supplies -- built on the host, loaded from a
+ * pair cache, shuffled (the reference's flow: cuda/force_cuda.cu:203-227, 255-263, 392-397 always hands
+ * the kernel such a list).  Bins q, lays out the tiles and translates every entry j of row i into the
+ * 16-bit index of j inside the shared-memory region of i's tile, in the row's own order (so the cell-tile
+ * kernel sums in the same order as the per-row kernel with 8 lanes per row).  Rows with an entry outside
+ * the region of their tile (a list built with a longer search length than `search_len`, or positions
+ * that have moved further than the skin since) are left out of the mirror and served by the per-row
+ * kernel on the caller's arrays right after the cell-tile kernel; *rows_outside_out tells how many.
+ * Full lists, FP64 layouts.  Synchronises.  flags: LJ_LIST_TILES_WIDE or 0. */
+LJ_API int lj_list_mirror(lj_ctx* ctx, const void* q, int64_t pn, int32_t layout, int64_t plane_stride,
+                          double search_len, const int32_t* number_of_partners, const void* pointer,
+                          int32_t pointer64, const int32_t* sorted_list, int64_t list_entries, int32_t flags,
+                          int64_t* rows_outside_out, void* stream);
+/* generation token of the mirror this context currently holds (0 = none): changes with every
+ * lj_build_list / lj_list_mirror that produces one; pass it in lj_force_args.mirror_token */
+LJ_API uint64_t lj_list_mirror_token(lj_ctx* ctx);
 /* drop the cluster mirror (call after modifying the list arrays yourself) */
 LJ_API int lj_list_invalidate(lj_ctx* ctx);
 /* status + totals of the most recent lj_build_list on this context (synchronises `stream`) */

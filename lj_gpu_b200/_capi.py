@@ -41,7 +41,7 @@ class LjForceArgs(C.Structure):
         ("variant", C.c_int32), ("group", C.c_int32), ("precision", C.c_int32),
         ("pointer64", C.c_int32), ("threads_per_block", C.c_int32), ("list_scalar", C.c_int32),
         ("plane_stride", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
-        ("list_entries", C.c_int64), ("ell_width", C.c_int64),
+        ("list_entries", C.c_int64), ("ell_width", C.c_int64), ("mirror_token", C.c_uint64),
     ]
 
 
@@ -103,6 +103,8 @@ PROTOTYPES = {
     "lj_force_loop_soa6": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(LjForceArgs), C.c_int, _vp]),
     "lj_build_list_soa6": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(LjListArgs), C.POINTER(_i64), _vp]),
     "lj_list_invalidate": (C.c_int, [_vp]),
+    "lj_list_mirror": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _dbl, _vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_i64), _vp]),
+    "lj_list_mirror_token": (C.c_uint64, [_vp]),
     "lj_list_result": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i32), _vp]),
     "lj_build_ell": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, C.POINTER(_i32), _vp]),
     "lj_build_ell_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i64, C.POINTER(_i32), _vp]),

@@ -127,6 +127,7 @@ class PairList:
     transposed_list: "torch.Tensor | None" = None
     sorted_list2d: "torch.Tensor | None" = None   # row-major padded table [pn, ell_width]
     ell_width: int = 0
+    token: int = 0                        # lj_list_mirror_token() of the mirror built with / for these arrays
     build_flags: dict | None = None      # tiles / clusters / sort_rows / per_particle of the build: rebuild() reuses them
 
     @property
@@ -244,6 +245,7 @@ class LJContext:
         mx = C.c_int32(0)
         self._check(self.lib.lj_list_result(self.h, C.byref(total), C.byref(mx), st))
         return PairList(nop, ptr, lst, int(total.value), int(mx.value), half, None, None, 0,
+                        int(self.lib.lj_list_mirror_token(self.h)),
                         dict(tiles=tiles, clusters=clusters, sort_rows=sort_rows, per_particle=per_particle,
                              rows=rows))
 
@@ -276,6 +278,25 @@ class LJContext:
         if rows is not None:
             a.row_begin, a.row_end = rows
         self._check(self.lib.lj_build_list(self.h, C.byref(a), None, self._stream(stream)))
+        pl.token = int(self.lib.lj_list_mirror_token(self.h))
+
+    def list_mirror(self, q, pl: PairList, search_len: float = SEARCH_LENGTH, layout=None, pn=None,
+                    wide: bool = False, stream=None) -> int:
+        """lj_list_mirror(): the cell-tile mirror of a list the CALLER supplies (loaded from a pair
+        cache, shuffled, built elsewhere).  Returns the number of rows the mirror could not take
+        (they are served by the per-row kernel on the caller's arrays)."""
+        lay = self._layout_of(q, layout)
+        n, stride = self._pn_stride(q, lay)
+        if pn is not None:
+            n = pn
+        outside = C.c_int64(0)
+        self._check(self.lib.lj_list_mirror(self.h, q.data_ptr(), n, lay, stride, search_len,
+                                            pl.number_of_partners.data_ptr(), pl.pointer.data_ptr(),
+                                            int(pl.pointer64), pl.sorted_list.data_ptr(), pl.sorted_list.numel(),
+                                            capi.LJ_LIST_TILES_WIDE if wide else 0, C.byref(outside),
+                                            self._stream(stream)))
+        pl.token = int(self.lib.lj_list_mirror_token(self.h))
+        return int(outside.value)
 
     def list_invalidate(self):
         self._check(self.lib.lj_list_invalidate(self.h))
@@ -354,6 +375,7 @@ class LJContext:
             a.list_entries = pl.sorted_list.numel()
         a.number_of_partners = pl.number_of_partners.data_ptr()
         a.layout = lay
+        a.mirror_token = pl.token
         v = VARIANTS[variant] if isinstance(variant, str) else variant
         if pl.half:
             v = LJ_VARIANT_NEWTON3   # CSR: group lanes per i; half ELL table: thread per i (memopt2/3_with_aar)
@@ -398,7 +420,9 @@ class LJContext:
             break
         mx = C.c_int32(0)
         self._check(self.lib.lj_list_result(self.h, C.byref(total), C.byref(mx), st))
-        return PairList(nop, ptr, lst, int(total.value), int(mx.value), half)
+        pl = PairList(nop, ptr, lst, int(total.value), int(mx.value), half)
+        pl.token = int(self.lib.lj_list_mirror_token(self.h))
+        return pl
 
     def force_loop_soa6(self, qx, qy, qz, px, py, pz, pl: PairList, loop: int = LOOP, dt: float = DT,
                         cl2: float = CL2, ell: bool = False, variant="auto", group: int = 0,
@@ -415,6 +439,7 @@ class LJContext:
             a.list, a.pointer, a.list_layout = pl.sorted_list.data_ptr(), pl.pointer.data_ptr(), LJ_LIST_CSR
             a.list_entries = pl.sorted_list.numel()
         a.number_of_partners = pl.number_of_partners.data_ptr()
+        a.mirror_token = pl.token
         v = VARIANTS[variant] if isinstance(variant, str) else variant
         if pl.half and not ell:
             v = LJ_VARIANT_NEWTON3

@@ -119,6 +119,14 @@ struct lj_ctx {
   const void* tl_id_nop = nullptr;
   const void* tl_id_ptr = nullptr;
   int64_t tl_pn = 0, tl_r0 = 0, tl_r1 = 0;
+  uint64_t tl_token = 0;                 // generation of the valid mirror (lj_list_mirror_token); callers pass it back
+  uint64_t tl_token_next = 1;
+  unsigned char* tl_rowflag = nullptr;   // lj_list_mirror: rows the mirror does not hold (an entry outside the tile's region)
+  int64_t tl_rowflag_cap = 0;
+  const unsigned char* only_rows_launch = nullptr;  // transient: row filter of the per-row launch in progress
+  int64_t tl_outside = 0;                // how many such rows; they take the per-row kernel after the cell-tile kernel
+  int32_t* tl_slot_of = nullptr;         // lj_list_mirror: cell-order slot of particle i
+  int64_t tl_slot_cap = 0;
   lj_tile_geom tl_g{};                   // host copy of the geometry of the valid mirror
 
   // mixed-precision scratch: origin-shifted float4 positions

@@ -37,12 +37,14 @@ __global__ void __launch_bounds__(1024)
 lj_gather_csr(const void* __restrict__ q, void* __restrict__ p, int64_t row_begin, int64_t row_end,
               int64_t plane, double c24, double c48, long long cl2_bits,
               const int32_t* __restrict__ list, const int32_t* __restrict__ nop,
-              const void* __restrict__ pointer, cudaTextureObject_t ltex = 0) {
+              const void* __restrict__ pointer, cudaTextureObject_t ltex = 0,
+              const unsigned char* __restrict__ only_rows = nullptr) {
   const int rows_per_block = blockDim.x / G;
   const int64_t i = row_begin + (int64_t)blockIdx.x * rows_per_block + threadIdx.x / G;
   const int lg = threadIdx.x % G;
   // whole groups leave together (G divides 32), so the shuffles below stay convergent
   if (i >= row_end) return;
+  if (only_rows && !only_rows[i]) return;  // lj_list_mirror: only the rows the mirror does not hold
 
   double xi, yi, zi;
   load_pos<LAYOUT>(q, i, plane, xi, yi, zi);
@@ -456,7 +458,7 @@ void launch_csr(lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1, int
     }
     lj_gather_csr<G, LAYOUT, PTR64><<<blocks, tb, 0, st>>>(a->q, a->p, r0, r1, a->plane_stride, c24,
                                                             c48, cl2_bits, a->list,
-                                                            a->number_of_partners, a->pointer);
+                                                            a->number_of_partners, a->pointer, 0, ctx->only_rows_launch);
   }
 }
 
@@ -594,7 +596,22 @@ int lj_force_launch(lj_ctx* ctx, const lj_force_args* a, cudaStream_t st, int pa
   }
   if ((a->variant == LJ_VARIANT_CELLTILE || (a->variant == LJ_VARIANT_AUTO && lj_celltile_worthwhile(ctx))) &&
       lj_celltile_usable(ctx, a, r0, r1))
-    return lj_force_celltile_launch(ctx, a, c24, c48, cl2_bits, st, 0);
+  {
+    int rc = lj_force_celltile_launch(ctx, a, c24, c48, cl2_bits, st, 0);
+    if (rc || ctx->tl_outside == 0) return rc;
+    // lj_list_mirror left some rows out (an entry outside their tile's region): the per-row kernel, those rows only
+    ctx->only_rows_launch = ctx->tl_rowflag;
+    bool ok = false;
+    switch (a->layout) {
+      case LJ_AOS_D3: ok = launch_layout<LJ_AOS_D3>(ctx, 8, a, r0, r1, tb, c24, c48, cl2_bits, false, st); break;
+      case LJ_AOS_D4: ok = launch_layout<LJ_AOS_D4>(ctx, 8, a, r0, r1, tb, c24, c48, cl2_bits, false, st); break;
+      case LJ_SOA_D: ok = launch_layout<LJ_SOA_D>(ctx, 8, a, r0, r1, tb, c24, c48, cl2_bits, false, st); break;
+    }
+    ctx->only_rows_launch = nullptr;
+    LJ_REQUIRE(ctx, ok, "lj_force_step: no per-row kernel for the rows outside the mirror");
+    LJ_LAUNCHED(ctx);
+    return LJ_OK;
+  }
   if (a->precision == LJ_PREC_MIXED) {
     LJ_REQUIRE(ctx, !n3 && a->list_layout == LJ_LIST_CSR, "lj_force_step: mixed precision is gather/CSR only");
     return lj_force_mixed_launch(ctx, a, r0, r1, g, tb, st);

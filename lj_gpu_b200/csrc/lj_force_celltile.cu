@@ -764,6 +764,9 @@ bool lj_celltile_worthwhile(const lj_ctx* ctx) { return ctx->tl_g.ntiles >= 32 *
 // true when the mirror describes exactly the list arrays and the row range of this call
 bool lj_celltile_usable(const lj_ctx* ctx, const lj_force_args* a, int64_t r0, int64_t r1) {
   if (!ctx->tl_valid || a->list_layout != LJ_LIST_CSR) return false;
+  // pointer identity alone cannot tell a list that was overwritten in place: the caller vouches with the token
+  if (a->mirror_token != ctx->tl_token) return false;
+  if (ctx->tl_outside > 0 && a->precision != LJ_PREC_FP64) return false;  // rows outside the mirror: FP64 per-row completion only
   if (a->precision != LJ_PREC_FP64 && a->precision != LJ_PREC_MIXED) return false;
   if (a->layout != LJ_AOS_D3 && a->layout != LJ_AOS_D4 && a->layout != LJ_SOA_D) return false;
   if (a->list != ctx->tl_id_list || a->number_of_partners != ctx->tl_id_nop ||

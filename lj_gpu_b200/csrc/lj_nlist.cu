@@ -1237,6 +1237,79 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
   }
 }
 
+// ---- lj_list_mirror: the mirror of a list the CALLER built ---------------------------------
+__global__ void __launch_bounds__(256)
+k_slot_of(int64_t pn, const int32_t* __restrict__ order, int32_t* __restrict__ slot_of) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < pn) slot_of[order[s]] = (int32_t)s;
+}
+
+// One CTA per tile, eight lanes per row: entry k of row i (the caller's order) -> region-local index
+// of j in i's tile.  A row with an entry outside the 25 pencils / the region's x-range is flagged
+// (row_flag[i] = 1, its mirror row gets length 0) and left to the per-row kernel.
+template <bool PTR64>
+__global__ void __launch_bounds__(kTeThreads)
+k_tile_translate(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* __restrict__ cell_start,
+                 const uint2* __restrict__ ytab, int ncx1, const int32_t* __restrict__ cell_of,
+                 const int32_t* __restrict__ slot_of, const int32_t* __restrict__ tl_order,
+                 const int32_t* __restrict__ tl_cnt, const uint32_t* __restrict__ tl_off, int4* __restrict__ meta,
+                 uint16_t* __restrict__ tl_list, const void* __restrict__ pointer, const int32_t* __restrict__ list,
+                 unsigned char* __restrict__ row_flag, lj_list_totals* __restrict__ tot) {
+  extern __shared__ __align__(16) unsigned char te_smem[];
+  const lj_tile_geom g = *tgp;
+  const uint32_t cap_y = (uint32_t)((g.max_yrow + 8 + 1) & ~1);
+  te_pencil* pen = reinterpret_cast<te_pencil*>(te_smem);
+  int* xoff = reinterpret_cast<int*>(pen + 25);
+  int ncx;
+  uint32_t s0, ns;
+  const int t = blockIdx.x;
+  te_setup(g, t, cap_y, cell_start, ytab, pen, xoff, ncx1, ncx, s0, ns);
+  const int cy = t % g.ny, tx = (t / g.ny) % g.ntx, cz = t / (g.ny * g.ntx);
+  int xa, xb, rxa, rxb;
+  tile_x_extent(tx * g.tc, g.tc, g.nx, xa, xb, rxa, rxb);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lg = lane % kTeLanes, gi = lane / kTeLanes;
+  const unsigned gmask = 0xffu << (gi * kTeLanes);
+  const uint16_t dummy = (uint16_t)(cap_y - 1);
+  for (uint32_t rb = warp * 4; rb < ns; rb += (kTeThreads / 32) * 4) {
+    const uint32_t r = rb + gi;
+    if (r >= ns) continue;  // (whole groups)
+    const uint32_t s = s0 + r;
+    const int want = tl_cnt[s];
+    const int i = tl_order[s];
+    const size_t base = (size_t)tl_off[s] * 8;
+    const int64_t pbase = row_offset<PTR64>(pointer, i);
+    bool outside = false;
+    for (int k = lg; k < want; k += kTeLanes) {
+      const int j = list[pbase + k];
+      uint16_t L = dummy;
+      bool ok = j >= 0 && j < pn;
+      if (ok) {
+        const int c = cell_of[j];
+        const int jx = c % g.nx, jy = (c / g.nx) % g.ny, jz = c / (g.nx * g.ny);
+        const int dy = jy - cy + 2, dz = jz - cz + 2;
+        ok = dy >= 0 && dy < 5 && dz >= 0 && dz < 5 && jx >= rxa && jx <= rxb;
+        if (ok) {
+          const te_pencil e = pen[dz * 5 + dy];
+          L = (uint16_t)(e.base + ((uint32_t)slot_of[j] - e.st));
+        }
+      }
+      outside |= !ok;
+      tl_list[base + k] = L;
+    }
+    const int padded = ((want + 7) >> 3) << 3;
+    for (int k = want + lg; k < padded; k += kTeLanes) tl_list[base + k] = dummy;
+    outside = __any_sync(gmask, outside);
+    if (lg == 0) {
+      row_flag[i] = outside ? 1 : 0;
+      if (outside) {
+        meta[s].x = 0;  // the cell-tile kernel skips the row
+        atomicAdd(&tot->cl_total, 1ull);  // (reused as the count of rows left to the per-row kernel)
+      }
+    }
+  }
+}
+
 int64_t blocks_for(int64_t n, int tb) { return (n + tb - 1) / tb; }
 
 }  // namespace
@@ -1332,6 +1405,7 @@ static int bin_particles(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st) {
       ctx->sorted_pos, sorted_pos32);
   LJ_LAUNCHED(ctx);
   ctx->tl_valid = false;  // the cell-sort scratch and any mirror derived from it are rebuilt from here
+  ctx->tl_token = 0;
   ctx->graph_loop = -1;   // ... and a cached CUDA graph may replay the kernel that ran on the old mirror
   return LJ_OK;
 }
@@ -1620,6 +1694,8 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
     return LJ_OK;
   ctx->tl_g = g;
   ctx->tl_valid = true;
+  ctx->tl_token = ctx->tl_token_next++;
+  ctx->tl_outside = 0;
   ctx->tl_id_list = a->sorted_list; ctx->tl_id_nop = a->number_of_partners; ctx->tl_id_ptr = a->pointer;
   ctx->tl_pn = pn; ctx->tl_r0 = r0; ctx->tl_r1 = r1;
   ctx->graph_loop = -1;  // the geometry is baked into the launch parameters
@@ -1797,11 +1873,156 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st,
     return LJ_OK;
   ctx->tl_g = g;
   ctx->tl_valid = true;
+  ctx->tl_token = ctx->tl_token_next++;
+  ctx->tl_outside = 0;
   ctx->tl_id_list = a->sorted_list; ctx->tl_id_nop = a->number_of_partners; ctx->tl_id_ptr = a->pointer;
   ctx->tl_pn = pn; ctx->tl_r0 = r0; ctx->tl_r1 = r1;
   ctx->graph_loop = -1;  // the geometry is baked into the launch parameters
   return LJ_OK;
 }
+
+template <int LAYOUT>
+static int list_mirror_impl(lj_ctx* ctx, const lj_list_args* a, int64_t* rows_outside_out, cudaStream_t st) {
+  const int64_t pn = a->pn;
+  int rc = bin_particles<LAYOUT>(ctx, a, st);
+  if (rc) return rc;
+  grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
+  float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
+  if (!ctx->tl_geom) {
+    LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->tl_geom, sizeof(lj_tile_geom), ctx->pool, st));
+    LJ_CUDA(ctx, cudaHostAlloc((void**)&ctx->tl_geom_host, sizeof(lj_tile_geom), cudaHostAllocDefault));
+  }
+  if (pn > ctx->tl_pn_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_order, sizeof(int32_t) * pn, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cnt, sizeof(int32_t) * pn, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_units, sizeof(uint32_t) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_off, sizeof(uint32_t) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_meta, sizeof(int4) * (pn + 1), st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_qs, 24 * (size_t)(pn + 2), st))) return rc;
+    LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_qs, 0, 24 * (size_t)(pn + 2), st));
+    ctx->tl_qz = ctx->tl_qs + 2 * (size_t)(pn + 2);
+    ctx->tl_pn_cap = pn;
+  }
+  if (pn > ctx->tl_rowflag_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_rowflag, (size_t)pn, st))) return rc;
+    ctx->tl_rowflag_cap = pn;
+  }
+  if (pn > ctx->tl_slot_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_slot_of, sizeof(int32_t) * (size_t)pn, st))) return rc;
+    ctx->tl_slot_cap = pn;
+  }
+  const int target_rows = (a->flags & LJ_LIST_TILES_WIDE) ? 56 : 40;
+  k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
+  LJ_LAUNCHED(ctx);
+  // rows in cell order with the caller's counts, their padded lengths and offsets
+  k_tile_rows<<<(unsigned)blocks_for(pn + 1, 256), 256, 0, st>>>(pn, sorted_pos32, a->number_of_partners,
+                                                                  ctx->tl_order, ctx->tl_cnt, ctx->tl_units);
+  LJ_LAUNCHED(ctx);
+  const unsigned utiles = (unsigned)blocks_for(pn + 1, kScanTile);
+  k_scan_reduce<<<utiles, kScanThreads, 0, st>>>(ctx->tl_units, pn + 1, nullptr, ctx->scan_tmp);
+  LJ_LAUNCHED(ctx);
+  k_scan_spine<<<1, kScanThreads, 0, st>>>(ctx->scan_tmp, utiles, &ctx->tl_geom->total_units);
+  LJ_LAUNCHED(ctx);
+  k_scan_down<uint32_t><<<utiles, kScanThreads, 0, st>>>(ctx->tl_units, pn + 1, nullptr, ctx->scan_tmp, ctx->tl_off);
+  LJ_LAUNCHED(ctx);
+  k_tile_meta<<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(pn, ctx->tl_order, ctx->tl_cnt, ctx->tl_off, ctx->tl_meta);
+  LJ_LAUNCHED(ctx);
+  k_slot_of<<<(unsigned)blocks_for(pn, 256), 256, 0, st>>>(pn, ctx->tl_order, ctx->tl_slot_of);
+  LJ_LAUNCHED(ctx);
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_geom_host, ctx->tl_geom, sizeof(lj_tile_geom), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  lj_tile_geom g = *ctx->tl_geom_host;
+  LJ_REQUIRE(ctx, g.ntiles > 0 && g.total_units < 0xffffffffull, "lj_list_mirror: list too large for 32-bit mirror offsets");
+  const int64_t ncell1 = (int64_t)g.nx * g.ny * g.nz + 1;
+  if (ncell1 > ctx->tl_cells_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cell_start, sizeof(uint32_t) * ncell1, st))) return rc;
+    ctx->tl_cells_cap = ncell1;
+  }
+  if (g.ntiles > ctx->tl_tab_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_tab, sizeof(uint2) * kTileYTab * (size_t)g.ntiles, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_ttab, sizeof(uint4) * kTileTTab * (size_t)g.ntiles, st))) return rc;
+    ctx->tl_tab_cap = g.ntiles;
+  }
+  const int ncols_all = g.ntx * g.nz;
+  if (ncols_all > ctx->tl_cols_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cols, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    ctx->tl_cols_cap = ncols_all;
+  }
+  if (ncols_all > ctx->tl_sel_cap) {
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_zflag, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_cols_sel, sizeof(int32_t) * (size_t)ncols_all, st))) return rc;
+    ctx->tl_sel_cap = ncols_all;
+  }
+  if ((int64_t)g.total_units + 2 > ctx->tl_list_cap) {
+    const int64_t cap = (int64_t)g.total_units + (int64_t)g.total_units / 32 + 1024;
+    if ((rc = tile_alloc(ctx, (void**)&ctx->tl_list, 16 * (size_t)cap, st))) return rc;
+    ctx->tl_list_cap = cap;
+  }
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_cell_start, ctx->cell_start, sizeof(uint32_t) * ncell1,
+                               cudaMemcpyDeviceToDevice, st));
+  LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_zflag, 0, sizeof(int32_t) * (size_t)ncols_all, st));
+  LJ_CUDA(ctx, cudaMemsetAsync(ctx->tl_cols, 0, sizeof(int32_t) * (size_t)ncols_all, st));
+  k_tile_table<<<(unsigned)blocks_for(g.ntiles, 128), 128, 0, st>>>(ctx->tl_cell_start, ctx->tl_off, ctx->tl_geom,
+                                                                     ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols, 2);
+  LJ_LAUNCHED(ctx);
+  k_tile_cols<<<1, 32, 0, st>>>(ncols_all, ctx->tl_cols, ctx->tl_geom);
+  LJ_LAUNCHED(ctx);
+  const int ncx1 = g.tc + 5;
+  const size_t smem_tab = 25 * sizeof(te_pencil) + sizeof(int) * 25 * (size_t)ncx1;
+  LJ_REQUIRE(ctx, smem_tab <= (size_t)200 * 1024, "lj_list_mirror: tile too wide");
+  LJ_FUNC_SMEM(ctx, k_tile_translate<true>, smem_tab);
+  LJ_FUNC_SMEM(ctx, k_tile_translate<false>, smem_tab);
+  if (a->pointer64)
+    k_tile_translate<true><<<(unsigned)g.ntiles, kTeThreads, smem_tab, st>>>(
+        pn, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ncx1, ctx->cell_of, ctx->tl_slot_of, ctx->tl_order,
+        ctx->tl_cnt, ctx->tl_off, ctx->tl_meta, ctx->tl_list, a->pointer, a->sorted_list, ctx->tl_rowflag, ctx->totals);
+  else
+    k_tile_translate<false><<<(unsigned)g.ntiles, kTeThreads, smem_tab, st>>>(
+        pn, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ncx1, ctx->cell_of, ctx->tl_slot_of, ctx->tl_order,
+        ctx->tl_cnt, ctx->tl_off, ctx->tl_meta, ctx->tl_list, a->pointer, a->sorted_list, ctx->tl_rowflag, ctx->totals);
+  LJ_LAUNCHED(ctx);
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->tl_geom_host, ctx->tl_geom, sizeof(lj_tile_geom), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaMemcpyAsync(ctx->totals_host, ctx->totals, sizeof(lj_list_totals), cudaMemcpyDeviceToHost, st));
+  LJ_CUDA(ctx, cudaStreamSynchronize(st));
+  g = *ctx->tl_geom_host;
+  const int64_t outside = (int64_t)ctx->totals_host->cl_total;
+  if (rows_outside_out) *rows_outside_out = outside;
+  LJ_REQUIRE(ctx, 5 * lj_celltile_cap_y(g) < 65536 &&
+                 kTileMinYSlots * lj_celltile_yslot_bytes(g) + kTileMinLSlots * lj_celltile_lslot_bytes(g) <= kTileSmemBudget,
+             "lj_list_mirror: a tile's neighbourhood does not fit in shared memory (system too dense)");
+  ctx->tl_g = g;
+  ctx->tl_valid = true;
+  ctx->tl_token = ctx->tl_token_next++;
+  ctx->tl_outside = outside;
+  ctx->tl_id_list = a->sorted_list; ctx->tl_id_nop = a->number_of_partners; ctx->tl_id_ptr = a->pointer;
+  ctx->tl_pn = pn; ctx->tl_r0 = 0; ctx->tl_r1 = pn;
+  ctx->graph_loop = -1;
+  return LJ_OK;
+}
+
+extern "C" int lj_list_mirror(lj_ctx* ctx, const void* q, int64_t pn, int32_t layout, int64_t plane_stride,
+                              double search_len, const int32_t* number_of_partners, const void* pointer,
+                              int32_t pointer64, const int32_t* sorted_list, int64_t list_entries, int32_t flags,
+                              int64_t* rows_outside_out, void* stream) {
+  LJ_ENTER(ctx);
+  LJ_REQUIRE(ctx, q && number_of_partners && pointer && sorted_list, "lj_list_mirror: null array");
+  LJ_REQUIRE(ctx, pn > 0 && pn < 2147483647LL && search_len > 0.0 && list_entries >= 0, "lj_list_mirror: bad size");
+  LJ_REQUIRE(ctx, layout == LJ_AOS_D3 || layout == LJ_AOS_D4 || layout == LJ_SOA_D, "lj_list_mirror: FP64 layouts only");
+  if (layout == LJ_SOA_D) LJ_REQUIRE(ctx, plane_stride >= pn, "lj_list_mirror: SoA plane_stride < particle_number");
+  if (layout == LJ_AOS_D4) LJ_REQUIRE(ctx, (uintptr_t)q % 32 == 0, "lj_list_mirror: double4 array must be 32-byte aligned");
+  cudaStream_t st = lj_stream(ctx, stream);
+  lj_list_args a{};
+  a.q = q; a.pn = pn; a.layout = layout; a.plane_stride = plane_stride; a.search_len = search_len;
+  a.number_of_partners = const_cast<int32_t*>(number_of_partners); a.pointer = const_cast<void*>(pointer);
+  a.sorted_list = const_cast<int32_t*>(sorted_list); a.capacity = list_entries; a.pointer64 = pointer64; a.flags = flags;
+  switch (layout) {
+    case LJ_AOS_D3: return list_mirror_impl<LJ_AOS_D3>(ctx, &a, rows_outside_out, st);
+    case LJ_AOS_D4: return list_mirror_impl<LJ_AOS_D4>(ctx, &a, rows_outside_out, st);
+    default: return list_mirror_impl<LJ_SOA_D>(ctx, &a, rows_outside_out, st);
+  }
+}
+
+extern "C" uint64_t lj_list_mirror_token(lj_ctx* ctx) { return (ctx && ctx->tl_valid) ? ctx->tl_token : 0; }
 
 // positions of this step in cell order (the force kernel's TMA source).  part 0: every particle;
 // 1 / 2 (lj_force_step_part): only the particles inside / outside the mirror's row range, and

@@ -523,6 +523,16 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
       M_TRY(lj_upload(ctx, ptr, m->pointer_host, sizeof(int32_t) * (size_t)pn, st));
       m->h2d_bytes += 4 * (npairs + 2 * pn);
       M_TRY(lj_validate_list(ctx, list, nop, ptr, 0, pn, npairs, st));
+      // the reference's flow (cuda/force_cuda.cu:392-397): the kernel always runs on a host-built or cached
+      // list.  Give it the cell-tile mirror too where that kernel wins; a system the mirror cannot take
+      // (too dense for shared memory) simply stays on the per-row kernels.
+      if (!m->half && m->precision == LJ_PREC_FP64 &&
+          (m->variant == LJ_VARIANT_CELLTILE || (m->variant == LJ_VARIANT_AUTO && pn >= 300000))) {
+        int64_t outside = 0;
+        const int mrc = lj_list_mirror(ctx, q, pn, m->layout, m->plane_stride, m->search_len, nop, ptr, 0, list,
+                                       capacity, 0, &outside, st);
+        if (mrc != LJ_OK && m->variant == LJ_VARIANT_CELLTILE) { rc = mrc; goto done; }
+      }
     }
 
     lj_force_args fa{};
@@ -531,6 +541,7 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
     fa.variant = m->half ? LJ_VARIANT_NEWTON3 : m->variant; fa.group = m->group;
     fa.precision = m->precision; fa.pointer64 = ptr64; fa.threads_per_block = m->threads_per_block;
     fa.plane_stride = m->plane_stride;
+    fa.mirror_token = lj_list_mirror_token(ctx);  // the list above is the library's own build
 
     M_TRY(lj_sync(ctx, st));
     const double t_k0 = now_s();
@@ -540,6 +551,7 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
       if (own_list && m->rebuild_every > 0) {
         if (done_steps > 0) {  // the list for steps [0, rebuild_every) was built above
           M_TRY(lj_build_list(ctx, &la, nullptr, st));
+          fa.mirror_token = lj_list_mirror_token(ctx);
           m->list_builds++;
         }
         if (chunk > m->rebuild_every) chunk = m->rebuild_every;

@@ -36,7 +36,7 @@ struct Options {
   double density = 0.5, L = 50.0;
   std::string layout = "aos4", variant = "auto", prec = "fp64";
   int group = 0, steps = 100, rebuild_every = 0;
-  bool graph = false, test = false, all = false, cache = false, soa6 = false;
+  bool graph = false, test = false, all = false, cache = false, soa6 = false, print = false;
 };
 
 [[noreturn]] void die(lj_ctx* ctx, int rc, const char* where) {
@@ -142,6 +142,8 @@ void measure(lj_ctx* ctx, const Options& o, const std::vector<double>& xyz, int6
   std::fprintf(stderr, "  pairs=%lld max_partners=%d list_builds=%d  %.4g pair-interactions/s\n",
                (long long)m.number_of_pairs, m.max_partners, m.list_builds,
                (double)m.number_of_pairs * (m.half ? 2.0 : 1.0) * o.steps / m.seconds_kernel);
+  if (lj_list_mirror_token(ctx))
+    std::fprintf(stderr, "  cell-tile mirror of the %s list: yes\n", m.list_host ? "loaded" : "built");
   if (print) print_results(p, pn, lay);
 }
 
@@ -237,6 +239,7 @@ int main(int argc, char** argv) {
     else if (s == "--test") o.test = true;
     else if (s == "--all") o.all = true;
     else if (s == "--cache") o.cache = true;
+    else if (s == "--print") o.print = true;
     else if (s == "--soa6") o.soa6 = true;
     else if (s[0] != '-') o.thread_block = std::atoi(s.c_str());
     else { std::fprintf(stderr, "unknown option %s\n", s.c_str()); return 1; }
@@ -278,7 +281,7 @@ int main(int argc, char** argv) {
     }
   } else {
     const std::string name = "force_" + o.variant + "_" + o.layout;
-    measure(ctx, o, xyz, pn, o.layout, o.variant, o.group, name.c_str(), false);
+    measure(ctx, o, xyz, pn, o.layout, o.variant, o.group, name.c_str(), o.print);
   }
   lj_ctx_destroy(ctx);
   return 0;

@@ -1016,3 +1016,102 @@ def test_force_step_parts_interior_plus_boundary_equal_one_step(ctx, torch, sysS
     plain = ctx.makepair(qd)
     with pytest.raises(LJError):
         ctx.force_step(qd, pd, plain, part="interior")
+
+
+# ------------------------------------------------------------------------ lj_list_mirror (round 2)
+def test_list_mirror_of_a_caller_supplied_shuffled_list(ctx, torch, oracle):
+    """The reference always hands the kernel a host-built, random_shfl()-ed or cache-loaded list
+    (cuda/force_cuda.cu:392-397).  lj_list_mirror builds the cell-tile mirror for such a list: the
+    cell-tile kernel then consumes the caller's row order (bit-identical to the per-row kernel with 8
+    lanes per row on the same arrays) and matches the oracle."""
+    from lj_gpu_b200 import LJError, PairList, init_fcc
+    q = init_fcc(1.0, 48.0)
+    pn = len(q)
+    nop_o, ptr_o, lst_o = oracle.makepair(q, full=True)
+    oracle.shuffle_rows(lst_o, nop_o, ptr_o, seed=10)               # the reference's random_shfl (std::shuffle)
+    p_o = np.zeros_like(q)
+    oracle.force_gather(q, p_o, nop_o, ptr_o, lst_o, steps=7, static_q=True)
+    q4 = np.zeros((pn, 4)); q4[:, :3] = q
+    qd = torch.from_numpy(q4).cuda()
+    pl = PairList(torch.from_numpy(nop_o).cuda(), torch.from_numpy(ptr_o.astype(np.int32)).cuda(),
+                  torch.from_numpy(lst_o).cuda(), len(lst_o), int(nop_o.max()))
+    # no mirror yet: explicit request fails, AUTO runs the per-row kernel
+    pd = torch.zeros_like(qd)
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, pl, variant="celltile")
+    assert ctx.list_mirror(qd, pl) == 0                              # every row fits its tile's region
+    assert pl.token != 0
+    launches = ctx.launches
+    ctx.force_loop(qd, pd, pl, loop=7, variant="celltile")
+    assert ctx.launches - launches == 14                             # permute + cell-tile kernel per step
+    pr = torch.zeros_like(qd)
+    ctx.force_loop(qd, pr, pl, loop=7, variant="subwarp", group=8)
+    assert torch.equal(pd, pr)
+    assert np.abs(pd.cpu().numpy()[:, :3] - p_o).max() / np.abs(p_o).max() < TOL_FP64
+    pm = torch.zeros_like(qd)
+    ctx.force_loop(qd, pm, pl, loop=7, variant="celltile", precision="mixed")
+    assert 1e-14 < np.abs(pm.cpu().numpy()[:, :3] - p_o).max() / np.abs(p_o).max() < TOL_MIXED
+    # the stale-list hazard: ANOTHER list written into the same three buffers.  A caller that does not
+    # vouch for the mirror (token 0) gets the per-row kernel and the right answer; the old token would not.
+    half_rows = nop_o.copy(); half_rows[::2] = 0                      # drop every second row's partners
+    pl.number_of_partners.copy_(torch.from_numpy(half_rows).cuda())
+    p2 = np.zeros_like(q)
+    oracle.force_gather(q, p2, half_rows, ptr_o, lst_o, steps=1)
+    fresh = PairList(pl.number_of_partners, pl.pointer, pl.sorted_list, len(lst_o), int(nop_o.max()))
+    pd.zero_()
+    ctx.force_step(qd, pd, fresh)                                     # AUTO, token 0
+    assert np.abs(pd.cpu().numpy()[:, :3] - p2).max() / np.abs(p2).max() < TOL_FP64
+    with pytest.raises(LJError):
+        ctx.force_step(qd, pd, fresh, variant="celltile")             # explicit request needs the token too
+
+
+def test_list_mirror_rows_outside_their_region_take_the_per_row_kernel(ctx, torch, oracle):
+    """A list built with a LONGER search length than the mirror's cell grid assumes: some rows have a
+    partner outside the 5 x 5 pencil region of their tile.  Those rows are left out of the mirror and
+    completed by the per-row kernel; the result is the oracle's either way."""
+    from lj_gpu_b200 import PairList, init_fcc
+    q = init_fcc(0.7, 20.0)
+    pn = len(q)
+    nop_o, ptr_o, lst_o = oracle.makepair(q, search_len=4.1, full=True)
+    p_o = np.zeros_like(q)
+    oracle.force_gather(q, p_o, nop_o, ptr_o, lst_o, steps=3, static_q=True)
+    q3 = torch.from_numpy(q).cuda()
+    pl = PairList(torch.from_numpy(nop_o).cuda(), torch.from_numpy(ptr_o.astype(np.int32)).cuda(),
+                  torch.from_numpy(lst_o).cuda(), len(lst_o), int(nop_o.max()))
+    outside = ctx.list_mirror(q3, pl, search_len=3.3, layout="aos3")
+    assert 0 < outside < pn
+    pd = torch.zeros_like(q3)
+    launches = ctx.launches
+    ctx.force_loop(q3, pd, pl, loop=3, layout="aos3", variant="celltile")
+    assert ctx.launches - launches == 9                               # permute + cell-tile + per-row completion
+    assert np.abs(pd.cpu().numpy() - p_o).max() / np.abs(p_o).max() < TOL_FP64
+    # with the search length the list was built with, every row fits
+    assert ctx.list_mirror(q3, pl, search_len=4.1, layout="aos3") == 0
+    pd.zero_()
+    ctx.force_loop(q3, pd, pl, loop=3, layout="aos3", variant="celltile")
+    assert np.abs(pd.cpu().numpy() - p_o).max() / np.abs(p_o).max() < TOL_FP64
+
+
+def test_cpp_driver_cached_list_runs_the_cell_tile_kernel(tmp_path, oracle):
+    """force_b200 --cache at N >= 3e5: the first run builds on the GPU and writes the reference's text cache,
+    the second loads it (the reference's own flow, cuda/force_cuda.cu:203-227), mirrors the LOADED list
+    (lj_list_mirror inside lj_measure) and prints the oracle's momenta."""
+    exe = os.path.join(ROOT, "lj_gpu_b200", "driver", "force_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    args = [exe, "--density", "1.0", "--L", "70.0", "--variant", "auto", "--layout", "aos4", "--steps", "10", "--cache",
+            "--print"]
+    r1 = subprocess.run(args, capture_output=True, text=True, timeout=600, cwd=tmp_path)
+    assert r1.returncode == 0, r1.stderr
+    assert "Now make pairlist .cache_pair_all.dat." in r1.stderr
+    r2 = subprocess.run(args, capture_output=True, text=True, timeout=600, cwd=tmp_path)
+    assert r2.returncode == 0, r2.stderr
+    assert ".cache_pair_all.dat is successfully loaded." in r2.stderr
+    assert "cell-tile mirror of the loaded list: yes" in r2.stderr
+    q = oracle.init_fcc(1.0, 70.0)
+    assert len(q) >= 300000
+    nop, ptr, lst = oracle.makepair(q, full=True)
+    p = np.zeros_like(q)
+    oracle.force_gather(q, p, nop, ptr, lst, steps=10, static_q=True)
+    from lj_gpu_b200 import print_results
+    assert r2.stdout == print_results(p) and r1.stdout == r2.stdout
