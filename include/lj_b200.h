@@ -395,6 +395,48 @@ LJ_API int lj_ipc_close(lj_ctx* ctx, void* peer_ptr);
  * with a grid of 16-byte P2P loads over NVLink. */
 LJ_API int lj_halo_pull(lj_ctx* ctx, void* local_dst, const void* peer_src, size_t bytes, void* stream);
 
+/* ---------------------------------------------------------------- z-slab decomposition, one process --- */
+/* The decomposed path for a C / C++ caller: ONE process drives `ngpus` devices, one lj_ctx each,
+ * peer access between neighbours, no MPI / NCCL / torch.  The caller supplies the particles in an order in
+ * which slab g is the contiguous index range [slab_begin[g], slab_begin[g+1]) and the ghosts a slab needs
+ * are the last `halo_rows` particles of the slab below and the first `halo_rows` of the slab above -- what the
+ * reference's generator produces (lattice layers z-outermost, cuda/force_cuda.cu:68-77); lj_decomp_plan_fcc
+ * computes both for that lattice.  Each slab keeps [owned | ghosts below | ghosts above] as double4 on its
+ * device, builds its list for the owned rows (LJ_LIST_TILES) and runs the cell-tile kernel in INTERIOR /
+ * BOUNDARY parts around a device-ordered ghost pull (lj_flag_set, lj_halo_pull_sync, lj_flag_wait). */
+typedef struct lj_decomp lj_decomp;
+typedef struct lj_decomp_args {
+  int32_t ngpus;
+  const int32_t* devices;       /* CUDA ordinals, NULL = 0 .. ngpus-1                                   */
+  const double* q_xyz_host;     /* [pn][3] positions, host                                              */
+  int64_t pn;
+  const int64_t* slab_begin;    /* [ngpus + 1], ascending, slab_begin[0] = 0, slab_begin[ngpus] = pn     */
+  int64_t halo_rows;            /* particles exchanged per slab face                                     */
+  double search_len, cutoff, dt; /* 0 = the reference's 3.3, 3.0, 0.001                                  */
+  int32_t precision;            /* lj_precision                                                          */
+  int32_t list_flags;           /* 0 = LJ_LIST_TILES (+ _WIDE for LJ_PREC_MIXED)                          */
+} lj_decomp_args;
+/* slab_begin[ngpus + 1] and halo_rows for the FCC lattice of lj_init_fcc(density, L): whole lattice layers
+ * per slab; LJ_ERR_BAD_ARG when a slab would be thinner than the halo (its ghosts would live two slabs away) */
+LJ_API int lj_decomp_plan_fcc(double density, double L, int32_t ngpus, double search_len, int64_t* slab_begin,
+                              int64_t* halo_rows);
+/* *out is set even on failure so that lj_decomp_last_error() can say why; destroy it either way */
+LJ_API int lj_decomp_create(lj_decomp** out, const lj_decomp_args* args);
+/* `nsteps` force steps on STATIC positions (the reference benchmark): the list is rebuilt every
+ * `rebuild_every` steps (0 = never); overlap != 0: interior tiles run while the ghost pull is in flight.
+ * Asynchronous: follow with lj_decomp_sync / lj_decomp_gather. */
+LJ_API int lj_decomp_step(lj_decomp* d, int32_t nsteps, int32_t rebuild_every, int32_t overlap);
+/* `nsteps` of kick (force step) + drift (q += p dt, owned particles), list rebuilt every `rebuild_every` steps */
+LJ_API int lj_decomp_md(lj_decomp* d, int32_t nsteps, int32_t rebuild_every, int32_t overlap);
+LJ_API int lj_decomp_rebuild(lj_decomp* d);
+LJ_API int lj_decomp_sync(lj_decomp* d);
+/* owned momenta (and positions, may be NULL) of all slabs in the caller's particle order, [pn][3] on the host */
+LJ_API int lj_decomp_gather(lj_decomp* d, double* p_xyz_host, double* q_xyz_host);
+LJ_API int64_t lj_decomp_pairs(lj_decomp* d);          /* list entries over all slabs */
+LJ_API int64_t lj_decomp_launch_count(lj_decomp* d);   /* kernels launched by all its contexts */
+LJ_API const char* lj_decomp_last_error(lj_decomp* d);
+LJ_API int lj_decomp_destroy(lj_decomp* d);
+
 /* Ordering between GPUs without host round trips: 32-bit step counters in peer-visible memory
  * (lj_ipc_alloc'ed, or any device memory a peer can address).  lj_flag_set stores `value` once all
  * earlier work of `stream` is done (system-scope release); lj_flag_wait holds `stream` until the flag

@@ -51,6 +51,12 @@ class LjHaloSeg(C.Structure):
                 ("done_flag", C.c_void_p)]
 
 
+class LjDecompArgs(C.Structure):
+    _fields_ = [("ngpus", C.c_int32), ("devices", C.c_void_p), ("q_xyz_host", C.c_void_p), ("pn", C.c_int64),
+                ("slab_begin", C.c_void_p), ("halo_rows", C.c_int64), ("search_len", C.c_double),
+                ("cutoff", C.c_double), ("dt", C.c_double), ("precision", C.c_int32), ("list_flags", C.c_int32)]
+
+
 class LjListArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("pn", C.c_int64), ("layout", C.c_int32), ("half", C.c_int32),
@@ -125,6 +131,17 @@ PROTOTYPES = {
     "lj_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "lj_ipc_close": (C.c_int, [_vp, _vp]),
     "lj_halo_pull": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "lj_decomp_plan_fcc": (C.c_int, [_dbl, _dbl, _i32, _dbl, _vp, C.POINTER(_i64)]),
+    "lj_decomp_create": (C.c_int, [C.POINTER(_vp), C.POINTER(LjDecompArgs)]),
+    "lj_decomp_step": (C.c_int, [_vp, _i32, _i32, _i32]),
+    "lj_decomp_md": (C.c_int, [_vp, _i32, _i32, _i32]),
+    "lj_decomp_rebuild": (C.c_int, [_vp]),
+    "lj_decomp_sync": (C.c_int, [_vp]),
+    "lj_decomp_gather": (C.c_int, [_vp, _vp, _vp]),
+    "lj_decomp_pairs": (_i64, [_vp]),
+    "lj_decomp_launch_count": (_i64, [_vp]),
+    "lj_decomp_last_error": (C.c_char_p, [_vp]),
+    "lj_decomp_destroy": (C.c_int, [_vp]),
     "lj_flag_set": (C.c_int, [_vp, _vp, _i32, _vp]),
     "lj_flag_wait": (C.c_int, [_vp, _vp, _i32, _vp]),
     "lj_halo_pull_sync": (C.c_int, [_vp, C.POINTER(LjHaloSeg), _i32, _vp]),

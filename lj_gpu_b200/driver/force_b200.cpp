@@ -36,8 +36,11 @@ struct Options {
   double density = 0.5, L = 50.0;
   std::string layout = "aos4", variant = "auto", prec = "fp64";
   int group = 0, steps = 100, rebuild_every = 0;
-  bool graph = false, test = false, all = false, cache = false, soa6 = false, print = false;
+  bool graph = false, test = false, all = false, cache = false, soa6 = false, print = false, md = false;
+  int gpus = 1;
 };
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 [[noreturn]] void die(lj_ctx* ctx, int rc, const char* where) {
   std::fprintf(stderr, "%s: %s: %s\n", where, lj_status_string(rc), ctx ? lj_last_error_string(ctx) : "");
@@ -147,6 +150,43 @@ void measure(lj_ctx* ctx, const Options& o, const std::vector<double>& xyz, int6
   if (print) print_results(p, pn, lay);
 }
 
+// --gpus N: the same benchmark on N GPUs of this box from ONE process (lj_decomp_*): z-slabs of lattice
+// layers, ghost positions pulled over NVLink every step, interior tiles overlapped with the pull.
+// No counterpart in the reference (single GPU); timing lines in the reference's format.
+int run_decomposed(const Options& o, const std::vector<double>& xyz, int64_t pn) {
+  std::vector<int64_t> slab((size_t)o.gpus + 1);
+  int64_t halo_rows = 0;
+  int rc = lj_decomp_plan_fcc(o.density, o.L, o.gpus, 3.3, slab.data(), &halo_rows);
+  if (rc) {
+    std::fprintf(stderr, "lj_decomp_plan_fcc: %s (a slab thinner than the halo: fewer GPUs or a larger box)\n", lj_status_string(rc));
+    return 1;
+  }
+  lj_decomp_args a{};
+  a.ngpus = o.gpus; a.q_xyz_host = xyz.data(); a.pn = pn; a.slab_begin = slab.data(); a.halo_rows = halo_rows;
+  a.search_len = 3.3; a.cutoff = 3.0; a.dt = 0.001;
+  a.precision = o.prec == "mixed" ? LJ_PREC_MIXED : LJ_PREC_FP64;
+  lj_decomp* d = nullptr;
+  const double t_all = now();
+  rc = lj_decomp_create(&d, &a);
+  if (rc) { std::fprintf(stderr, "lj_decomp_create: %s: %s\n", lj_status_string(rc), lj_decomp_last_error(d)); return 1; }
+  const double t_calc = now();
+  rc = o.md ? lj_decomp_md(d, o.steps, o.rebuild_every, 1) : lj_decomp_step(d, o.steps, o.rebuild_every, 1);
+  if (!rc) rc = lj_decomp_sync(d);
+  const double sec = now() - t_calc;
+  std::vector<double> p((size_t)pn * 3);
+  if (!rc) rc = lj_decomp_gather(d, p.data(), nullptr);
+  if (rc) { std::fprintf(stderr, "lj_decomp: %s: %s\n", lj_status_string(rc), lj_decomp_last_error(d)); return 1; }
+  const char* name = o.md ? "force_decomposed_md" : "force_decomposed";
+  std::fprintf(stderr, "N=%d, %s_%dgpus %f [sec]\n", (int)pn, name, o.gpus, now() - t_all);
+  std::fprintf(stderr, "N=%d, %s_%dgpus %f [sec] (without Host<->Device)\n", (int)pn, name, o.gpus, sec);
+  std::fprintf(stderr, "  pairs=%lld slabs=%d halo_rows=%lld  %.4g pair-interactions/s  launches=%lld\n",
+               (long long)lj_decomp_pairs(d), o.gpus, (long long)halo_rows,
+               (double)lj_decomp_pairs(d) * o.steps / sec, (long long)lj_decomp_launch_count(d));
+  if (o.print) print_results(p, pn, LJ_AOS_D3);
+  lj_decomp_destroy(d);
+  return 0;
+}
+
 // The OpenACC SoA program (openacc/force_oacc_soa.cpp) on the new library: six separately
 // allocated arrays qx,qy,qz,px,py,pz (:17-22), makepair + CSR list (force_reactless, OACC_REF) or
 // the transposed list (force_reactless_memopt, OACC_TRANS), LOOP force calls between one upload
@@ -240,6 +280,8 @@ int main(int argc, char** argv) {
     else if (s == "--all") o.all = true;
     else if (s == "--cache") o.cache = true;
     else if (s == "--print") o.print = true;
+    else if (s == "--gpus") o.gpus = std::atoi(next());
+    else if (s == "--md") o.md = true;
     else if (s == "--soa6") o.soa6 = true;
     else if (s[0] != '-') o.thread_block = std::atoi(s.c_str());
     else { std::fprintf(stderr, "unknown option %s\n", s.c_str()); return 1; }
@@ -254,6 +296,8 @@ int main(int argc, char** argv) {
   std::vector<double> xyz((size_t)need * 3);
   const int64_t pn = lj_init_fcc(o.density, o.L, xyz.data(), need, &cells);
   if (pn <= 0) { std::fprintf(stderr, "empty system\n"); return 1; }
+
+  if (o.gpus > 1) return run_decomposed(o, xyz, pn);
 
   lj_ctx* ctx = nullptr;
   int rc = lj_ctx_create(&ctx, 0);

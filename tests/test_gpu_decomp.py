@@ -102,3 +102,72 @@ def test_two_gpu_moving_particles_match_the_oracle(mode, tmp_path, md_oracle, or
     assert np.abs(q - q0).max() > 1e-3                               # the particles really moved
     assert np.abs(q_got - q).max() < 1e-11
     assert np.abs(p_got - p).max() / np.abs(p).max() < 1e-11        # 40 dependent steps: rounding compounds
+
+
+# ------------------------------------------------------------------------ the same behind the C ABI, ONE process
+def _decomp_capi(q, ngpus, steps, rebuild_every, md=False, dt=0.001, prec=0):
+    """lj_decomp_* through ctypes: one process, `ngpus` contexts on `ngpus` devices."""
+    import ctypes as C
+
+    from lj_gpu_b200 import _capi
+    lib = _capi.load()
+    pn = len(q)
+    slab = (C.c_int64 * (ngpus + 1))()
+    halo = C.c_int64(0)
+    assert lib.lj_decomp_plan_fcc(DENSITY, L, ngpus, 3.3, slab, C.byref(halo)) == 0
+    a = _capi.LjDecompArgs()
+    qc = np.ascontiguousarray(q, np.float64)
+    a.ngpus, a.q_xyz_host, a.pn = ngpus, qc.ctypes.data, pn
+    a.slab_begin, a.halo_rows = C.cast(slab, C.c_void_p), halo.value
+    a.search_len, a.cutoff, a.dt, a.precision = 3.3, 3.0, dt, prec
+    d = C.c_void_p()
+    rc = lib.lj_decomp_create(C.byref(d), C.byref(a))
+    assert rc == 0, lib.lj_decomp_last_error(d)
+    rc = (lib.lj_decomp_md if md else lib.lj_decomp_step)(d, steps, rebuild_every, 1)
+    assert rc == 0, lib.lj_decomp_last_error(d)
+    p = np.zeros((pn, 3)); qo = np.zeros((pn, 3))
+    assert lib.lj_decomp_gather(d, p.ctypes.data, qo.ctypes.data) == 0, lib.lj_decomp_last_error(d)
+    pairs, launches = lib.lj_decomp_pairs(d), lib.lj_decomp_launch_count(d)
+    assert lib.lj_decomp_destroy(d) == 0
+    return p, qo, pairs, launches
+
+
+def test_capi_decomposition_two_contexts_two_devices_one_process(static_oracle, md_oracle, oracle):
+    """lj_decomp_create/step/md/gather: two lj_ctx on two devices driven from ONE host thread (what a C++
+    caller of the reference's driver would do) -- the per-device kernel attributes, the device guard at
+    every entry point and the peer-memory flag handshake all have to hold.  Checker: the oracle."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    q, ref = static_oracle
+    nop, _, lst = oracle.makepair(q, full=True)
+    p, qo, pairs, launches = _decomp_capi(q, 2, STEPS, 10)
+    assert pairs == len(lst) and launches > 4 * STEPS
+    assert np.array_equal(qo, q)
+    assert np.abs(p - ref).max() / np.abs(ref).max() < 1e-12
+    pm, _, _, _ = _decomp_capi(q, 2, STEPS, 10, prec=1)                # mixed precision on the slabs
+    assert 1e-14 < np.abs(pm - ref).max() / np.abs(ref).max() < 1e-5
+    qm, pmd = md_oracle
+    p, qo, _, _ = _decomp_capi(q, 2, MD_STEPS, MD_REBUILD, md=True, dt=MD_DT)
+    assert np.abs(qo - qm).max() < 1e-11
+    assert np.abs(p - pmd).max() / np.abs(pmd).max() < 1e-11
+    # one slab is the plain single-GPU run through the same entry points
+    p1, _, _, _ = _decomp_capi(q, 1, STEPS, 10)
+    assert np.abs(p1 - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_cpp_driver_gpus_2(static_oracle):
+    from conftest import ROOT
+    import subprocess
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "lj_gpu_b200", "driver", "force_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    r = subprocess.run([exe, "--gpus", "2", "--density", str(DENSITY), "--L", str(L), "--steps", str(STEPS),
+                        "--rebuild-every", "10", "--print"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "force_decomposed_2gpus" in r.stderr and "(without Host<->Device)" in r.stderr
+    from lj_gpu_b200 import print_results
+    assert r.stdout == print_results(static_oracle[1])
