@@ -129,6 +129,13 @@ struct ct_params {
 template <int LAYOUT, bool MX, int NCONS, int NB>
 __global__ void __launch_bounds__((NCONS + 2) * 32, NB)
 lj_celltile_force(const ct_params P) {
+#if LJ_DIAG  // per-warp cycle counters and kernel-surgery modes exist in diagnostic builds only
+  long long* const dbgp = P.dbg;
+  const int modev = P.mode;
+#else
+  constexpr long long* dbgp = nullptr;
+  constexpr int modev = 0;
+#endif
   constexpr uint32_t RB = MX ? 16u : 24u;  // bytes per staged position record
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t tfull[kCtMaxL], tempty[kCtMaxL];
@@ -187,12 +194,12 @@ lj_celltile_force(const ct_params P) {
     int tseq = 0, tslot = 0;             // tile being assembled: sequence number, slot (ring of rl)
     int done = 0, dslot = 0, dphase = 0; // tiles known to be released: [0, done)
     long long p_idle = 0;                // diagnostics: cycles spent waiting for the consumers
-    const long long p_begin = P.dbg ? clock64() : 0;
+    const long long p_begin = dbgp ? clock64() : 0;
     auto ensure_done = [&](int q) {      // block until tile q has been released by every consumer
       while (done <= q) {
-        const long long w0 = P.dbg ? clock64() : 0;
+        const long long w0 = dbgp ? clock64() : 0;
         mbar_wait(&tempty[dslot], dphase);
-        if (P.dbg) p_idle += clock64() - w0;
+        if (dbgp) p_idle += clock64() - w0;
         done++;
         if (++dslot == rl) { dslot = 0; dphase ^= 1; }
       }
@@ -287,7 +294,7 @@ lj_celltile_force(const ct_params P) {
           const uint32_t pb_next = __shfl_down_sync(0xffffffffu, ey.y, 1);
           const uint32_t len = lane < kTileYPencils ? pb_next - ey.y : 0u;
           uint32_t ylen = __shfl_sync(0xffffffffu, ey.y, 5);
-          if (P.mode & 16) ylen = 0;  // diagnostics: no y-row copies
+          if (modev & 16) ylen = 0;  // diagnostics: no y-row copies
           if ((int)ylen > cap_y - 8) __trap();
           if (lane == 0) {
             yrel[yslot] = tbase + min(i, ntile - 1);  // the tile that has it as its oldest row
@@ -331,7 +338,7 @@ lj_celltile_force(const ct_params P) {
           const uint32_t s0 = __shfl_sync(0xffffffffu, et.x, 0), ns = __shfl_sync(0xffffffffu, et.y, 0);
           const uint32_t u0 = __shfl_sync(0xffffffffu, et.z, 0), units = __shfl_sync(0xffffffffu, et.w, 0);
           const uint32_t self0 = __shfl_sync(0xffffffffu, et.x, 1);
-          const uint32_t units_c = (P.mode & 32) ? 0u : units, ns_c = (P.mode & 64) ? 0u : ns;  // diagnostics
+          const uint32_t units_c = (modev & 32) ? 0u : units, ns_c = (modev & 64) ? 0u : ns;  // diagnostics
           if ((int)units > P.cap_units || (int)ns > P.cap_rows) __trap();
           unsigned char* dst = lbase + (size_t)tslot * P.lslot_bytes;
           if (lane == 0) {
@@ -353,8 +360,8 @@ lj_celltile_force(const ct_params P) {
     if (lane == 0) {
       if (!isY) hdr[tslot].ns = -1;
       mbar_arrive(&tfull[tslot]);
-      if (P.dbg) {  // producer records: {idle, 0, tiles, total}
-        long long* d = P.dbg + ((size_t)gridDim.x * NCONS + 2 * blockIdx.x + (isY ? 0 : 1)) * 4;
+      if (dbgp) {  // producer records: {idle, 0, tiles, total}
+        long long* d = dbgp + ((size_t)gridDim.x * NCONS + 2 * blockIdx.x + (isY ? 0 : 1)) * 4;
         d[0] = p_idle; d[1] = 0; d[2] = tseq; d[3] = clock64() - p_begin;
       }
     }
@@ -382,16 +389,16 @@ lj_celltile_force(const ct_params P) {
   const uint32_t dummy = (uint32_t)cap_y - 1u;
   int tslot = 0, tphase = 0;
   long long t_wait = 0, t_work = 0, n_quads = 0;
-  const long long t_begin = P.dbg ? clock64() : 0;
+  const long long t_begin = dbgp ? clock64() : 0;
   int first = warp;  // quads are dealt round-robin over the warps ACROSS tiles: tiles hold fewer
                      // quads than there are warps, a per-tile deal would leave the high warps idle
   for (;;) {
     {
       long long tw0 = 0;
-      if (P.dbg) tw0 = clock64();
+      if (dbgp) tw0 = clock64();
       mbar_wait(&tfull[tslot], tphase);
       long long tw1 = 0;
-      if (P.dbg) { tw1 = clock64(); t_wait += tw1 - tw0; }
+      if (dbgp) { tw1 = clock64(); t_wait += tw1 - tw0; }
       const int4 h = *reinterpret_cast<const int4*>(&hdr[tslot]);  // ns, self0, u0, yslot0
       const int ns = h.x;
       if (ns < 0) break;  // end marker
@@ -400,7 +407,7 @@ lj_celltile_force(const ct_params P) {
       int quad = first;
       const bool had_quad = quad < nquads;
       first = (first + NCONS - nquads % NCONS) % NCONS;
-      if (quad < nquads && (P.mode & 15) != 3) {
+      if (quad < nquads && (modev & 15) != 3) {
         const int self0 = h.y;
         const uint32_t u0 = (uint32_t)h.z;
         const unsigned char* lptr = lbase + (size_t)tslot * P.lslot_bytes;
@@ -423,7 +430,7 @@ lj_celltile_force(const ct_params P) {
           // it otherwise re-derives yslot0 * cap_y inside the pair loop, one IMAD per pair
           const uint32_t c1 = __shfl_sync(0xffffffffu, ybase_s + off0 * 16u, 0);
 #if LJ_CT_DIAG
-          const int dmode = P.mode & 15;
+          const int dmode = modev & 15;
 #endif
           const int ngroups = nquads;  // groups of R rows, dealt round-robin across tiles like the FP64 quads
           int grp = quad;
@@ -607,13 +614,13 @@ lj_celltile_force(const ct_params P) {
         }  // FP64
       }
       __syncwarp();
-      if (P.dbg && had_quad) t_work += clock64() - tw1;
+      if (dbgp && had_quad) t_work += clock64() - tw1;
       if (lane == 0) mbar_arrive(&tempty[tslot]);  // this warp is through with the tile
       if (++tslot == rl) { tslot = 0; tphase ^= 1; }
     }
   }
-  if (P.dbg && lane == 0) {
-    long long* d = P.dbg + ((size_t)blockIdx.x * NCONS + warp) * 4;
+  if (dbgp && lane == 0) {
+    long long* d = dbgp + ((size_t)blockIdx.x * NCONS + warp) * 4;
     d[0] = t_wait; d[1] = t_work; d[2] = n_quads; d[3] = clock64() - t_begin;
   }
 }
