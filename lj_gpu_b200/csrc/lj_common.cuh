@@ -138,6 +138,10 @@ struct lj_ctx {
   std::unordered_map<const void*, size_t> func_smem;  // kernel -> opted-in dynamic shared memory
   std::unordered_map<const void*, int> func_occ;      // kernel -> resident CTAs per SM (occupancy query)
 
+  // lj_measure: the tile engine allocates sorted_list itself right after its count pass (no sizing build)
+  cudaEvent_t ev_copy = nullptr;  // lj_measure: copy-stream upload of p <-> the caller-visible stream
+  int32_t* alloc_list = nullptr;
+  int64_t alloc_capacity = 0;
   unsigned int* pull_counter = nullptr;  // lj_halo_pull_sync: blocks of the running copy that have finished
   long long* diag_buf = nullptr;  // LJ_DIAG builds only: per-warp cycle counters of the cell-tile kernel
   int diag_dumps = 0;
@@ -212,6 +216,10 @@ static inline bool lj_diag_set(const char* name) {
     if (cudaGetDevice(&cur__) != cudaSuccess || cur__ != (ctx)->device)        \
       LJ_CUDA((ctx), cudaSetDevice((ctx)->device));                            \
   } while (0)
+
+// (internal) lj_list_args.flags: sorted_list = NULL, capacity = 0 -> the tile engine allocates the list from the
+// context's pool once its count pass knows the total and leaves it in ctx->alloc_list / alloc_capacity
+constexpr int LJ_LIST_ALLOC_INTERNAL = 1 << 30;
 
 // NULL is the CUDA legacy default stream, exactly as for a kernel launch: the reference runs
 // everything there (cuda/force_cuda.cu:334) and torch hands out 0 for its default stream.

@@ -1061,7 +1061,8 @@ k_tile_count(int64_t pn, int64_t r0, int64_t r1, const grid_ext* __restrict__ ge
       if (nw > 64) { if (lg == 0) atomicOr(&tot->overflow, 16); nw = 64; }
       const int iters = __reduce_max_sync(0xffffffffu, (nw + kTeLanes - 1) / kTeLanes);
       const float4* __restrict__ cand = reg + (e.base + (uint32_t)w0 + (uint32_t)lg);
-      unsigned ha = 0, hb = 0, band = 0;  // band: bit it = row a, bit 8 + it = row b
+      // la/lb: r2 < lo (hit for sure), ua/ub: r2 < hi (hit or inside the error band), one predicated OR each
+      unsigned ha = 0, hb = 0, ua = 0, ub = 0;
       unsigned bit = 1u;
       int left = nw - lg;  // this lane's candidates: idx = lg, lg + 8, ... < nw
 #pragma unroll 1
@@ -1072,11 +1073,12 @@ k_tile_count(int64_t pn, int64_t r0, int64_t r1, const grid_ext* __restrict__ ge
         const float bx = mb.x - c.x, by = mb.y - c.y, bz = mb.z - c.z;
         const float r2a = fmaf(az, az, fmaf(ay, ay, ax * ax));
         const float r2b = fmaf(bz, bz, fmaf(by, by, bx * bx));
-        if (r2a < lo_f) ha |= b1;
-        if (r2b < lo_f) hb |= b1;
-        if (r2a >= lo_f && r2a < hi_f) band |= b1;
-        if (r2b >= lo_f && r2b < hi_f) band |= b1 << 8;
+        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(ha) : "f"(r2a), "f"(lo_f), "r"(b1));
+        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(hb) : "f"(r2b), "f"(lo_f), "r"(b1));
+        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(ua) : "f"(r2a), "f"(hi_f), "r"(b1));
+        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(ub) : "f"(r2b), "f"(hi_f), "r"(b1));
       }
+      unsigned band = (ua & ~ha) | ((ub & ~hb) << 8);  // band: bit it = row a, bit 8 + it = row b
       if (p == 12) {  // a row is not its own neighbour
         if ((selfa & 7) == lg) ha &= ~(1u << (selfa >> 3));
         if ((selfb & 7) == lg) hb &= ~(1u << (selfb >> 3));
@@ -1225,7 +1227,8 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
     const int padded = ((want + 7) >> 3) << 3;
     if (staged) {
       __syncwarp(gmask);
-      for (int k = lg; k < padded; k += kTeLanes) {
+#pragma unroll 4
+      for (int k = lg; k < padded; k += kTeLanes) {  // (unrolled: four gathers of tl_order in flight per lane)
         const bool real = k < want;
         tl_list[base + k] = real ? sm_l[k] : dummy;
         if (pub && real) list[pbase + k] = tl_order[sm_m[k]];
@@ -1709,8 +1712,12 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
 // masks, a region that does not fit in shared memory, mask scratch too large, > 2^32 mirror units);
 // the binning has been done, the caller continues with the round-1 engine.
 template <int LAYOUT>
-static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st, bool* done) {
+static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a_in, cudaStream_t st, bool* done) {
   *done = false;
+  lj_list_args a_local = *a_in;
+  lj_list_args* a = &a_local;
+  const bool self_alloc = (a->flags & LJ_LIST_ALLOC_INTERNAL) && !a->sorted_list && a->capacity == 0;
+  ctx->alloc_list = nullptr; ctx->alloc_capacity = 0;
   const int64_t pn = a->pn;
   int64_t r0 = a->row_begin, r1 = a->row_end;
   if (r0 == 0 && r1 == 0) r1 = pn;
@@ -1803,7 +1810,7 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st,
     k_scan_down<uint32_t><<<row_tiles, kScanThreads, 0, st>>>(nop_u, pn, nullptr, ctx->scan_tmp,
                                                                reinterpret_cast<uint32_t*>(a->pointer));
   LJ_LAUNCHED(ctx);
-  k_finish_totals<<<1, 1, 0, st>>>(ctx->totals, a->capacity, a->pointer64);
+  k_finish_totals<<<1, 1, 0, st>>>(ctx->totals, self_alloc ? (int64_t)0x7fffffffffffffffLL : a->capacity, a->pointer64);
   LJ_LAUNCHED(ctx);
   ctx->last_capacity = a->capacity;
   const unsigned utiles = (unsigned)blocks_for(pn + 1, kScanTile);
@@ -1847,6 +1854,13 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st,
     const int64_t cap = (int64_t)g.total_units + (int64_t)g.total_units / 32 + 1024;
     if ((rc = tile_alloc(ctx, (void**)&ctx->tl_list, 16 * (size_t)cap, st))) return rc;
     ctx->tl_list_cap = cap;
+  }
+  if (self_alloc) {  // lj_measure: the total is known now -- no separate sizing build
+    const int64_t total = (int64_t)ctx->totals_host->total;
+    ctx->alloc_capacity = total + total / 64 + 1024;  // headroom for later rebuilds
+    LJ_CUDA(ctx, cudaMallocAsync((void**)&ctx->alloc_list, sizeof(int32_t) * (size_t)ctx->alloc_capacity, ctx->pool, st));
+    a->sorted_list = ctx->alloc_list; a->capacity = ctx->alloc_capacity;
+    ctx->last_capacity = a->capacity;
   }
   const size_t smem_replay = smem_tab + (size_t)(kTeThreads / kTeLanes) * kTeRowCap * 6;
   LJ_FUNC_SMEM(ctx, k_tile_replay<true>, smem_replay);

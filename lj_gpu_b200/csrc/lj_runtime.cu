@@ -482,13 +482,29 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
   int64_t capacity = 0, npairs = 0;
   int32_t max_np = 0;
   int ptr64 = own_list ? 1 : 0;  // int64 offsets whenever the library builds the list itself
+  bool p_on_copy_stream = false;
 #define M_TRY(x) do { rc = (x); if (rc) goto done; } while (0)
   M_TRY(lj_dev_alloc(ctx, qbytes, &q, st));
   M_TRY(lj_dev_alloc(ctx, qbytes, &p, st));
   M_TRY(lj_dev_alloc(ctx, sizeof(int32_t) * pn, (void**)&nop, st));
   M_TRY(lj_dev_alloc(ctx, (ptr64 ? 8 : 4) * (size_t)pn, &ptr, st));
   M_TRY(lj_upload(ctx, q, m->q_host, qbytes, st));
-  M_TRY(lj_upload(ctx, p, m->p_host, qbytes, st));
+  // p is not needed before the first force step: its upload runs on the copy stream behind the list build
+  {
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, m->p_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned && ctx->copy_stream && ctx->copy_stream != st) {
+      if (!ctx->ev_copy) LJ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+      if ((rc = cudaEventRecord(ctx->ev_copy, st)) != cudaSuccess) goto cuda_fail;   // p was allocated on st
+      if ((rc = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0)) != cudaSuccess) goto cuda_fail;
+      if ((rc = cudaMemcpyAsync(p, m->p_host, qbytes, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess) goto cuda_fail;
+      if ((rc = cudaEventRecord(ctx->ev_copy, ctx->copy_stream)) != cudaSuccess) goto cuda_fail;
+      p_on_copy_stream = true;
+    } else {
+      M_TRY(lj_upload(ctx, p, m->p_host, qbytes, st));
+    }
+  }
   m->h2d_bytes += 2 * (int64_t)qbytes;
 
   {
@@ -504,14 +520,26 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
         (m->variant == LJ_VARIANT_CELLTILE || (m->variant == LJ_VARIANT_AUTO && pn >= 300000)))
       la.flags |= LJ_LIST_TILES;
     if (own_list) {
-      // first build sizes the list: count pass only needs capacity 0 to learn the total
+      // With the tile engine the list is allocated by the build itself right after its count pass
+      // (LJ_LIST_ALLOC_INTERNAL).  Otherwise the capacity protocol: a sizing call (count pass only:
+      // capacity 0 returns the total), then the real build.
       la.sorted_list = nullptr; la.capacity = 0;
+      const int user_flags = la.flags;
+      if ((la.flags & LJ_LIST_TILES) && !(la.flags & LJ_LIST_SORT_ROWS)) la.flags |= LJ_LIST_ALLOC_INTERNAL;
       rc = lj_build_list(ctx, &la, &npairs, st);
-      if (rc != LJ_OK && rc != LJ_ERR_CAPACITY) goto done;
-      capacity = npairs + npairs / 64 + 1024;  // headroom for later rebuilds
-      M_TRY(lj_dev_alloc(ctx, sizeof(int32_t) * (size_t)capacity, (void**)&list, st));
-      la.sorted_list = list; la.capacity = capacity;
-      M_TRY(lj_build_list(ctx, &la, &npairs, st));
+      la.flags = user_flags;
+      if (rc == LJ_OK && ctx->alloc_list) {
+        list = ctx->alloc_list; capacity = ctx->alloc_capacity;
+        ctx->alloc_list = nullptr;
+        // the mirror was registered for the internally allocated array: same pointer from here on
+        la.sorted_list = list; la.capacity = capacity;
+      } else {
+        if (rc != LJ_OK && rc != LJ_ERR_CAPACITY) goto done;
+        capacity = npairs + npairs / 64 + 1024;  // headroom for later rebuilds
+        M_TRY(lj_dev_alloc(ctx, sizeof(int32_t) * (size_t)capacity, (void**)&list, st));
+        la.sorted_list = list; la.capacity = capacity;
+        M_TRY(lj_build_list(ctx, &la, &npairs, st));
+      }
       M_TRY(lj_list_result(ctx, &npairs, &max_np, st));
       m->list_builds = 1;
     } else {
@@ -543,6 +571,7 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
     fa.plane_stride = m->plane_stride;
     fa.mirror_token = lj_list_mirror_token(ctx);  // the list above is the library's own build
 
+    if (p_on_copy_stream && cudaStreamWaitEvent(st, ctx->ev_copy, 0) != cudaSuccess) { rc = cudaErrorUnknown; goto cuda_fail; }
     M_TRY(lj_sync(ctx, st));
     const double t_k0 = now_s();
     int done_steps = 0;
@@ -568,7 +597,11 @@ int lj_measure(lj_ctx* ctx, lj_measure_args* m) {
   m->d2h_bytes += (int64_t)qbytes;
   m->number_of_pairs = npairs;
   m->max_partners = max_np;
+  goto done;
+cuda_fail:
+  rc = lj_set_error(ctx, LJ_ERR_CUDA, "lj_measure", cudaGetErrorString((cudaError_t)rc));
 done:
+  if (p_on_copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   lj_dev_free(ctx, q, st);
   lj_dev_free(ctx, p, st);
   lj_dev_free(ctx, list, st);
