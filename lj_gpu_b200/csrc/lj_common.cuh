@@ -384,12 +384,27 @@ __device__ __forceinline__ void lj_pair(double dx, double dy, double dz, double 
                                         long long cl2_bits, double& fx, double& fy,
                                         double& fz) {
   const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+#if LJ_PAIR_FSEL
+  // Mask the scalar, not the three products: ptxas turns a guarded accumulation (also one written
+  // as @p fma in PTX) into six FSELs per pair, masking df costs two (the reference's "ifless"
+  // form, kernel.cuh:59).
   const double x = fast_rcp(r2);
   const double x3 = x * x * x;
   const double t = fma(-c48, x3, c24);
-  // Mask the scalar, not the three products: ptxas turns a guarded accumulation into six
-  // FSELs per pair, masking df costs two (the reference's "ifless" form, kernel.cuh:59).
   const double df = (__double_as_longlong(r2) <= cl2_bits) ? (x * x3) * t : 0.0;
+#else
+  // Mask the SEED of the reciprocal: MUFU.RCP64H delivers only a high word (the low word of
+  // rcp.approx.ftz.f64 is zero by definition), so one 32-bit select makes x0 = +0 exactly, and then
+  // e = 1, x = fma(0, 2, 0) = 0, x^3 = 0, df = 0 * c24 = 0: a pair beyond the cutoff adds exactly
+  // zero, at the cost of one SEL instead of two FSEL on df.
+  double x0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(r2));
+  x0 = __hiloint2double((__double_as_longlong(r2) <= cl2_bits) ? __double2hiint(x0) : 0, 0);
+  const double e = fma(-r2, x0, 1.0);
+  const double x = fma(x0, fma(e, e, e), x0);
+  const double x3 = x * x * x;
+  const double df = (x * x3) * fma(-c48, x3, c24);
+#endif
   fx = fma(df, dx, fx);
   fy = fma(df, dy, fy);
   fz = fma(df, dz, fz);

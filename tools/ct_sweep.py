@@ -58,8 +58,11 @@ def main():
 
     for rows in (args.rows.split(",") if args.rows else [""]):
         for prec in args.prec.split(","):
+            wide = rows == "wide"            # LJ_LIST_TILES_WIDE (product builds too); numbers need DIAG=1
+            if wide:
+                rows = ""
             setenv("LJ_TILE_ROWS=%s" % rows if rows else "")
-            pl = ctx.makepair(qd, tiles="wide" if prec == "mixed" and not rows else True)
+            pl = ctx.makepair(qd, tiles="wide" if wide or (prec == "mixed" and not rows) else True)
             P = pl.number_of_pairs
             p_ref = torch.zeros_like(qd)
             ctx.force_step(qd, p_ref, pl, variant="subwarp", group=8)
@@ -73,10 +76,12 @@ def main():
                 err = (p_new - p_ref).abs().max().item() / scale
                 ok = (err == 0.0) if prec == "fp64" else (0 < err < 1e-5)
                 ms = timeit(lambda: ctx.force_step(qd, p_new, pl, variant="celltile", precision=prec), args.reps)
-                print("rows=%-3s %-5s %-44s %.4f ms  %5.1f %% of 6535 GB/s  err %.2e %s" % (
-                    rows or "def", prec, cfg or "(default)", ms, 100 * algo / (ms * 1e-3) / 6535.1e9, err,
+                print("rows=%-4s %-5s %-44s %.4f ms  %5.1f %% of 6535 GB/s  err %.2e %s" % (
+                    "wide" if wide else (rows or "def"), prec, cfg or "(default)", ms, 100 * algo / (ms * 1e-3) / 6535.1e9, err,
                     "ok" if ok else "MISMATCH"), flush=True)
             del pl
+            if wide:
+                rows = "wide"
 
 
 if __name__ == "__main__":

@@ -16,7 +16,6 @@ set -u
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
 task=${1:-check}; shift || true
-torchrun_n() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$1" --master-addr 127.0.0.1 --master-port $((29500 + $1)) "${@:2}"; }
 case "$task" in
   check)
     timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
@@ -28,7 +27,7 @@ case "$task" in
     timeout -s KILL 1200 python -m pytest tests/test_gpu_decomp.py -q 2>&1 | tail -6 | tee gpurun_out/pytest_decomp_2gpu.log ;;
   scale)
     for n in "$@"; do
-      if [ "$n" -eq 1 ]; then CMD="python bench.py"; else CMD="torchrun_n $n bench.py"; fi
+      if [ "$n" -eq 1 ]; then CMD="python bench.py"; else CMD="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py"; fi
       timeout -s KILL 1500 $CMD --gpus "$n" --steps "${STEPS:-100}" --warmup "${WARMUP:-10}" > "gpurun_out/scale_n$n.json" 2> "gpurun_out/scale_n$n.err"; echo "bench n=$n rc=$?"
       python - "$n" <<'PY'
 import json, sys
