@@ -451,7 +451,13 @@ lj_celltile_force(const ct_params P) {
               if (valid) m = meta[r];
               const int np = m.x;
               const int trips = ((np + 7) >> 3) * (8 / G);  // rows are padded to 8 entries
+#if LJ_CT_TMIN_ALL
               const int tmin = __reduce_min_sync(0xffffffffu, trips);
+#else
+              // rows past the end of the tile (the last quad of three tiles in four) do not shorten the unrolled
+              // loop: they walk the tile's first entries against the dummy point (every pair masked)
+              const int tmin = __reduce_min_sync(0xffffffffu, valid ? trips : 0x7fffffff);
+#endif
               const int tmax = __reduce_max_sync(0xffffffffu, trips);
               const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lgx;
               const int4 me = fetchx(valid ? (uint32_t)(self0 + r) : dummy);
@@ -574,7 +580,13 @@ lj_celltile_force(const ct_params P) {
               if (valid) m = meta[r];
               const int np = m.x;
               const int trips = (np + 7) >> 3;
+#if LJ_CT_TMIN_ALL
               const int tmin = __reduce_min_sync(0xffffffffu, trips);
+#else
+              // rows past the end of the tile (the last quad of three tiles in four) do not shorten the unrolled
+              // loop: they walk the tile's first entries against the dummy point (every pair masked)
+              const int tmin = __reduce_min_sync(0xffffffffu, valid ? trips : 0x7fffffff);
+#endif
               const int tmax = __reduce_max_sync(0xffffffffu, trips);
               const uint16_t* __restrict__ e = lst + ((uint32_t)m.y - u0) * 8u + lg;
               double xi, yi, zi;
@@ -715,12 +727,15 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
       std::vector<long long> h((size_t)4 * (NCONS + 2) * grid);
       cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       double w = 0, k = 0, q = 0, t = 0, tmax = 0, tmin = 1e30, qmax = 0, qmin = 1e30;
+      double wlo = 0, whi = 0, klo = 0, khi = 0;  // per CTA: least / most waiting warp, least / most working warp
       for (int b = 0; b < grid; b++) {
-        double qb = 0, tb = 0;
+        double qb = 0, tb = 0, w0 = 1e30, w1 = 0, k0 = 1e30, k1 = 0;
         for (int c = 0; c < NCONS; c++) {
           const long long* d = &h[((size_t)b * NCONS + c) * 4];
           w += d[0]; k += d[1]; q += d[2]; t += d[3]; qb += d[2]; if (d[3] > tb) tb = d[3];
+          if (d[0] < w0) w0 = d[0]; if (d[0] > w1) w1 = d[0]; if (d[1] < k0) k0 = d[1]; if (d[1] > k1) k1 = d[1];
         }
+        wlo += w0; whi += w1; klo += k0; khi += k1;
         if (tb > tmax) tmax = tb; if (tb < tmin) tmin = tb; if (qb > qmax) qmax = qb; if (qb < qmin) qmin = qb;
       }
       for (int pw = 0; pw < 2; pw++) {
@@ -735,6 +750,8 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
       const double n = (double)grid * NCONS;
       fprintf(stderr, "[lj] celltile dbg: per warp avg wait %.0f, work %.0f, total %.0f cycles, quads %.1f (%.0f cycles/quad); "
               "CTA total min %.0f max %.0f, quads per CTA min %.0f max %.0f\n", w / n, k / n, t / n, q / n, k / q, tmin, tmax, qmin, qmax);
+      fprintf(stderr, "[lj] celltile dbg: within a CTA (avg over CTAs): wait of the least / most waiting warp %.0f / %.0f, "
+              "work of the least / most working warp %.0f / %.0f\n", wlo / grid, whi / grid, klo / grid, khi / grid);
     }
   }
 #endif
@@ -757,6 +774,8 @@ int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c4
   }
   if (nc == 24 && ring_sizes(kTileSmemBudget, ys, ls, ry, rl))
     return launch_celltile<LAYOUT, MX, 24, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
+  if (nc == 20 && ring_sizes(kTileSmemBudget, ys, ls, ry, rl))
+    return launch_celltile<LAYOUT, MX, 20, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
 #endif
   LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
   return launch_celltile<LAYOUT, MX, 16, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);

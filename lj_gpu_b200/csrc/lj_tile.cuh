@@ -21,12 +21,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "LJ_WAIT:\n"
+#ifdef LJ_MBAR_HINT_NS  // suspend-time hint: the warp sleeps in hardware until the phase completes or the time is up
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
       "@p bra LJ_DONE;\n"
       "bra LJ_WAIT;\n"
       "LJ_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
+#ifdef LJ_MBAR_HINT_NS
+      , "r"((uint32_t)LJ_MBAR_HINT_NS)
+#endif
       : "memory");
 }
 // TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
