@@ -94,7 +94,7 @@ int lj_ctx_destroy(lj_ctx* ctx) {
   void* frees[] = {ctx->bbox, ctx->grid, ctx->totals, ctx->cell_of, ctx->cell_slot, ctx->cell_count,
                    ctx->cell_start, ctx->sorted_pos, ctx->sorted_tmp, ctx->scan_tmp, ctx->q32,
                    ctx->cl_list, ctx->cl_ptr, ctx->cl_cnt, ctx->tl_geom, ctx->tl_order, ctx->tl_cnt,
-                   ctx->tl_units, ctx->tl_off, ctx->tl_qs, ctx->tl_qfx, ctx->soa6_q, ctx->soa6_p, ctx->tl_cell_start, ctx->tl_list, ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols, ctx->tl_meta};
+                   ctx->tl_units, ctx->tl_off, ctx->tl_qs, ctx->tl_qfx, ctx->soa6_q, ctx->soa6_p, ctx->tl_cell_start, ctx->tl_list, ctx->tl_tab, ctx->tl_ttab, ctx->tl_cols, ctx->tl_meta, ctx->tl_zflag, ctx->tl_cols_sel, ctx->tl_rowflag, ctx->tl_slot_of};
   for (void* f : frees)
     if (f) cudaFreeAsync(f, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
