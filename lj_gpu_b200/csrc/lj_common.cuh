@@ -47,6 +47,7 @@ struct lj_tile_geom {
 struct lj_ctx {
   int device = 0;
   int sm_count = 148;
+  size_t smem_optin = 227 * 1024;  // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
   cudaStream_t stream = nullptr;       // the context's own stream
   cudaStream_t copy_stream = nullptr;  // staging-ring DMA
   cudaMemPool_t pool = nullptr;
@@ -197,15 +198,16 @@ static inline bool lj_diag_set(const char* name) {
 #endif
 }
 
-// opt a kernel in to `bytes` of dynamic shared memory on this context's device (idempotent, cached per ctx)
+// opt a kernel in to `bytes` of dynamic shared memory on this context's device (idempotent, cached per ctx).
+// The attribute belongs to the DEVICE, not to the context: two contexts on one device (lj_decomp_args.devices
+// may repeat an ordinal) would lower each other's setting if each asked for exactly what it needs, so a kernel
+// is always opted in to the device's maximum; `bytes` above that fails here rather than at the launch.
 #define LJ_FUNC_SMEM(ctx, kern, bytes)                                                              \
   do {                                                                                              \
-    size_t& have__ = (ctx)->func_smem[reinterpret_cast<const void*>(kern)];                         \
-    if ((size_t)(bytes) > have__) {                                                                 \
-      LJ_CUDA((ctx), cudaFuncSetAttribute((kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
-      have__ = (size_t)(bytes);                                                                     \
-    }                                                                                               \
+    int rc__ = lj_func_smem((ctx), reinterpret_cast<const void*>(kern), (size_t)(bytes));           \
+    if (rc__) return rc__;                                                                          \
   } while (0)
+int lj_func_smem(lj_ctx* ctx, const void* kern, size_t bytes);  // lj_runtime.cu
 
 // Top of every public entry point: a context belongs to ONE device; make it current for the calling
 // host thread (a caller driving several GPUs from one thread switches contexts, not devices).

@@ -37,6 +37,20 @@ double now_s() {
 }
 }  // namespace
 
+// See LJ_FUNC_SMEM: opt `kern` in to the most dynamic shared memory the device allows next to the kernel's
+// static shared memory (never to less than another context on the same device asked for).
+int lj_func_smem(lj_ctx* ctx, const void* kern, size_t bytes) {
+  size_t& have = ctx->func_smem[kern];
+  if (bytes <= have) return LJ_OK;
+  cudaFuncAttributes fa{};
+  LJ_CUDA(ctx, cudaFuncGetAttributes(&fa, kern));
+  const size_t most = ctx->smem_optin > fa.sharedSizeBytes ? ctx->smem_optin - fa.sharedSizeBytes : 0;
+  LJ_REQUIRE(ctx, bytes <= most, "kernel needs more shared memory than the device offers");
+  LJ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+  have = most;
+  return LJ_OK;
+}
+
 extern "C" {
 
 const char* lj_status_string(int s) {
@@ -65,7 +79,10 @@ int lj_ctx_create(lj_ctx** out, int device) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LJ_ERR_CUDA; }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  }
   cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   // private pool: never hand memory back to the OS between steps (180 GB HBM, one tenant)

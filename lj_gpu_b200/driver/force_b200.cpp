@@ -38,6 +38,7 @@ struct Options {
   int group = 0, steps = 100, rebuild_every = 0;
   bool graph = false, test = false, all = false, cache = false, soa6 = false, print = false, md = false;
   int gpus = 1;
+  bool one_device = false;  // --one-device: every slab of --gpus N on device 0 (the decomposed path on a one-GPU box)
 };
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -165,6 +166,8 @@ int run_decomposed(const Options& o, const std::vector<double>& xyz, int64_t pn)
   a.ngpus = o.gpus; a.q_xyz_host = xyz.data(); a.pn = pn; a.slab_begin = slab.data(); a.halo_rows = halo_rows;
   a.search_len = 3.3; a.cutoff = 3.0; a.dt = 0.001;
   a.precision = o.prec == "mixed" ? LJ_PREC_MIXED : LJ_PREC_FP64;
+  const std::vector<int32_t> dev0((size_t)o.gpus, 0);
+  if (o.one_device) a.devices = dev0.data();
   lj_decomp* d = nullptr;
   const double t_all = now();
   rc = lj_decomp_create(&d, &a);
@@ -282,6 +285,7 @@ int main(int argc, char** argv) {
     else if (s == "--print") o.print = true;
     else if (s == "--gpus") o.gpus = std::atoi(next());
     else if (s == "--md") o.md = true;
+    else if (s == "--one-device") o.one_device = true;
     else if (s == "--soa6") o.soa6 = true;
     else if (s[0] != '-') o.thread_block = std::atoi(s.c_str());
     else { std::fprintf(stderr, "unknown option %s\n", s.c_str()); return 1; }

@@ -105,8 +105,8 @@ def test_two_gpu_moving_particles_match_the_oracle(mode, tmp_path, md_oracle, or
 
 
 # ------------------------------------------------------------------------ the same behind the C ABI, ONE process
-def _decomp_capi(q, ngpus, steps, rebuild_every, md=False, dt=0.001, prec=0):
-    """lj_decomp_* through ctypes: one process, `ngpus` contexts on `ngpus` devices."""
+def _decomp_capi(q, ngpus, steps, rebuild_every, md=False, dt=0.001, prec=0, devices=None, overlap=1):
+    """lj_decomp_* through ctypes: one process, `ngpus` contexts on `ngpus` devices (or on `devices`)."""
     import ctypes as C
 
     from lj_gpu_b200 import _capi
@@ -120,10 +120,13 @@ def _decomp_capi(q, ngpus, steps, rebuild_every, md=False, dt=0.001, prec=0):
     a.ngpus, a.q_xyz_host, a.pn = ngpus, qc.ctypes.data, pn
     a.slab_begin, a.halo_rows = C.cast(slab, C.c_void_p), halo.value
     a.search_len, a.cutoff, a.dt, a.precision = 3.3, 3.0, dt, prec
+    if devices is not None:
+        dev = (C.c_int32 * ngpus)(*devices)
+        a.devices = C.cast(dev, C.c_void_p)
     d = C.c_void_p()
     rc = lib.lj_decomp_create(C.byref(d), C.byref(a))
     assert rc == 0, lib.lj_decomp_last_error(d)
-    rc = (lib.lj_decomp_md if md else lib.lj_decomp_step)(d, steps, rebuild_every, 1)
+    rc = (lib.lj_decomp_md if md else lib.lj_decomp_step)(d, steps, rebuild_every, overlap)
     assert rc == 0, lib.lj_decomp_last_error(d)
     p = np.zeros((pn, 3)); qo = np.zeros((pn, 3))
     assert lib.lj_decomp_gather(d, p.ctypes.data, qo.ctypes.data) == 0, lib.lj_decomp_last_error(d)
@@ -156,6 +159,31 @@ def test_capi_decomposition_two_contexts_two_devices_one_process(static_oracle, 
     assert np.abs(p1 - ref).max() / np.abs(ref).max() < 1e-12
 
 
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_capi_decomposition_slabs_share_one_device(nslabs, static_oracle, md_oracle, oracle):
+    """The whole decomposed path on a ONE-GPU box: `nslabs` contexts on device 0 (lj_decomp_args.devices), so
+    slabs, ghost plan, device-side flag handshake, INTERIOR / BOUNDARY part launches, rebuilds on ghosted slabs
+    and the drift ordering all run exactly as on `nslabs` devices -- only the peer pointers are local.
+    Checker: the oracle on the undecomposed system."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    q, ref = static_oracle
+    nop, _, lst = oracle.makepair(q, full=True)
+    dev = [0] * nslabs
+    for overlap in (1, 0):
+        p, qo, pairs, launches = _decomp_capi(q, nslabs, STEPS, 10, devices=dev, overlap=overlap)
+        assert pairs == len(lst) and launches > 2 * nslabs * STEPS
+        assert np.array_equal(qo, q)
+        assert np.abs(p - ref).max() / np.abs(ref).max() < 1e-12
+    pm, _, _, _ = _decomp_capi(q, nslabs, STEPS, 10, prec=1, devices=dev)
+    assert 1e-14 < np.abs(pm - ref).max() / np.abs(ref).max() < 1e-5
+    qm, pmd = md_oracle
+    p, qo, _, _ = _decomp_capi(q, nslabs, MD_STEPS, MD_REBUILD, md=True, dt=MD_DT, devices=dev)
+    assert np.abs(qo - qm).max() < 1e-11
+    assert np.abs(p - pmd).max() / np.abs(pmd).max() < 1e-11
+
+
 def test_cpp_driver_gpus_2(static_oracle):
     from conftest import ROOT
     import subprocess
@@ -169,5 +197,23 @@ def test_cpp_driver_gpus_2(static_oracle):
                         "--rebuild-every", "10", "--print"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     assert "force_decomposed_2gpus" in r.stderr and "(without Host<->Device)" in r.stderr
+    from lj_gpu_b200 import print_results
+    assert r.stdout == print_results(static_oracle[1])
+
+
+def test_cpp_driver_gpus_3_on_one_device(static_oracle):
+    """force_b200 --gpus 3 --one-device: the C++ driver's decomposed run with its three slabs on device 0."""
+    from conftest import ROOT
+    import subprocess
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    exe = os.path.join(ROOT, "lj_gpu_b200", "driver", "force_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    r = subprocess.run([exe, "--gpus", "3", "--one-device", "--density", str(DENSITY), "--L", str(L), "--steps", str(STEPS),
+                        "--rebuild-every", "10", "--print"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "force_decomposed_3gpus" in r.stderr and "slabs=3" in r.stderr
     from lj_gpu_b200 import print_results
     assert r.stdout == print_results(static_oracle[1])

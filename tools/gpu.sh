@@ -67,6 +67,6 @@ PY
     # the cell-tile kernel is covered by memcheck above and by the bit-exact tests
     timeout -s KILL 1500 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/debug/sanitize_target.py --skip-celltile > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck.log ;;
   micro)
-    for m in dp_coissue tma_small fp64_peak; do [ -x tools/micro/$m ] && ./tools/micro/$m | tee gpurun_out/micro_$m.txt; done ;;
+    for m in dp_coissue tma_small fp64_peak dp_latency; do [ -x tools/micro/$m ] && ./tools/micro/$m | tee gpurun_out/micro_$m.txt; done ;;
   *) echo "unknown task $task"; exit 2 ;;
 esac
