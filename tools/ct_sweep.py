@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KNOBS = ("LJ_TILE_WPG", "LJ_TILE_CONSUMERS", "LJ_TILE_RY", "LJ_TILE_RL", "LJ_TILE_SEG", "LJ_TILE_MODE",
+KNOBS = ("LJ_TILE_NG", "LJ_TILE_WPG", "LJ_TILE_CONSUMERS", "LJ_TILE_RY", "LJ_TILE_RL", "LJ_TILE_SEG", "LJ_TILE_MODE",
          "LJ_TILE_ROWS")
 
 
@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--configs", default=";LJ_TILE_WPG=16")
     ap.add_argument("--prec", default="fp64,mixed")
+    ap.add_argument("--check-steps", type=int, default=30, help="steps of the bit-for-bit check against the per-row kernel")
     ap.add_argument("--rows", default="", help="comma list of LJ_TILE_ROWS values to rebuild the mirror with")
     args = ap.parse_args()
     import numpy as np
@@ -65,13 +66,13 @@ def main():
             pl = ctx.makepair(qd, tiles="wide" if wide or (prec == "mixed" and not rows) else True)
             P = pl.number_of_pairs
             p_ref = torch.zeros_like(qd)
-            ctx.force_step(qd, p_ref, pl, variant="subwarp", group=8)
+            ctx.force_loop(qd, p_ref, pl, loop=args.check_steps, variant="subwarp", group=8)
             scale = p_ref.abs().max().item()
             algo = 4.0 * P + 104.0 * pn
             for cfg in args.configs.split(";"):
                 setenv(cfg + (",LJ_TILE_ROWS=%s" % rows if rows else ""))
                 p_new = torch.zeros_like(qd)
-                ctx.force_step(qd, p_new, pl, variant="celltile", precision=prec)
+                ctx.force_loop(qd, p_new, pl, loop=args.check_steps, variant="celltile", precision=prec)
                 torch.cuda.synchronize()
                 err = (p_new - p_ref).abs().max().item() / scale
                 ok = (err == 0.0) if prec == "fp64" else (0 < err < 1e-5)
