@@ -31,6 +31,7 @@
 // re-permuted into cell order at the start of every step (k_tile_permute[_fx], ~10 us at N = 1M),
 // so moving particles are handled exactly like in the per-row kernels: the list decides
 // membership, the current q decides the force.
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -52,6 +53,16 @@ constexpr int kCtUnrollMx = LJ_CT_UNROLL_MX;
 #define LJ_CT_LANES_MX 8
 #endif
 constexpr int kCtLanesMx = LJ_CT_LANES_MX;  // lanes per row in the mixed kernel: 8 or 4
+#ifndef LJ_CT_GRADED
+#define LJ_CT_GRADED 1
+#endif
+#ifndef LJ_CT_GRADE_PCT
+#define LJ_CT_GRADE_PCT 45
+#endif
+#ifndef LJ_CT_GRADE_MIN
+#define LJ_CT_GRADE_MIN 3
+#endif
+constexpr bool kCtGraded = LJ_CT_GRADED != 0;  // graded column segments (see launch_celltile)
 #ifndef LJ_CT_ALU_SUB
 #define LJ_CT_ALU_SUB 0  // 1: integer differences as VIADDMNMX on the ALU pipe (measured: no gain)
 #endif
@@ -81,6 +92,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 constexpr int kCtMaxY = 16, kCtMaxL = 8;
 constexpr int kCtMaxSeg = 32;  // tiles per unit (column segment) at most
+constexpr int kCtMaxUnitsPerCol = 32;  // segments a column is cut into at most
 
 struct ct_params {
   const unsigned char* qs;  // positions in cell order: int4 fixed point (mixed) or the {x,y} plane (FP64)
@@ -98,7 +110,8 @@ struct ct_params {
   int ntx, ny, ncols;    // tiles per pencil, cells in y, ACTIVE columns (all of them: ntx * nz)
   const int32_t* cols;   // the active columns, or NULL when every column is active
   const int* ncols_dev;  // part launches: the number of selected columns is only known on the device
-  int seg_len, nseg;     // a unit = one column x [seg*seg_len, min(ny, (seg+1)*seg_len))
+  int seg_len, nseg;     // a unit = one column x the tiles [seg_y0[seg], seg_y0[seg + 1]) (seg_len: the longest)
+  short seg_y0[kCtMaxUnitsPerCol + 1];
   int cap_y, cap_units, cap_rows;
   int ry, rl;            // ring sizes: y-row slots, tile slots (list + metadata + barriers)
   int lslot_bytes;
@@ -231,7 +244,7 @@ lj_celltile_force(const ct_params P) {
     auto stage_tables = [&](int u, int b) {  // returns the unit's column (tx, cz)
       const int ci = u % ncols, seg = u / ncols;
       const int col = P.cols ? __ldg(P.cols + ci) : ci;
-      const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
+      const int y0 = P.seg_y0[seg], y1 = P.seg_y0[seg + 1];
       const int ylo = max(y0 - 2, 0), yhi = min(y1 + 1, P.ny - 1);
       if (lane == 0) {
         if (isY) {
@@ -256,7 +269,7 @@ lj_celltile_force(const ct_params P) {
     for (; u < nunits; nu++) {
       const int u_next = next_unit(nu + 1);
       const int seg = u / ncols;
-      const int y0 = seg * P.seg_len, y1 = min(y0 + P.seg_len, P.ny);
+      const int y0 = P.seg_y0[seg], y1 = P.seg_y0[seg + 1];
       const int ntile = y1 - y0;
       const int tb = nu & 1;
       __syncwarp();  // every lane is done with the other buffer (the previous unit's tables)
@@ -676,6 +689,35 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   if (seg_len > g.ny) seg_len = g.ny;
   if (seg_len > kCtMaxSeg) seg_len = kCtMaxSeg;
   nseg = (g.ny + seg_len - 1) / seg_len;
+  // Units are dealt dynamically in the order (segment, column).  With equal segments the kernel ends when the
+  // CTA that drew the last 11-tile unit is through: CTAs finished between 571k and 606k cycles (6 % apart).
+  // GRADED segments -- long ones first, each 45 % of what is left, the last ones 4-5 tiles (ny = 63: 29, 16, 9, 5, 4) -- end the
+  // deal within a few tiles of each other and re-stage fewer y-rows on the way (every unit stages four extra).
+  short seg_y0[kCtMaxUnitsPerCol + 1];
+  bool graded = false;
+  if (seg_env <= 0 && kCtGraded && nseg >= 3 && nseg <= 8) {
+    int lens[kCtMaxUnitsPerCol], n = 0, rem = g.ny;
+    while (rem > 0 && n < kCtMaxUnitsPerCol) {
+      int len = (rem * LJ_CT_GRADE_PCT + 99) / 100;
+      if (len < LJ_CT_GRADE_MIN) len = LJ_CT_GRADE_MIN;
+      if (len > kCtMaxSeg) len = kCtMaxSeg;
+      if (rem - len < 3 && rem <= kCtMaxSeg) len = rem;
+      if (len > rem) len = rem;
+      lens[n++] = len;
+      rem -= len;
+    }
+    if (rem > 0) n = 0;  // (does not happen: ny <= 32 * 32) fall back to equal segments
+    if (n > 0) {
+      std::sort(lens, lens + n, [](int x, int y) { return x > y; });
+      nseg = n; seg_len = lens[0];
+      seg_y0[0] = 0;
+      for (int k = 0; k < n; k++) seg_y0[k + 1] = (short)(seg_y0[k] + lens[k]);
+      graded = true;
+    }
+  }
+  LJ_REQUIRE(ctx, nseg <= kCtMaxUnitsPerCol, "cell-tile force: too many segments per column");
+  if (!graded)
+    for (int k = 0; k <= nseg; k++) seg_y0[k] = (short)(k * seg_len < g.ny ? k * seg_len : g.ny);
 
   ct_params P;
   P.qs = MX ? reinterpret_cast<const unsigned char*>(ctx->tl_qfx) : reinterpret_cast<const unsigned char*>(ctx->tl_qs);
@@ -692,6 +734,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   }
   P.ytab = ctx->tl_tab; P.ttab = ctx->tl_ttab; P.meta = ctx->tl_meta; P.list = ctx->tl_list;
   P.ntx = g.ntx; P.ny = g.ny; P.ncols = ncols; P.seg_len = seg_len; P.nseg = nseg;
+  for (int k = 0; k <= nseg; k++) P.seg_y0[k] = seg_y0[k];
   P.cols = all_cols ? nullptr : ctx->tl_cols;
   P.ncols_dev = nullptr;
   if (part != 0) {  // the permute kernel compacted the selected columns; their number stays on the device
