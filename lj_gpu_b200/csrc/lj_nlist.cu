@@ -30,8 +30,20 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(256)
 k_bbox(const void* __restrict__ q, int64_t pn, int64_t plane, unsigned long long* bb) {
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pn;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  // four independent loads in flight per thread: one load per trip left the kernel latency-bound
+  // (24 us for 32 MB at N = 1M)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < pn; i += 4 * stride) {
+    double v[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; u++) load_pos<LAYOUT>(q, i + u * stride, plane, v[u][0], v[u][1], v[u][2]);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) { lo[d] = fmin(lo[d], v[u][d]); hi[d] = fmax(hi[d], v[u][d]); }
+  }
+  for (; i < pn; i += stride) {
     double v[3];
     load_pos<LAYOUT>(q, i, plane, v[0], v[1], v[2]);
 #pragma unroll
@@ -43,12 +55,19 @@ k_bbox(const void* __restrict__ q, int64_t pn, int64_t plane, unsigned long long
       lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], m));
       hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], m));
     }
+  __shared__ double wlo[8][3], whi[8][3];  // one set of six atomics per block, not per warp
+  const int warp = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-      atomicMin(bb + d, enc_ordered(lo[d]));
-      atomicMax(bb + 3 + d, enc_ordered(hi[d]));
-    }
+    for (int d = 0; d < 3; d++) { wlo[warp][d] = lo[d]; whi[warp][d] = hi[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int d = threadIdx.x;
+    double l = wlo[0][d], h = whi[0][d];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { l = fmin(l, wlo[w][d]); h = fmax(h, whi[w][d]); }
+    atomicMin(bb + d, enc_ordered(l));
+    atomicMax(bb + 3 + d, enc_ordered(h));
   }
 }
 
@@ -942,7 +961,7 @@ k_tile_zflag(int64_t pn, int64_t r0, int64_t r1, const int32_t* __restrict__ cel
 // and writes both lists without looking at a single position.  Membership is decided by the same
 // tests as k_search (FP32 on origin-shifted coordinates, the exact FP64 fma chain inside the error
 // band), rows are emitted in the same order as k_tile_fill did (pencil dz-major, cell order within).
-constexpr int kTeThreads = 192;  // six warps: 48 rows per round of row pairs (tiles hold ~40, ~56 wide)
+constexpr int kTeThreads = 192;  // replay / translate: six warps, four rows of eight lanes each
 constexpr int kTeLanes = 8;      // lanes per row (pair), four per warp
 constexpr int kTeRowCap = 256;   // replay: entries of a row staged in shared memory (longer rows are written directly)
 
@@ -959,6 +978,8 @@ __device__ __forceinline__ void te_setup(const lj_tile_geom& g, int t, uint32_t 
   int xa, xb, rxa, rxb;
   tile_x_extent(tx * g.tc, g.tc, g.nx, xa, xb, rxa, rxb);
   ncx = rxb - rxa + 1;
+  // one global round trip: the y-row table entries (threads 0 .. 24) and the cell starts of the 25 window
+  // tables are loaded side by side, the pencil's first record is subtracted once both have arrived
   if (threadIdx.x < 25) {
     const int p = threadIdx.x, dz = p / 5, dy = p % 5;
     const int Y = cy + dy - 2, z = cz + dz - 2;
@@ -972,15 +993,20 @@ __device__ __forceinline__ void te_setup(const lj_tile_geom& g, int t, uint32_t 
     }
     pen[p] = e;
   }
-  __syncthreads();
   for (int idx = threadIdx.x; idx < 25 * ncx1; idx += blockDim.x) {
     const int p = idx / ncx1, k = idx - p * ncx1;
-    const te_pencil e = pen[p];
-    xoff[idx] = (e.rowc >= 0 && k <= ncx) ? (int)(cell_start[e.rowc + rxa + k] - e.st) : 0;
+    const int Y = cy + p % 5 - 2, z = cz + p / 5 - 2;
+    const bool inside = Y >= 0 && Y < g.ny && z >= 0 && z < g.nz && k <= ncx;
+    xoff[idx] = inside ? (int)cell_start[(z * g.ny + Y) * g.nx + rxa + k] : -1;
   }
   const int rowc = (cz * g.ny + cy) * g.nx;
   s0 = cell_start[rowc + xa];
   ns = cell_start[rowc + xb + 1] - s0;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 25 * ncx1; idx += blockDim.x) {
+    const int v = xoff[idx];
+    xoff[idx] = v >= 0 ? v - (int)pen[idx / ncx1].st : 0;
+  }
   __syncthreads();
 }
 
@@ -991,28 +1017,46 @@ __device__ __forceinline__ int te_row_cell(const int* __restrict__ xoff_c, int n
   return kx;
 }
 
-// COUNT pass.  One CTA per tile.  Eight lanes work on a PAIR of consecutive rows (a, b): each lane
-// loads a candidate record once and tests it against both rows (they sit in the same or in
-// neighbouring cells, so they share one window: the x-cells min(kx) - 2 .. max(kx) + 2).  The loop
-// body is branch-free: a candidate with r2 < lo is a hit (the row's own record is removed afterwards:
-// any other record that close is a neighbour), candidates inside the FP32 error band [lo, hi) of the
-// search radius are collected in a bit field and decided exactly after the loop (about one in 5000).
-// Mask layout: byte lg of mask[s][p] belongs to lane lg, its bit `it` = window record it * 8 + lg.
-// Outputs per row (cell-order slot s): the 25 masks, tl_order[s], tl_cnt[s], tl_units[s] and the
-// public number_of_partners[i].  status bit 16: a window holds more than 64 records (cells too
-// crowded for the masks) -- the caller falls back to the round-1 engine.
-__global__ void __launch_bounds__(kTeThreads)
-k_tile_count(int64_t pn, int64_t r0, int64_t r1, const grid_ext* __restrict__ ge, const lj_tile_geom* __restrict__ tgp,
-             const uint32_t* __restrict__ cell_start, const uint2* __restrict__ ytab,
-             const double4* __restrict__ sorted_pos, const float4* __restrict__ sorted_pos32, double sl2,
-             int ncx1, int32_t* __restrict__ nop, int32_t* __restrict__ tl_order, int32_t* __restrict__ tl_cnt,
-             uint32_t* __restrict__ tl_units, unsigned char* __restrict__ masks, lj_list_totals* __restrict__ tot) {
+// COUNT pass, second form: ONE THREAD PER (row, pencil).  A tile of ~40 rows has 1000 such jobs, lanes are
+// consecutive rows of one pencil, so the lanes of a warp read the same few candidate records (rows that are
+// neighbours in cell order share their window: a multicast shared-memory load), nobody waits for a slower
+// lane (the trip count is the warp's largest window, rounded to 8) and there is no per-pencil set-up shared
+// by only two rows: 11 instructions per test instead of 16 and no 90-instruction pencil prologue per eight
+// rows -- the count pass executes 2.5x fewer instructions than k_tile_count.  Same tests, same windows
+// (the window of a row is that of its PAIR (2k, 2k + 1): k_tile_replay recomputes it), mask bit b = window
+// record b, masks stored pencil-major (masks[p * pn + s]: a warp writes 256 contiguous bytes).
+constexpr int kTcThreads = 256;
+constexpr int kTcRowChunk = 128;  // rows of a tile worked on at a time (tiles hold ~40-60)
+
+#define LJ_TC_TEST(H, U, J)                                                                                         \
+  {                                                                                                                 \
+    const float4 c = cand[(J)];                                                                                     \
+    const float dx = me.x - c.x, dy = me.y - c.y, dz = me.z - c.z;                                                  \
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));                                                           \
+    asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(H) : "f"(r2), "f"(lo_f), "n"(1u << ((J) & 31))); \
+    asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(U) : "f"(r2), "f"(hi_f), "n"(1u << ((J) & 31))); \
+  }
+#define LJ_TC_GROUP(H, U, K)                                                                                        \
+  if (nmax > (K)) {                                                                                                 \
+    LJ_TC_TEST(H, U, (K) + 0) LJ_TC_TEST(H, U, (K) + 1) LJ_TC_TEST(H, U, (K) + 2) LJ_TC_TEST(H, U, (K) + 3)          \
+    LJ_TC_TEST(H, U, (K) + 4) LJ_TC_TEST(H, U, (K) + 5) LJ_TC_TEST(H, U, (K) + 6) LJ_TC_TEST(H, U, (K) + 7)          \
+  }
+
+__global__ void __launch_bounds__(kTcThreads, 4)
+k_tile_count2(int64_t pn, int64_t r0, int64_t r1, const grid_ext* __restrict__ ge, const lj_tile_geom* __restrict__ tgp,
+              const uint32_t* __restrict__ cell_start, const uint2* __restrict__ ytab,
+              const double4* __restrict__ sorted_pos, const float4* __restrict__ sorted_pos32, double sl2,
+              int ncx1, int32_t* __restrict__ nop, int32_t* __restrict__ tl_order, int32_t* __restrict__ tl_cnt,
+              uint32_t* __restrict__ tl_units, unsigned long long* __restrict__ masks, lj_list_totals* __restrict__ tot) {
   extern __shared__ __align__(16) unsigned char te_smem[];
   const lj_tile_geom g = *tgp;
   const uint32_t cap_y = (uint32_t)((g.max_yrow + 8 + 1) & ~1);
-  float4* reg = reinterpret_cast<float4*>(te_smem);
-  te_pencil* pen = reinterpret_cast<te_pencil*>(reg + 5 * cap_y);
+  float4* reg = reinterpret_cast<float4*>(te_smem);  // 5 * cap_y records + 64 of slack (windows are read in
+                                                      // groups of 8: a read past the region's end stays inside)
+  te_pencil* pen = reinterpret_cast<te_pencil*>(reg + 5 * cap_y + 64);
   int* xoff = reinterpret_cast<int*>(pen + 25);
+  int* rowcnt = xoff + 25 * ncx1;
+  unsigned char* rowkx = reinterpret_cast<unsigned char*>(rowcnt + kTcRowChunk);
   __shared__ int blk_max;
   if (threadIdx.x == 0) blk_max = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) tl_units[pn] = 0u;  // sentinel: the scan then yields off[pn] = total
@@ -1021,113 +1065,84 @@ k_tile_count(int64_t pn, int64_t r0, int64_t r1, const grid_ext* __restrict__ ge
   te_setup(g, blockIdx.x, cap_y, cell_start, ytab, pen, xoff, ncx1, ncx, s0, ns);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (ns == 0) return;  // (uniform) an empty tile
-  // stage the region: warp w copies pencils w, w + 6, ...; a lane has ~10 independent loads in flight
-  for (int p = warp; p < 25; p += kTeThreads / 32) {
+  for (int p = warp; p < 25; p += kTcThreads / 32) {  // stage the region: a warp per pencil
     const te_pencil e = pen[p];
     float4* dst = reg + e.base;
     for (uint32_t k = lane; k < e.len; k += 32) dst[k] = sorted_pos32[e.st + k];
   }
-  __syncthreads();
   const float margin = ge->margin, sl2f = ge->sl2f;
   const float lo_f = sl2f - margin, hi_f = sl2f + margin;
-  const int lg = lane % kTeLanes, gi = lane / kTeLanes;
-  const unsigned gmask = 0xffu << (gi * kTeLanes);
   const te_pencil pc = pen[12];  // the centre pencil holds the tile's rows
   const int* xoff_c = xoff + 12 * ncx1;
   int my_max = 0;
-  for (uint32_t rb = warp * 8; rb < ns; rb += (kTeThreads / 32) * 8) {
-    const uint32_t ra = rb + 2 * gi, rbb = ra + 1;
-    const bool va = ra < ns, vb = rbb < ns;
-    const uint32_t sa = s0 + (va ? ra : 0u), sb = s0 + (vb ? rbb : (va ? ra : 0u));
-    const uint32_t rela = sa - pc.st, relb = sb - pc.st;
-    const float4 ma = reg[pc.base + rela], mb = reg[pc.base + relb];
-    const int ia = __float_as_int(ma.w), ib = __float_as_int(mb.w);
-    const bool in_a = va && ia >= r0 && ia < r1, in_b = vb && ib >= r0 && ib < r1;
-    const int kxa = te_row_cell(xoff_c, ncx, rela), kxb = te_row_cell(xoff_c, ncx, relb);
-    const int k_lo = max(min(kxa, kxb) - 2, 0), k_hi = min(max(kxa, kxb) + 2, ncx - 1);
-    const int* xlo = xoff + k_lo;
-    const int* xhi = xoff + k_hi + 1;
-    unsigned char* mpa = masks + (size_t)sa * 200 + lg;   // 25 masks of 8 bytes per row
-    unsigned char* mpb = masks + (size_t)sb * 200 + lg;
-    // the rows' own records (centre pencil): window record -> (lane, bit)
-    const int wc = xlo[12 * ncx1];
-    const int selfa = (int)rela - wc, selfb = (int)relb - wc;
-    int cnta = 0, cntb = 0;
-#pragma unroll 1
-    for (int p = 0; p < 25; p++) {
+  for (uint32_t rbase = 0; rbase < ns; rbase += kTcRowChunk) {
+    const int nr = (int)min((uint32_t)kTcRowChunk, ns - rbase);
+    if (rbase > 0) __syncthreads();  // the previous chunk's counts have been read
+    for (int r = threadIdx.x; r < nr; r += kTcThreads) {
+      rowkx[r] = (unsigned char)te_row_cell(xoff_c, ncx, s0 + rbase + r - pc.st);
+      rowcnt[r] = 0;
+    }
+    __syncthreads();  // (first chunk: the region is staged as well)
+    const int njobs = nr * 25;
+    for (int job0 = warp * 32; job0 < njobs; job0 += kTcThreads) {
+      const int job = job0 + lane;
+      const bool live = job < njobs;
+      const int p = live ? job / nr : 0, r = live ? job - p * nr : 0;
+      const uint32_t rr = rbase + (uint32_t)r;
+      const uint32_t rp = (rr ^ 1u) < ns ? (rr ^ 1u) : rr;  // the other row of the pair (same chunk: the chunk is even)
+      const uint32_t s = s0 + rr, rel = s - pc.st;
+      const int kx = rowkx[r], kxp = rowkx[rp - rbase];
+      const int k_lo = max(min(kx, kxp) - 2, 0), k_hi = min(max(kx, kxp) + 2, ncx - 1);
       const te_pencil e = pen[p];
-      const int w0 = xlo[p * ncx1];
-      int nw = ((in_a || in_b) && e.rowc >= 0) ? xhi[p * ncx1] - w0 : 0;
-      if (nw > 64) { if (lg == 0) atomicOr(&tot->overflow, 16); nw = 64; }
-      const int iters = __reduce_max_sync(0xffffffffu, (nw + kTeLanes - 1) / kTeLanes);
-      const float4* __restrict__ cand = reg + (e.base + (uint32_t)w0 + (uint32_t)lg);
-      // la/lb: r2 < lo (hit for sure), ua/ub: r2 < hi (hit or inside the error band), one predicated OR each
-      unsigned ha = 0, hb = 0, ua = 0, ub = 0;
-      unsigned bit = 1u;
-      int left = nw - lg;  // this lane's candidates: idx = lg, lg + 8, ... < nw
-#pragma unroll 1
-      for (int it = 0; it < iters; it++, bit <<= 1, left -= kTeLanes) {
-        const float4 c = cand[left > 0 ? it * kTeLanes : 0];
-        const unsigned b1 = left > 0 ? bit : 0u;
-        const float ax = ma.x - c.x, ay = ma.y - c.y, az = ma.z - c.z;
-        const float bx = mb.x - c.x, by = mb.y - c.y, bz = mb.z - c.z;
-        const float r2a = fmaf(az, az, fmaf(ay, ay, ax * ax));
-        const float r2b = fmaf(bz, bz, fmaf(by, by, bx * bx));
-        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(ha) : "f"(r2a), "f"(lo_f), "r"(b1));
-        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(hb) : "f"(r2b), "f"(lo_f), "r"(b1));
-        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(ua) : "f"(r2a), "f"(hi_f), "r"(b1));
-        asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(ub) : "f"(r2b), "f"(hi_f), "r"(b1));
+      const float4 me = reg[pc.base + rel];
+      const int ia = __float_as_int(me.w);
+      const bool in = live && ia >= r0 && ia < r1;
+      const int w0 = xoff[p * ncx1 + k_lo];
+      int nw = (in && e.rowc >= 0) ? xoff[p * ncx1 + k_hi + 1] - w0 : 0;
+      if (nw > 64) { atomicOr(&tot->overflow, 16); nw = 64; }
+      const int nmax = __reduce_max_sync(0xffffffffu, nw);
+      const float4* __restrict__ cand = reg + (e.base + (uint32_t)w0);
+      // h: r2 < lo (a hit for sure), u: r2 < hi (a hit or inside the FP32 error band), one predicated OR each
+      unsigned h0 = 0, u0 = 0, h1 = 0, u1 = 0;
+      LJ_TC_GROUP(h0, u0, 0) LJ_TC_GROUP(h0, u0, 8) LJ_TC_GROUP(h0, u0, 16) LJ_TC_GROUP(h0, u0, 24)
+      if (nmax > 32) {
+        LJ_TC_GROUP(h1, u1, 32) LJ_TC_GROUP(h1, u1, 40) LJ_TC_GROUP(h1, u1, 48) LJ_TC_GROUP(h1, u1, 56)
       }
-      unsigned band = (ua & ~ha) | ((ub & ~hb) << 8);  // band: bit it = row a, bit 8 + it = row b
-      if (p == 12) {  // a row is not its own neighbour
-        if ((selfa & 7) == lg) ha &= ~(1u << (selfa >> 3));
-        if ((selfb & 7) == lg) hb &= ~(1u << (selfb >> 3));
+      const unsigned long long lm = nw >= 64 ? ~0ull : (1ull << nw) - 1ull;  // records past the window do not count
+      unsigned long long ha = ((unsigned long long)h1 << 32 | h0) & lm;
+      unsigned long long band = ((unsigned long long)u1 << 32 | u0) & lm & ~ha;
+      if (p == 12 && nw > 0) {  // a row is not its own neighbour
+        const unsigned long long self = 1ull << ((int)rel - w0);
+        ha &= ~self; band &= ~self;
       }
-      if (!in_a) { ha = 0; band &= ~0xffu; }
-      if (!in_b) { hb = 0; band &= 0xffu; }
-      if (__any_sync(0xffffffffu, band != 0)) {  // rare: the exact FP64 test
-        while (band) {
-          const int k = __ffs((int)band) - 1;
-          band &= band - 1;
-          const int it = k & 7;
-          const uint32_t m = e.st + (uint32_t)(w0 + it * kTeLanes + lg), sr = k < 8 ? sa : sb;
-          const double4 cj = sorted_pos[m], md = sorted_pos[sr];
-          const double dx = md.x - cj.x, dy = md.y - cj.y, dz = md.z - cj.z;
-          if (m != sr && fma(dz, dz, fma(dy, dy, dx * dx)) < sl2) { if (k < 8) ha |= 1u << it; else hb |= 1u << it; }
-        }
+      while (band) {  // rare (about one candidate in 5000): the exact FP64 test
+        const int k = __ffsll((long long)band) - 1;
+        band &= band - 1;
+        const uint32_t m = e.st + (uint32_t)(w0 + k);
+        const double4 cj = sorted_pos[m], md = sorted_pos[s];
+        const double dx = md.x - cj.x, dy = md.y - cj.y, dz = md.z - cj.z;
+        if (fma(dz, dz, fma(dy, dy, dx * dx)) < sl2) ha |= 1ull << k;
       }
-      cnta += __popc(ha);
-      cntb += __popc(hb);
-      if (in_a) mpa[p * 8] = (unsigned char)ha;
-      if (in_b) mpb[p * 8] = (unsigned char)hb;
+      if (in) {
+        masks[(size_t)p * (size_t)pn + s] = ha;
+        const int c = __popcll(ha);
+        if (c) atomicAdd(&rowcnt[r], c);
+      }
     }
-#pragma unroll
-    for (int d = 1; d < kTeLanes; d <<= 1) {
-      cnta += __shfl_xor_sync(gmask, cnta, d, kTeLanes);
-      cntb += __shfl_xor_sync(gmask, cntb, d, kTeLanes);
-    }
-    if (lg == 0 && va) {
-      tl_order[sa] = ia; tl_cnt[sa] = cnta; tl_units[sa] = (uint32_t)(cnta + 7) >> 3; nop[ia] = cnta;
-      my_max = max(my_max, cnta);
-    }
-    if (lg == 1 && vb) {
-      tl_order[sb] = ib; tl_cnt[sb] = cntb; tl_units[sb] = (uint32_t)(cntb + 7) >> 3; nop[ib] = cntb;
-      my_max = max(my_max, cntb);
+    __syncthreads();
+    for (int r = threadIdx.x; r < nr; r += kTcThreads) {
+      const uint32_t s = s0 + rbase + (uint32_t)r;
+      const int ia = __float_as_int(reg[pc.base + (s - pc.st)].w), c = rowcnt[r];
+      tl_order[s] = ia; tl_cnt[s] = c; tl_units[s] = (uint32_t)(c + 7) >> 3; nop[ia] = c;
+      my_max = max(my_max, c);
     }
   }
   if (my_max > 0) atomicMax(&blk_max, my_max);
   __syncthreads();
   if (threadIdx.x == 0 && blk_max > *(volatile int*)&tot->max_np) atomicMax(&tot->max_np, blk_max);
 }
-
-// 8 x 8 bit-matrix transpose (Hacker's Delight 7-3): mask bit lg * 8 + it -> bit it * 8 + lg = window record
-__device__ __forceinline__ unsigned long long te_transpose8(unsigned long long x) {
-  unsigned long long t;
-  t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull; x = x ^ t ^ (t << 7);
-  t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
-  t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
-  return x;
-}
+#undef LJ_TC_GROUP
+#undef LJ_TC_TEST
 
 // REPLAY pass: masks -> mirror entries (16-bit region-local indices) and the public list (original
 // indices), both at the offsets the scans produced.  No positions are read.  A row's entries are
@@ -1186,7 +1201,7 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
 #pragma unroll
     for (int q4 = 0; q4 < 4; q4++) {
       const int p = q4 * kTeLanes + lg;
-      mk[q4] = p < 25 ? te_transpose8(masks[(size_t)s * 25 + p]) : 0ull;
+      mk[q4] = p < 25 ? masks[(size_t)p * (size_t)pn + s] : 0ull;  // (pencil-major: four rows of a warp = one sector)
       const int c = __popcll(mk[q4]);
       int inc = c;  // inclusive scan over the eight lanes of the row
 #pragma unroll
@@ -1350,7 +1365,7 @@ int lj_scratch_reserve(lj_ctx* ctx, int64_t pn, cudaStream_t st) {
 int lj_bbox_launch(lj_ctx* ctx, const void* q, int layout, int64_t pn, int64_t plane,
                    lj_list_totals* reset_totals, cudaStream_t st) {
   unsigned long long* bb = reinterpret_cast<unsigned long long*>(ctx->bbox);
-  const int nb = (int)(blocks_for(pn, 256) < 4 * ctx->sm_count ? blocks_for(pn, 256) : 4 * ctx->sm_count);
+  const int nb = (int)(blocks_for(pn, 1024) < 8 * ctx->sm_count ? (blocks_for(pn, 1024) > 0 ? blocks_for(pn, 1024) : 1) : 8 * ctx->sm_count);
   k_bbox_init<<<1, 32, 0, st>>>(bb, reset_totals);
   LJ_LAUNCHED(ctx);
   switch (layout) {
@@ -1786,15 +1801,15 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a_in, cudaStream_t 
   const int cap_y = lj_celltile_cap_y(g);
   const int ncx1 = g.tc + 5;  // x-cells of a region + 1
   const size_t smem_tab = 25 * sizeof(te_pencil) + sizeof(int) * 25 * (size_t)ncx1;
-  const size_t smem_count = (size_t)5 * cap_y * sizeof(float4) + smem_tab;
+  const size_t smem_count = (size_t)(5 * cap_y + 64) * sizeof(float4) + smem_tab + kTcRowChunk * (sizeof(int) + 1);
   if (5 * cap_y >= 65536 || smem_count > (size_t)200 * 1024) return LJ_OK;
   unsigned long long* masks = nullptr;
   LJ_CUDA(ctx, cudaMallocAsync((void**)&masks, mask_bytes, ctx->pool, st));
-  LJ_FUNC_SMEM(ctx, k_tile_count, smem_count);
+  LJ_FUNC_SMEM(ctx, k_tile_count2, smem_count);
   const double sl2 = a->search_len * a->search_len;
-  k_tile_count<<<(unsigned)g.ntiles, kTeThreads, smem_count, st>>>(
+  k_tile_count2<<<(unsigned)g.ntiles, kTcThreads, smem_count, st>>>(
       pn, r0, r1, ge, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ctx->sorted_pos, sorted_pos32, sl2, ncx1,
-      a->number_of_partners, ctx->tl_order, ctx->tl_cnt, ctx->tl_units, reinterpret_cast<unsigned char*>(masks), ctx->totals);
+      a->number_of_partners, ctx->tl_order, ctx->tl_cnt, ctx->tl_units, masks, ctx->totals);
   LJ_LAUNCHED(ctx);
   // pointer[] = exclusive scan of number_of_partners (64-bit carry), mirror offsets = scan of the padded units
   const unsigned row_tiles = (unsigned)blocks_for(pn, kScanTile);
@@ -1862,6 +1877,7 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a_in, cudaStream_t 
     a->sorted_list = ctx->alloc_list; a->capacity = ctx->alloc_capacity;
     ctx->last_capacity = a->capacity;
   }
+  // staged entries of a tile (6 B each) + tables + per-row arrays (see k_tile_replay2)
   const size_t smem_replay = smem_tab + (size_t)(kTeThreads / kTeLanes) * kTeRowCap * 6;
   LJ_FUNC_SMEM(ctx, k_tile_replay<true>, smem_replay);
   LJ_FUNC_SMEM(ctx, k_tile_replay<false>, smem_replay);
