@@ -355,6 +355,10 @@ def run_cuda(args):
             m1.record(stream)
             torch.cuda.synchronize()
             ms_mixed = m0.elapsed_time(m1) / nf
+            # (one untimed rebuild first: the first rebuild after the first mixed-precision step grows the
+            # stream-ordered pool -- a one-off of 10-100 ms that is not the cost of a rebuild)
+            ctx.rebuild(qd, pl, clusters=use_cl, tiles="wide" if use_tiles else False)
+            torch.cuda.synchronize()
             mb0, mb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             mb0.record(stream)
             for _ in range(5):
