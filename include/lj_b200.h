@@ -208,8 +208,8 @@ enum {
    * systems), in which case AUTO stays on the per-row kernels. */
   LJ_LIST_TILES = 8,
   /* With LJ_LIST_TILES: size the tiles of the mirror for the mixed-precision force kernel
-   * (LJ_PREC_MIXED: 16-byte position records leave shared memory for ~56-row tiles, measured 8 %
-   * faster than the 40-row tiles the FP64 kernel prefers).  Either kernel runs on either mirror. */
+   * (LJ_PREC_MIXED: 16-byte position records leave shared memory for ~72-row tiles, measured faster
+   * than the ~56-row tiles the FP64 kernel prefers).  Either kernel runs on either mirror. */
   LJ_LIST_TILES_WIDE = 16
 };
 

@@ -53,6 +53,9 @@ constexpr int kCtUnrollMx = LJ_CT_UNROLL_MX;
 #define LJ_CT_LANES_MX 8
 #endif
 constexpr int kCtLanesMx = LJ_CT_LANES_MX;  // lanes per row in the mixed kernel: 8 or 4
+#ifndef LJ_CT_LIST_DEPTH
+#define LJ_CT_LIST_DEPTH 5
+#endif
 #ifndef LJ_CT_GRADED
 #define LJ_CT_GRADED 1
 #endif
@@ -90,7 +93,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                : "memory");
 }
 
-constexpr int kCtMaxY = 16, kCtMaxL = 8;
+#ifndef LJ_CT_MAXY
+#define LJ_CT_MAXY 16
+#endif
+constexpr int kCtMaxY = LJ_CT_MAXY, kCtMaxL = 8;
 constexpr int kCtMaxSeg = 32;  // tiles per unit (column segment) at most
 constexpr int kCtMaxUnitsPerCol = 32;  // segments a column is cut into at most
 
@@ -113,8 +119,8 @@ struct ct_params {
   int seg_len, nseg;     // a unit = one column x the tiles [seg_y0[seg], seg_y0[seg + 1]) (seg_len: the longest)
   short seg_y0[kCtMaxUnitsPerCol + 1];
   int cap_y, cap_units, cap_rows;
-  int ry, rl;            // ring sizes: y-row slots, tile slots (list + metadata + barriers)
-  int lslot_bytes;
+  int ry, rl;            // ring sizes: y-row slots, tiles in flight (headers + barriers)
+  int lring_bytes;       // the list ring: every tile takes exactly what its list and row metadata need
   int* unit_counter;     // zeroed by k_tile_permute before every launch: units are dealt dynamically
   long long* dbg;        // diagnostics (LJ_TILE_DBG): per consumer warp {wait, work, quads, total} cycles
   int mode;              // diagnostics (LJ_TILE_MODE): 0 normal, 1 no pair math, 3 staging only
@@ -153,6 +159,7 @@ lj_celltile_force(const ct_params P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t tfull[kCtMaxL], tempty[kCtMaxL];
   __shared__ tile_hdr hdr[kCtMaxL];
+  __shared__ uint32_t lstart[kCtMaxL];  // warp L: first byte of the tile's data in the list ring
   __shared__ int yrel[kCtMaxY];  // producer: tile sequence number whose release frees the y slot
   // the producer's view of the y-row / tile tables of the current and the next unit (bulk-copied one
   // unit ahead: a table entry fetched with a plain load costs a DRAM round trip per tile)
@@ -206,6 +213,8 @@ lj_celltile_force(const ct_params P) {
     const bool isY = warp == NCONS;
     int tseq = 0, tslot = 0;             // tile being assembled: sequence number, slot (ring of rl)
     int done = 0, dslot = 0, dphase = 0; // tiles known to be released: [0, done)
+    uint32_t lhead = 0u;                 // warp L: next free byte of the list ring
+    const uint32_t lring = (uint32_t)P.lring_bytes;
     long long p_idle = 0;                // diagnostics: cycles spent waiting for the consumers
     const long long p_begin = dbgp ? clock64() : 0;
     auto ensure_done = [&](int q) {      // block until tile q has been released by every consumer
@@ -353,14 +362,32 @@ lj_celltile_force(const ct_params P) {
           const uint32_t self0 = __shfl_sync(0xffffffffu, et.x, 1);
           const uint32_t units_c = (modev & 32) ? 0u : units, ns_c = (modev & 64) ? 0u : ns;  // diagnostics
           if ((int)units > P.cap_units || (int)ns > P.cap_rows) __trap();
-          unsigned char* dst = lbase + (size_t)tslot * P.lslot_bytes;
+          // The list ring is BYTE-granular: a tile takes [row metadata | list units] = (ns + units) * 16 bytes,
+          // contiguous (a bulk copy does not wrap), wherever the ring has room.  Slots sized for the longest
+          // tile were half empty on average (tiles hold 30-70 rows), and what the ring saves went to y-row
+          // slots.  Tiles are released in order, so the free space is what lies between the head and the
+          // first byte of the oldest tile still in use.
+          const uint32_t need = (ns + units) * 16u;
+          for (;;) {
+            if (done == tseq) { lhead = 0u; break; }  // nothing in flight: start over at the bottom
+            const uint32_t tail = *reinterpret_cast<volatile uint32_t*>(&lstart[dslot]);
+            if (lhead >= tail) {
+              if (lhead + need <= lring) break;             // room above the head
+              if (need < tail) { lhead = 0u; break; }       // wrap: room below the oldest tile
+            } else if (lhead + need < tail) break;          // wrapped already: room up to the oldest tile
+            ensure_done(done);                              // wait for the oldest tile, look again
+          }
+          unsigned char* dst = lbase + lhead;
           if (lane == 0) {
-            hdr[tslot].ns = (int)ns; hdr[tslot].self0 = (int)self0 + 2 * cap_y; hdr[tslot].u0 = u0;
+            lstart[tslot] = lhead;
+            hdr[tslot].ns = (int)(ns | (lhead >> 4) << 16);  // low half: rows, high half: ring offset / 16
+            hdr[tslot].self0 = (int)self0 + 2 * cap_y; hdr[tslot].u0 = u0;
             mbar_arrive_expect_tx(&tfull[tslot], units_c * 16u + ns_c * 16u);
           }
           __syncwarp();
-          if (lane == 0 && units_c) bulk_g2s(dst, P.list + (size_t)u0 * 8, units * 16u, &tfull[tslot]);
-          if (lane == 1 && ns_c) bulk_g2s(dst + (size_t)P.cap_units * 16, P.meta + s0, ns * 16u, &tfull[tslot]);
+          if (lane == 1 && ns_c) bulk_g2s(dst, P.meta + s0, ns * 16u, &tfull[tslot]);
+          if (lane == 0 && units_c) bulk_g2s(dst + (size_t)ns * 16, P.list + (size_t)u0 * 8, units * 16u, &tfull[tslot]);
+          lhead += need;
           tseq++;
           if (++tslot == rl) tslot = 0;
         }
@@ -368,10 +395,10 @@ lj_celltile_force(const ct_params P) {
       u = u_next;
       col_cur = col_next;
     }
-    // end marker for the consumers: a tile header with ns < 0 (both producer warps arrive)
+    // end marker for the consumers: a tile header with ns = 0xffff (both producer warps arrive)
     if (tseq >= rl) ensure_done(tseq - rl);
     if (lane == 0) {
-      if (!isY) hdr[tslot].ns = -1;
+      if (!isY) hdr[tslot].ns = 0xffff;
       mbar_arrive(&tfull[tslot]);
       if (dbgp) {  // producer records: {idle, 0, tiles, total}
         long long* d = dbgp + ((size_t)gridDim.x * NCONS + 2 * blockIdx.x + (isY ? 0 : 1)) * 4;
@@ -413,8 +440,8 @@ lj_celltile_force(const ct_params P) {
       long long tw1 = 0;
       if (dbgp) { tw1 = clock64(); t_wait += tw1 - tw0; }
       const int4 h = *reinterpret_cast<const int4*>(&hdr[tslot]);  // ns, self0, u0, yslot0
-      const int ns = h.x;
-      if (ns < 0) break;  // end marker
+      const int ns = h.x & 0xffff;
+      if (ns == 0xffff) break;  // end marker
       constexpr int kRows = MX ? 32 / kCtLanesMx : 4;  // rows a warp works on in lock step
       const int nquads = (ns + kRows - 1) / kRows;
       int quad = first;
@@ -423,9 +450,9 @@ lj_celltile_force(const ct_params P) {
       if (quad < nquads && (modev & 15) != 3) {
         const int self0 = h.y;
         const uint32_t u0 = (uint32_t)h.z;
-        const unsigned char* lptr = lbase + (size_t)tslot * P.lslot_bytes;
-        const uint16_t* __restrict__ lst = reinterpret_cast<const uint16_t*>(lptr);
-        const int4* __restrict__ meta = reinterpret_cast<const int4*>(lptr + (size_t)P.cap_units * 16);
+        const unsigned char* lptr = lbase + (size_t)((uint32_t)h.x >> 16) * 16;  // [row metadata | list units]
+        const int4* __restrict__ meta = reinterpret_cast<const int4*>(lptr);
+        const uint16_t* __restrict__ lst = reinterpret_cast<const uint16_t*>(lptr + (size_t)ns * 16);
         // region-local index L -> ring record: (slot of the tile's first y-row) * cap_y + L, wrapped
         const uint32_t off0 = (uint32_t)h.w * (uint32_t)cap_y;
         if constexpr (MX) {
@@ -650,33 +677,47 @@ lj_celltile_force(const ct_params P) {
   }
 }
 
-// ring sizes for a CTA with `budget` bytes of dynamic shared memory.  A tile holds five y-rows and
-// one list slot; at a unit boundary the last tile of the old unit and the first tile of the new one
-// hold ten y-rows between them, so fewer than ten y slots drain the pipeline at every boundary.
-// Prefer >= 10 y slots, then balance the look-ahead of the two rings.
-static bool ring_sizes(size_t budget, size_t ys, size_t ls, int& ry, int& rl) {
-  int best = -1;
-  ry = rl = 0;
-  for (int l = kCtMaxL; l >= kTileMinLSlots; l--) {
-    if ((size_t)l * ls + kTileMinYSlots * ys > budget) continue;
-    int y = (int)((budget - (size_t)l * ls) / ys);
-    if (y > kCtMaxY) y = kCtMaxY;
-    int score = (y - 5 < l - 1) ? y - 5 : l - 1;
-    if (y >= 10 && l >= 3) score += 100;
-    if (score > best) { best = score; ry = y; rl = l; }
-  }
-  return best >= 0;
+// Ring sizes for a CTA with `budget` bytes of dynamic shared memory.  A tile holds five y-rows; at a unit
+// boundary the last tile of the old unit and the first tile of the new one hold ten y-rows between them, so
+// fewer than ten y slots drain the pipeline at every boundary, and every further slot is worth ~2 % (measured
+// 8 .. 11 slots: 0.342 / 0.334 / 0.324 / 0.318 ms).  The list ring is byte-granular: it must hold two tiles of
+// the longest kind (ls_max each), beyond that kCtListDepth AVERAGE tiles are enough and the rest of the
+// shared memory goes to y slots.
+constexpr int kCtListDepth = LJ_CT_LIST_DEPTH;
+static bool ring_sizes(size_t budget, size_t ys, size_t ls_max, size_t ls_avg, int& ry, int& rl, size_t& lring) {
+  ry = rl = 0; lring = 0;
+  const size_t lmin = 2 * ls_max;
+  size_t want = (size_t)kCtListDepth * ls_avg;
+  if (want < lmin) want = lmin;
+  if (want + kTileMinYSlots * ys > budget) want = lmin;
+  if (want + kTileMinYSlots * ys > budget) return false;
+  int y = (int)((budget - want) / ys);
+  if (y > kCtMaxY) y = kCtMaxY;
+  ry = y;
+  rl = kCtMaxL;
+  lring = (budget - (size_t)ry * ys) & ~(size_t)15;
+  return true;
+}
+// bytes an average tile takes in the list ring (row metadata + list units)
+static size_t avg_tile_bytes(const lj_ctx* ctx) {
+  const lj_tile_geom& g = ctx->tl_g;
+  const size_t tiles = g.ntiles > 0 ? (size_t)g.ntiles : 1;
+  size_t avg = 16 * ((size_t)g.total_units + (size_t)ctx->tl_pn) / tiles;
+  const size_t ls = lj_celltile_lslot_bytes(g);
+  if (avg < ls / 4) avg = ls / 4;  // (empty tiles in the count pull the mean down)
+  return (avg + 15) & ~(size_t)15;
 }
 
 template <int LAYOUT, bool MX, int NCONS, int NB>
 int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
-                    cudaStream_t st, int ry, int rl, int part) {
+                    cudaStream_t st, int ry, int rl, size_t lring, int part) {
   const lj_tile_geom& g = ctx->tl_g;
   const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
-  {  // diagnostics: cap the ring sizes
-    const int ry_env = lj_diag_int("LJ_TILE_RY"), rl_env = lj_diag_int("LJ_TILE_RL");
+  {  // diagnostics: cap the ring sizes (LJ_TILE_LRING in KB, not below two of the longest tiles)
+    const int ry_env = lj_diag_int("LJ_TILE_RY"), rl_env = lj_diag_int("LJ_TILE_RL"), lr_env = lj_diag_int("LJ_TILE_LRING");
     if (ry_env >= kTileMinYSlots && ry_env < ry) ry = ry_env;
     if (rl_env >= kTileMinLSlots && rl_env < rl) rl = rl_env;
+    if (lr_env > 0 && (size_t)lr_env * 1024 < lring && (size_t)lr_env * 1024 >= 2 * ls) lring = (size_t)lr_env * 1024;
   }
   const int seg_env = lj_diag_int("LJ_TILE_SEG");
   // columns without a single list entry (the ghost layers of a decomposed run) are skipped
@@ -742,7 +783,7 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
     P.ncols_dev = &ctx->tl_geom->pad2;
   }
   P.cap_y = lj_celltile_cap_y(g); P.cap_units = g.max_units; P.cap_rows = g.max_rows;
-  P.ry = ry; P.rl = rl; P.lslot_bytes = (int)ls;
+  P.ry = ry; P.rl = rl; P.lring_bytes = (int)lring;
   P.mode = lj_diag_int("LJ_TILE_MODE");
   P.unit_counter = &ctx->tl_geom->pad;
   P.dbg = nullptr;
@@ -752,15 +793,15 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
     P.dbg = ctx->diag_buf;
   }
 #endif
-  const size_t smem = (size_t)ry * ys + (size_t)rl * ls;
+  const size_t smem = (size_t)ry * ys + lring;
   auto kern = lj_celltile_force<LAYOUT, MX, NCONS, NB>;
   LJ_FUNC_SMEM(ctx, kern, smem);
   const int nunits = ncols * nseg;  // part launches: an upper bound, CTAs without a unit leave at once
   const int grid = nunits < NB * ctx->sm_count ? nunits : NB * ctx->sm_count;
   if (lj_diag_set("LJ_TILE_DEBUG"))
     fprintf(stderr, "[lj] cell-tile force: %d consumer warps, %d units (%d columns x %d segments of %d), "
-            "y ring %d x %zu B, list ring %d x %zu B, smem %zu B\n", NCONS, nunits, ncols, nseg, seg_len, ry, ys, rl,
-            ls, smem);
+            "y ring %d x %zu B, list ring %zu B for %d tiles in flight (longest tile %zu B), smem %zu B\n", NCONS, nunits,
+            ncols, nseg, seg_len, ry, ys, lring, rl, ls, smem);
   kern<<<(unsigned)grid, (NCONS + 2) * 32, smem, st>>>(P);
   LJ_LAUNCHED(ctx);
 #if LJ_DIAG
@@ -807,21 +848,23 @@ int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c4
                       cudaStream_t st, int part) {
   const lj_tile_geom& g = ctx->tl_g;
   const size_t ys = (size_t)lj_celltile_cap_y(g) * (MX ? 16 : 24), ls = lj_celltile_lslot_bytes(g);
+  const size_t la = avg_tile_bytes(ctx);
   int ry = 0, rl = 0;
+  size_t lring = 0;
 #if LJ_DIAG
   const int nc = lj_diag_int("LJ_TILE_CONSUMERS");
   if (nc == 8) {  // two CTAs per SM (measured slower: two pipelines, twice the producers)
     const size_t half = (size_t)(227 * 1024) / 2 - 9 * 1024;
-    LJ_REQUIRE(ctx, ring_sizes(half, ys, ls, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
-    return launch_celltile<LAYOUT, MX, 8, 2>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
+    LJ_REQUIRE(ctx, ring_sizes(half, ys, ls, la, ry, rl, lring), "lj_force_step: cell-tile geometry does not fit in shared memory");
+    return launch_celltile<LAYOUT, MX, 8, 2>(ctx, a, c24, c48, cl2_bits, st, ry, rl, lring, part);
   }
-  if (nc == 24 && ring_sizes(kTileSmemBudget, ys, ls, ry, rl))
-    return launch_celltile<LAYOUT, MX, 24, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
-  if (nc == 20 && ring_sizes(kTileSmemBudget, ys, ls, ry, rl))
-    return launch_celltile<LAYOUT, MX, 20, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
+  if (nc == 24 && ring_sizes(kTileSmemBudget, ys, ls, la, ry, rl, lring))
+    return launch_celltile<LAYOUT, MX, 24, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, lring, part);
+  if (nc == 20 && ring_sizes(kTileSmemBudget, ys, ls, la, ry, rl, lring))
+    return launch_celltile<LAYOUT, MX, 20, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, lring, part);
 #endif
-  LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, ry, rl), "lj_force_step: cell-tile geometry does not fit in shared memory");
-  return launch_celltile<LAYOUT, MX, 16, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, part);
+  LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, la, ry, rl, lring), "lj_force_step: cell-tile geometry does not fit in shared memory");
+  return launch_celltile<LAYOUT, MX, 16, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, lring, part);
 }
 
 }  // namespace

@@ -17,6 +17,13 @@
 #include "lj_celltile.cuh"
 #include "lj_common.cuh"
 
+#ifndef LJ_TILE_ROWS_WIDE
+#define LJ_TILE_ROWS_WIDE 72
+#endif
+#ifndef LJ_TILE_ROWS_STD
+#define LJ_TILE_ROWS_STD 56
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------ small utilities ---
@@ -1017,7 +1024,7 @@ __device__ __forceinline__ int te_row_cell(const int* __restrict__ xoff_c, int n
   return kx;
 }
 
-// COUNT pass, second form: ONE THREAD PER (row, pencil).  A tile of ~40 rows has 1000 such jobs, lanes are
+// COUNT pass, second form: ONE THREAD PER (row, pencil).  A tile of ~56 rows has 1400 such jobs, lanes are
 // consecutive rows of one pencil, so the lanes of a warp read the same few candidate records (rows that are
 // neighbours in cell order share their window: a multicast shared-memory load), nobody waits for a slower
 // lane (the trip count is the warp's largest window, rounded to 8) and there is no per-pencil set-up shared
@@ -1026,7 +1033,7 @@ __device__ __forceinline__ int te_row_cell(const int* __restrict__ xoff_c, int n
 // (the window of a row is that of its PAIR (2k, 2k + 1): k_tile_replay recomputes it), mask bit b = window
 // record b, masks stored pencil-major (masks[p * pn + s]: a warp writes 256 contiguous bytes).
 constexpr int kTcThreads = 256;
-constexpr int kTcRowChunk = 128;  // rows of a tile worked on at a time (tiles hold ~40-60)
+constexpr int kTcRowChunk = 128;  // rows of a tile worked on at a time (tiles hold ~56, ~72 wide)
 
 #define LJ_TC_TEST(H, U, J)                                                                                         \
   {                                                                                                                 \
@@ -1622,7 +1629,7 @@ static int build_tile_mirror(lj_ctx* ctx, const lj_list_args* a, cudaStream_t st
     ctx->tl_pn_cap = pn;
   }
   const int rows_env = lj_diag_int("LJ_TILE_ROWS");
-  const int target_rows = rows_env > 0 ? rows_env : (a->flags & LJ_LIST_TILES_WIDE) ? 56 : 40;
+  const int target_rows = rows_env > 0 ? rows_env : (a->flags & LJ_LIST_TILES_WIDE) ? LJ_TILE_ROWS_WIDE : LJ_TILE_ROWS_STD;
   k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
   LJ_LAUNCHED(ctx);
   k_tile_rows<<<(unsigned)blocks_for(pn + 1, 256), 256, 0, st>>>(pn, sorted_pos32, a->number_of_partners,
@@ -1761,7 +1768,7 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a_in, cudaStream_t 
     ctx->tl_pn_cap = pn;
   }
   const int rows_env = lj_diag_int("LJ_TILE_ROWS");
-  const int target_rows = rows_env > 0 ? rows_env : (a->flags & LJ_LIST_TILES_WIDE) ? 56 : 40;
+  const int target_rows = rows_env > 0 ? rows_env : (a->flags & LJ_LIST_TILES_WIDE) ? LJ_TILE_ROWS_WIDE : LJ_TILE_ROWS_STD;
   k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
   LJ_LAUNCHED(ctx);
   // read-back 1: the grid and the tile count (size the tables and the launches)
@@ -1941,7 +1948,7 @@ static int list_mirror_impl(lj_ctx* ctx, const lj_list_args* a, int64_t* rows_ou
     if ((rc = tile_alloc(ctx, (void**)&ctx->tl_slot_of, sizeof(int32_t) * (size_t)pn, st))) return rc;
     ctx->tl_slot_cap = pn;
   }
-  const int target_rows = (a->flags & LJ_LIST_TILES_WIDE) ? 56 : 40;
+  const int target_rows = (a->flags & LJ_LIST_TILES_WIDE) ? LJ_TILE_ROWS_WIDE : LJ_TILE_ROWS_STD;
   k_tile_prepare<<<1, 1, 0, st>>>(ge, pn, target_rows, ctx->tl_geom);
   LJ_LAUNCHED(ctx);
   // rows in cell order with the caller's counts, their padded lengths and offsets

@@ -28,4 +28,4 @@ for _ in range(a.reps):
     ctx.rebuild(qd, pl, tiles=tiles)
 e1.record()
 torch.cuda.synchronize()
-print("N=%d pairs=%d  list build %.4f ms (%s tiles)" % (len(q), pl.number_of_pairs, e0.elapsed_time(e1) / a.reps, "wide" if a.wide else "40-row"))
+print("N=%d pairs=%d  list build %.4f ms (%s tiles)" % (len(q), pl.number_of_pairs, e0.elapsed_time(e1) / a.reps, "wide" if a.wide else "standard"))
