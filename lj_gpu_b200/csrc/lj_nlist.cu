@@ -967,10 +967,20 @@ k_tile_zflag(int64_t pn, int64_t r0, int64_t r1, const int32_t* __restrict__ cel
 // window = the five x-cells around its own cell).  After the scans, k_tile_replay walks the masks
 // and writes both lists without looking at a single position.  Membership is decided by the same
 // tests as k_search (FP32 on origin-shifted coordinates, the exact FP64 fma chain inside the error
-// band), rows are emitted in the same order as k_tile_fill did (pencil dz-major, cell order within).
+// band); a row's entries are emitted pencil by pencil in the order kTePerm, cell order within a pencil.
 constexpr int kTeThreads = 192;  // replay / translate: six warps, four rows of eight lanes each
 constexpr int kTeLanes = 8;      // lanes per row (pair), four per warp
-constexpr int kTeRowCap = 256;   // replay: entries of a row staged in shared memory (longer rows are written directly)
+constexpr int kTeRowKx = 256;    // replay: rows of a tile whose region x-cell is tabulated (tiles hold ~56-72)
+constexpr int kTeRowCap = 256;   // replay: entries of a row staged in shared memory at most (longer rows are written directly);
+                                 // the launch sizes the staging area for the longest row of THIS list (occupancy: the pass is
+                                 // latency-bound, 256 entries per row = 5 CTAs per SM, 176 = 6: 1.40 -> 1.29 ms per build)
+
+// replay: bytes a row group takes in the staging area (rowcap 4-byte + rowcap 2-byte entries, padded: see the kernel)
+__host__ __device__ inline uint32_t te_group_stride(int rowcap) {
+  uint32_t w = ((uint32_t)rowcap * 6u + 3u) / 4u;
+  w += (8u - (w & 31u)) & 31u;
+  return w * 4u;
+}
 
 struct te_pencil { uint32_t st, base, len; int rowc; };  // cell-order start, region-local index of its first record,
                                                           // records, first cell of the (y,z) row (-1: outside the grid)
@@ -1155,20 +1165,28 @@ k_tile_count2(int64_t pn, int64_t r0, int64_t r1, const grid_ext* __restrict__ g
 // indices), both at the offsets the scans produced.  No positions are read.  A row's entries are
 // expanded into shared memory (each lane its pencils, scattered) and written out by the row's eight
 // lanes in runs of eight consecutive entries: 16 contiguous bytes of the mirror, 32 of the list.
+// replay: the order in which a row's 25 pencils (p = dz * 5 + dy) are expanded, by expected number of hits:
+// (0,0); the four with |dy| + |dz| = 1; (+-1,+-1); (+-2,0), (0,+-2); the eight (+-2,+-1), (+-1,+-2); the corners
+__constant__ unsigned char kTePerm[32] = {12, 7,  11, 13, 17, 6,  8,  16,  18, 2,  10, 14, 22, 1,  3,  5,
+                                          9,  15, 19, 21, 23, 0,  4,  20,  24, 255, 255, 255, 255, 255, 255, 255};
+
+#ifndef LJ_TE_MINBLOCKS
+#define LJ_TE_MINBLOCKS 7  // 48 registers: seven CTAs per SM (the pass waits on dependent global loads)
+#endif
 template <bool PTR64>
-__global__ void __launch_bounds__(kTeThreads)
+__global__ void __launch_bounds__(kTeThreads, LJ_TE_MINBLOCKS)
 k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* __restrict__ cell_start,
               const uint2* __restrict__ ytab, int ncx1, const int32_t* __restrict__ tl_order,
               const int32_t* __restrict__ tl_cnt, const uint32_t* __restrict__ tl_off,
               const unsigned long long* __restrict__ masks, uint16_t* __restrict__ tl_list,
-              const void* __restrict__ pointer, int32_t* __restrict__ list, int64_t capacity,
+              const void* __restrict__ pointer, int32_t* __restrict__ list, int64_t capacity, int rowcap,
               lj_list_totals* __restrict__ tot) {
   extern __shared__ __align__(16) unsigned char te_smem[];
   const lj_tile_geom g = *tgp;
   const uint32_t cap_y = (uint32_t)((g.max_yrow + 8 + 1) & ~1);
   te_pencil* pen = reinterpret_cast<te_pencil*>(te_smem);
   int* xoff = reinterpret_cast<int*>(pen + 25);
-  // per row group: kTeRowCap x {cell-order index of j (4 B)} then kTeRowCap x {region-local index (2 B)}
+  // per row group: rowcap x {cell-order index of j (4 B)} then rowcap x {region-local index (2 B)}
   unsigned char* stage = reinterpret_cast<unsigned char*>(xoff + 25 * ncx1);
   int ncx;
   uint32_t s0, ns;
@@ -1179,8 +1197,18 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
   const te_pencil pc = pen[12];
   const int* xoff_c = xoff + 12 * ncx1;
   const uint16_t dummy = (uint16_t)(cap_y - 1);  // last record of the dy = 0 ring slot: far-away point
-  uint32_t* sm_m = reinterpret_cast<uint32_t*>(stage + (size_t)(warp * 4 + gi) * kTeRowCap * 6);
-  uint16_t* sm_l = reinterpret_cast<uint16_t*>(sm_m + kTeRowCap);
+  // region x-cell of every row, once per tile (one thread per row) instead of twice per row group by all of
+  // its lanes: the linear search was 18 % of the kernel's instructions
+  __shared__ unsigned char rowkx[kTeRowKx];
+  const uint32_t ntab = ncx <= 256 ? min(ns, (uint32_t)kTeRowKx) : 0u;  // (an x-cell fits in a byte)
+  for (uint32_t r = threadIdx.x; r < ntab; r += kTeThreads)
+    rowkx[r] = (unsigned char)te_row_cell(xoff_c, ncx, s0 + r - pc.st);
+  __syncthreads();
+  // stride of a row group: 8 words mod 32, so that the four groups of a warp (same k, eight consecutive words
+  // each) read four different sets of banks in the write-out loop
+  const uint32_t gstride = te_group_stride(rowcap);
+  uint32_t* sm_m = reinterpret_cast<uint32_t*>(stage + (size_t)(warp * 4 + gi) * gstride);
+  uint16_t* sm_l = reinterpret_cast<uint16_t*>(sm_m + rowcap);
   for (uint32_t rb = warp * 4; rb < ns; rb += (kTeThreads / 32) * 4) {
     const uint32_t r = rb + gi;
     const bool valid = r < ns;
@@ -1189,8 +1217,9 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
     if (want == 0) continue;  // (whole groups: the eight lanes of a row agree)
     // the window of the COUNT pass: shared with the other row of the pair (2k, 2k + 1)
     const uint32_t rp = (r ^ 1u) < ns ? (r ^ 1u) : r;
-    const int kx = te_row_cell(xoff_c, ncx, s - pc.st);
-    const int kxp = te_row_cell(xoff_c, ncx, s0 + rp - pc.st);
+    const uint32_t rv = valid ? r : 0u;
+    const int kx = rv < ntab ? rowkx[rv] : te_row_cell(xoff_c, ncx, s - pc.st);
+    const int kxp = rp < ntab ? rowkx[rp] : te_row_cell(xoff_c, ncx, s0 + rp - pc.st);
     const int* xlo = xoff + max(min(kx, kxp) - 2, 0);
     const size_t base = (size_t)tl_off[s] * 8;
     const int i = tl_order[s];
@@ -1200,14 +1229,16 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
       if (lg == 0) atomicOr(&tot->overflow, 1);
       pub = false;
     }
-    const bool staged = want <= kTeRowCap;
-    // lane lg owns pencils lg, lg + 8, lg + 16 (and 24 for lg = 0); entries are emitted in pencil order
+    const bool staged = want <= rowcap;
+    // lane lg owns the pencils kTePerm[lg], [lg + 8], [lg + 16] (and [24] for lg = 0); entries are emitted in
+    // that order.  The eight pencils of a step hold about the same number of hits (the step costs its longest
+    // mask): the centre pencil and its nearest eight first, the corners last.
     unsigned long long mk[4];
     int before = 0;  // entries of all earlier pencils
     int off[4];
 #pragma unroll
     for (int q4 = 0; q4 < 4; q4++) {
-      const int p = q4 * kTeLanes + lg;
+      const int p = kTePerm[q4 * kTeLanes + lg];
       mk[q4] = p < 25 ? masks[(size_t)p * (size_t)pn + s] : 0ull;  // (pencil-major: four rows of a warp = one sector)
       const int c = __popcll(mk[q4]);
       int inc = c;  // inclusive scan over the eight lanes of the row
@@ -1222,7 +1253,7 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
     if (before != want) { if (lg == 0) atomicOr(&tot->overflow, 8); continue; }  // cannot happen
 #pragma unroll
     for (int q4 = 0; q4 < 4; q4++) {
-      const int p = q4 * kTeLanes + lg;
+      const int p = kTePerm[q4 * kTeLanes + lg];
       if (p >= 25) continue;
       const te_pencil e = pen[p];
       const int w0 = xlo[p * ncx1];
@@ -1885,17 +1916,19 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a_in, cudaStream_t 
     ctx->last_capacity = a->capacity;
   }
   // staged entries of a tile (6 B each) + tables + per-row arrays (see k_tile_replay2)
-  const size_t smem_replay = smem_tab + (size_t)(kTeThreads / kTeLanes) * kTeRowCap * 6;
+  int rowcap = (ctx->totals_host->max_np + 7) & ~7;  // (read-back 3) a multiple of 8: the 4-byte plane stays aligned
+  rowcap = rowcap < 64 ? 64 : rowcap > kTeRowCap ? kTeRowCap : rowcap;
+  const size_t smem_replay = smem_tab + (size_t)(kTeThreads / kTeLanes) * te_group_stride(rowcap);
   LJ_FUNC_SMEM(ctx, k_tile_replay<true>, smem_replay);
   LJ_FUNC_SMEM(ctx, k_tile_replay<false>, smem_replay);
   if (a->pointer64)
     k_tile_replay<true><<<(unsigned)g.ntiles, kTeThreads, smem_replay, st>>>(
         pn, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ncx1, ctx->tl_order, ctx->tl_cnt, ctx->tl_off, masks, ctx->tl_list,
-        a->pointer, a->sorted_list, a->capacity, ctx->totals);
+        a->pointer, a->sorted_list, a->capacity, rowcap, ctx->totals);
   else
     k_tile_replay<false><<<(unsigned)g.ntiles, kTeThreads, smem_replay, st>>>(
         pn, ctx->tl_geom, ctx->tl_cell_start, ctx->tl_tab, ncx1, ctx->tl_order, ctx->tl_cnt, ctx->tl_off, masks, ctx->tl_list,
-        a->pointer, a->sorted_list, a->capacity, ctx->totals);
+        a->pointer, a->sorted_list, a->capacity, rowcap, ctx->totals);
   LJ_LAUNCHED(ctx);
   LJ_CUDA(ctx, cudaFreeAsync(masks, st));
   // read-back 4 is not needed: the geometry is final since read-back 3 (k_tile_cols included); the
