@@ -24,7 +24,7 @@
 //     sums, FP64 reduction and momenta.  Pairs within the FP32 error band of the cutoff are left
 //     out of the hot loop and re-decided in FP64 from the caller's positions (rare rows only).
 //
-// Sixteen consumer warps: eight lanes per row, four rows (a quad) per warp in lock step with
+// Twenty consumer warps (FP64; twenty-four in mixed precision: LJ_CT_NCONS / LJ_CT_NCONS_MX): eight lanes per row, four rows (a quad) per warp in lock step with
 // warp-uniform trip counts, quads dealt round-robin across tiles, shuffle reduction, one
 // RED.ADD.F64 per component and row (exactly one add per step: deterministic).  FP64 results are
 // bit-identical to the per-row kernel with group = 8 on the same list order.  Positions are
@@ -66,6 +66,15 @@ constexpr int kCtLanesMx = LJ_CT_LANES_MX;  // lanes per row in the mixed kernel
 #define LJ_CT_GRADE_MIN 3
 #endif
 constexpr bool kCtGraded = LJ_CT_GRADED != 0;  // graded column segments (see launch_celltile)
+// Consumer warps of the product kernels.  Measured on the byte-granular ring (same box, 100 launches, bit-exact):
+// FP64 16 / 17 / 18 / 20 / 22 / 24 warps -> 0.2926 / 0.3163 / 0.3024 / 0.2904 / 0.2974 / 0.2927 ms (80 registers at 20,
+// no spills); mixed 16 / 20 / 22 / 24 -> 0.2343 / 0.2316 / 0.2305 / 0.2284 ms (64-72 registers).
+#ifndef LJ_CT_NCONS
+#define LJ_CT_NCONS 20
+#endif
+#ifndef LJ_CT_NCONS_MX
+#define LJ_CT_NCONS_MX 24
+#endif
 #ifndef LJ_CT_ALU_SUB
 #define LJ_CT_ALU_SUB 0  // 1: integer differences as VIADDMNMX on the ALU pipe (measured: no gain)
 #endif
@@ -842,7 +851,8 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
   return LJ_OK;
 }
 
-// 16 consumer warps + 2 producer warps in one CTA per SM; other layouts in diagnostic builds only
+// LJ_CT_NCONS (FP64) / LJ_CT_NCONS_MX (mixed) consumer warps + 2 producer warps in one CTA per SM; other layouts in
+// diagnostic builds only
 template <int LAYOUT, bool MX>
 int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48, long long cl2_bits,
                       cudaStream_t st, int part) {
@@ -864,7 +874,7 @@ int dispatch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c4
     return launch_celltile<LAYOUT, MX, 20, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, lring, part);
 #endif
   LJ_REQUIRE(ctx, ring_sizes(kTileSmemBudget, ys, ls, la, ry, rl, lring), "lj_force_step: cell-tile geometry does not fit in shared memory");
-  return launch_celltile<LAYOUT, MX, 16, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, lring, part);
+  return launch_celltile<LAYOUT, MX, MX ? LJ_CT_NCONS_MX : LJ_CT_NCONS, 1>(ctx, a, c24, c48, cl2_bits, st, ry, rl, lring, part);
 }
 
 }  // namespace

@@ -842,16 +842,17 @@ def test_celltile_moving_particles_rebuild_and_row_ranges(ctx, torch, sysS):
     s = sysS
     qd, pd = s.device_arrays(torch, "aos4")
     qr, pr = qd.clone(), pd.clone()
-    pl = ctx.makepair(qd, tiles=True)
-    plr = ctx.makepair(qr)
-    pl = ctx.makepair(qd, tiles=True)                    # the plain build above dropped the mirror
+    # the reference run uses the per-row kernel on a list of its own from the same engine: the order of a row's
+    # entries is unspecified by contract and differs between the engines, bit equality needs the same order
+    plr = ctx.makepair(qr, tiles=True)
+    pl = ctx.makepair(qd, tiles=True)                    # (one mirror per context: this build replaces plr's)
     for step in range(12):                                # kick + drift, list reused (skin 0.3)
         ctx.force_step(qd, pd, pl, variant="celltile")
         ctx.drift(qd, pd)
         ctx.force_step(qr, pr, plr, variant="subwarp", group=8)
         ctx.drift(qr, pr)
         if step == 5:                                     # rebuild both lists in place mid-run
-            ctx.rebuild(qr, plr)
+            ctx.rebuild(qr, plr, tiles=True)
             ctx.rebuild(qd, pl, tiles=True)
     assert torch.equal(qd, qr) and torch.equal(pd, pr)
     # rebuild() reuses the flags the list was built with (the mirror is rebuilt with the list) ...
