@@ -835,6 +835,33 @@ def test_celltile_random_cloud_and_clusters_of_particles(ctx, torch, oracle):
     ctx.force_step(qd, p1, pl, layout="aos3", dt=1e-9)
 
 
+def test_tile_engine_rows_longer_than_the_staging_area(ctx, torch, oracle):
+    """Search length 4.4 at rho = 1.0: up to 368 partners per row, more than the 256 entries per row
+    the replay pass of the tile engine stages in shared memory at most (longer rows are written
+    directly; where a (row, pencil) window exceeds 64 records the round-1 engine serves the build) and
+    46 trips per row in the cell-tile force kernel.  List against the oracle, both force kernels on it
+    against the oracle's gather and against each other bit for bit."""
+    from lj_gpu_b200 import init_fcc
+    q = init_fcc(1.0, 15.0)
+    pn = len(q)
+    search, cutoff = 4.4, 4.0
+    nop_o, ptr_o, lst_o = oracle.makepair(q, search_len=search, full=True)
+    assert nop_o.max() > 256
+    q4 = np.zeros((pn, 4)); q4[:, :3] = q
+    qd = torch.from_numpy(q4).cuda()
+    pl = ctx.makepair(qd, search_len=search, tiles=True)
+    nop, ptr, lst = list_to_host(pl)
+    assert np.array_equal(nop[:pn], nop_o)
+    assert np.array_equal(_rows_as_sets(nop, ptr, lst, pn), _rows_as_sets(nop_o, ptr_o, lst_o, pn))
+    p1 = torch.zeros_like(qd); p2 = torch.zeros_like(qd)
+    ctx.force_loop(qd, p1, pl, loop=5, variant="celltile", cl2=cutoff * cutoff)
+    ctx.force_loop(qd, p2, pl, loop=5, variant="subwarp", group=8, cl2=cutoff * cutoff)
+    assert torch.equal(p1, p2)
+    po = np.zeros((pn, 3))
+    oracle.force_gather(q, po, nop_o, ptr_o, lst_o, steps=5, cl2=cutoff * cutoff, static_q=True)
+    assert np.abs(p1.cpu().numpy()[:, :3] - po).max() / np.abs(po).max() < TOL_FP64
+
+
 def test_celltile_moving_particles_rebuild_and_row_ranges(ctx, torch, sysS):
     """The mirror is a LIST: it stays valid while particles move (positions are re-permuted every
     step), it is rebuilt with the list, and it serves exactly the row range it was built for."""
