@@ -1777,7 +1777,25 @@ static int build_list_tiles(lj_ctx* ctx, const lj_list_args* a_in, cudaStream_t 
   int rc = bin_particles<LAYOUT>(ctx, a, st);
   if (rc) return rc;
   const size_t mask_bytes = sizeof(unsigned long long) * 25 * (size_t)pn;
-  if (mask_bytes > ((size_t)16 << 30)) return LJ_OK;
+  if (mask_bytes > ((size_t)16 << 30)) {
+    // A big system (config 5 on one GPU: 26 GB of masks beside a 70 GB list): only when the device has the
+    // room -- what the driver reports free plus what this context's pool holds cached -- for the masks, the
+    // mirror (2 B per entry + padding, unless one of that size exists) and the per-row arrays, with 8 GiB to
+    // spare; otherwise the round-1 engine builds the list without mask scratch.
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return LJ_OK; }
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += (size_t)(reserved - used);
+    else
+      cudaGetLastError();
+    const size_t entries = a->capacity > 0 ? (size_t)a->capacity : (size_t)pn * 160;
+    size_t need = mask_bytes + ((size_t)8 << 30);
+    if (16 * (size_t)ctx->tl_list_cap < entries * 2) need += entries * 2 + entries / 4;
+    if (pn > ctx->tl_pn_cap) need += (size_t)pn * 64;
+    if (free_b < need) return LJ_OK;
+  }
   grid_ext* ge = reinterpret_cast<grid_ext*>(ctx->grid);
   float4* sorted_pos32 = reinterpret_cast<float4*>(ctx->sorted_pos + pn);
   if (ctx->cl_valid && (ctx->cl_id_list == a->sorted_list || ctx->cl_id_nop == a->number_of_partners ||
