@@ -1213,6 +1213,13 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
     const uint32_t r = rb + gi;
     const bool valid = r < ns;
     const uint32_t s = s0 + (valid ? r : 0u);
+    // the row's masks are requested together with its count: one round trip to global memory instead of two
+    unsigned long long mk[4];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      const int p = kTePerm[q4 * kTeLanes + lg];
+      mk[q4] = (valid && p < 25) ? masks[(size_t)p * (size_t)pn + s] : 0ull;  // (pencil-major: four rows of a warp = one sector)
+    }
     const int want = valid ? tl_cnt[s] : 0;
     if (want == 0) continue;  // (whole groups: the eight lanes of a row agree)
     // the window of the COUNT pass: shared with the other row of the pair (2k, 2k + 1)
@@ -1233,13 +1240,10 @@ k_tile_replay(int64_t pn, const lj_tile_geom* __restrict__ tgp, const uint32_t* 
     // lane lg owns the pencils kTePerm[lg], [lg + 8], [lg + 16] (and [24] for lg = 0); entries are emitted in
     // that order.  The eight pencils of a step hold about the same number of hits (the step costs its longest
     // mask): the centre pencil and its nearest eight first, the corners last.
-    unsigned long long mk[4];
     int before = 0;  // entries of all earlier pencils
     int off[4];
 #pragma unroll
     for (int q4 = 0; q4 < 4; q4++) {
-      const int p = kTePerm[q4 * kTeLanes + lg];
-      mk[q4] = p < 25 ? masks[(size_t)p * (size_t)pn + s] : 0ull;  // (pencil-major: four rows of a warp = one sector)
       const int c = __popcll(mk[q4]);
       int inc = c;  // inclusive scan over the eight lanes of the row
 #pragma unroll
