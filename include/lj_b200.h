@@ -99,6 +99,13 @@ LJ_API const char* lj_last_error_string(lj_ctx* ctx);
 LJ_API const char* lj_status_string(int status);
 /* number of kernels this library has launched through `ctx` since creation */
 LJ_API int64_t lj_launch_count(lj_ctx* ctx);
+/* Live timing of the DOMINANT force kernel alone (lj_celltile_force, the kernel AUTO runs on large systems):
+ * while enabled, every launch of it outside a stream capture is bracketed by two CUDA events on the launching
+ * stream.  lj_kernel_timing(ctx, 1) starts with empty sums, (ctx, 0) stops; lj_kernel_timing_read() waits for
+ * the recorded launches and returns their summed duration and their number.  Measurement aid for the roofline
+ * of bench.py (the reference has no counterpart: its measure() times the whole loop, cuda/force_cuda.cu:319-342). */
+LJ_API int lj_kernel_timing(lj_ctx* ctx, int enable);
+LJ_API int lj_kernel_timing_read(lj_ctx* ctx, double* total_ms_out, int64_t* launches_out);
 /* the context's own non-blocking stream (a cudaStream_t) */
 LJ_API void* lj_ctx_stream(lj_ctx* ctx);
 LJ_API int lj_device_sm_count(lj_ctx* ctx);

@@ -91,6 +91,8 @@ PROTOTYPES = {
     "lj_last_error_string": (C.c_char_p, [_vp]),
     "lj_status_string": (C.c_char_p, [C.c_int]),
     "lj_launch_count": (_i64, [_vp]),
+    "lj_kernel_timing": (C.c_int, [_vp, C.c_int]),
+    "lj_kernel_timing_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "lj_ctx_stream": (_vp, [_vp]),
     "lj_device_sm_count": (C.c_int, [_vp]),
     "lj_buf_allocate": (C.c_int, [_vp, _sz, C.POINTER(LjBuf), _vp]),

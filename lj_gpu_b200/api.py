@@ -179,6 +179,16 @@ class LJContext:
     def launches(self) -> int:
         return int(self.lib.lj_launch_count(self.h))
 
+    def kernel_timing(self, enable: bool = True) -> None:
+        """Start (with empty sums) / stop the live CUDA-event timing of the dominant force kernel alone."""
+        self._check(self.lib.lj_kernel_timing(self.h, 1 if enable else 0))
+
+    def kernel_timing_read(self):
+        """-> (summed milliseconds, launches) of the dominant force kernel since kernel_timing(True)."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        self._check(self.lib.lj_kernel_timing_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
     def sync(self, stream=None):
         self._check(self.lib.lj_sync(self.h, self._stream(stream)))
 

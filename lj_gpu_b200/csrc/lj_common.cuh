@@ -54,6 +54,14 @@ struct lj_ctx {
   int64_t launches = 0;
   std::string err;
 
+  // lj_kernel_timing: CUDA events around every launch of the dominant force kernel (lj_celltile_force), on the
+  // launching stream; a ring of event pairs, folded into the sums when a pair is reused or the sums are read
+  bool kt_on = false;
+  cudaEvent_t kt_ev[2 * 64] = {};
+  int kt_head = 0, kt_pending = 0;   // next pair to use; pairs recorded and not folded yet
+  double kt_ms = 0.0;
+  int64_t kt_launches = 0;
+
   // pinned staging ring for pageable host memory (lj_upload / lj_download)
   void* ring[2] = {nullptr, nullptr};
   cudaEvent_t ring_ev[2] = {nullptr, nullptr};
@@ -155,6 +163,7 @@ struct lj_ctx {
 };
 
 int lj_set_error(lj_ctx* ctx, int status, const char* what, const char* detail);
+cudaEvent_t lj_kernel_timing_event(lj_ctx* ctx, cudaStream_t st, bool first);  // lj_runtime.cu (lj_kernel_timing)
 
 #define LJ_CUDA(ctx, call)                                                            \
   do {                                                                                \

@@ -811,7 +811,10 @@ int launch_celltile(lj_ctx* ctx, const lj_force_args* a, double c24, double c48,
     fprintf(stderr, "[lj] cell-tile force: %d consumer warps, %d units (%d columns x %d segments of %d), "
             "y ring %d x %zu B, list ring %zu B for %d tiles in flight (longest tile %zu B), smem %zu B\n", NCONS, nunits,
             ncols, nseg, seg_len, ry, ys, lring, rl, ls, smem);
+  cudaEvent_t kt0 = lj_kernel_timing_event(ctx, st, true);  // lj_kernel_timing: this kernel alone, live
+  if (kt0) cudaEventRecord(kt0, st);
   kern<<<(unsigned)grid, (NCONS + 2) * 32, smem, st>>>(P);
+  if (kt0) cudaEventRecord(lj_kernel_timing_event(ctx, st, false), st);
   LJ_LAUNCHED(ctx);
 #if LJ_DIAG
   if (P.dbg) {  // diagnostics only: synchronises

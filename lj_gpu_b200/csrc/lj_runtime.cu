@@ -51,6 +51,44 @@ int lj_func_smem(lj_ctx* ctx, const void* kern, size_t bytes) {
   return LJ_OK;
 }
 
+// ---- lj_kernel_timing: event pairs around the dominant force kernel (see lj_b200.h) ----
+static void kt_fold(lj_ctx* ctx, int pair) {  // waits for the pair's second event
+  float ms = 0.f;
+  if (cudaEventSynchronize(ctx->kt_ev[2 * pair + 1]) == cudaSuccess &&
+      cudaEventElapsedTime(&ms, ctx->kt_ev[2 * pair], ctx->kt_ev[2 * pair + 1]) == cudaSuccess) {
+    ctx->kt_ms += ms;
+    ctx->kt_launches++;
+  } else {
+    cudaGetLastError();
+  }
+}
+static void kt_fold_all(lj_ctx* ctx) {
+  const int n = 64;
+  for (int k = ctx->kt_pending; k > 0; k--) kt_fold(ctx, ((ctx->kt_head - k) % n + n) % n);
+  ctx->kt_pending = 0;
+}
+// called by the launcher of the dominant kernel: the event to record BEFORE (first = true) / AFTER the launch,
+// or nullptr when timing is off or the stream is being captured
+cudaEvent_t lj_kernel_timing_event(lj_ctx* ctx, cudaStream_t st, bool first) {
+  if (!ctx->kt_on) return nullptr;
+  const int n = 64;
+  if (first) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+    if (ctx->kt_pending == n) { kt_fold(ctx, ctx->kt_head); ctx->kt_pending--; }  // the oldest pair is reused
+    for (int e = 0; e < 2; e++)
+      if (!ctx->kt_ev[2 * ctx->kt_head + e] && cudaEventCreate(&ctx->kt_ev[2 * ctx->kt_head + e]) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+    return ctx->kt_ev[2 * ctx->kt_head];
+  }
+  cudaEvent_t e = ctx->kt_ev[2 * ctx->kt_head + 1];
+  ctx->kt_head = (ctx->kt_head + 1) % n;
+  ctx->kt_pending++;
+  return e;
+}
+
 extern "C" {
 
 const char* lj_status_string(int s) {
@@ -117,6 +155,8 @@ int lj_ctx_destroy(lj_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->totals_host) cudaFreeHost(ctx->totals_host);
   if (ctx->tl_geom_host) cudaFreeHost(ctx->tl_geom_host);
+  for (cudaEvent_t e : ctx->kt_ev)
+    if (e) cudaEventDestroy(e);
   for (int k = 0; k < 2; k++) {
     if (ctx->ring[k]) cudaFreeHost(ctx->ring[k]);
     if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
@@ -154,6 +194,22 @@ int lj_list_invalidate(lj_ctx* ctx) {
 
 const char* lj_last_error_string(lj_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int64_t lj_launch_count(lj_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lj_kernel_timing(lj_ctx* ctx, int enable) {
+  LJ_ENTER(ctx);
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  if (enable) { kt_fold_all(ctx); ctx->kt_ms = 0.0; ctx->kt_launches = 0; }
+  ctx->kt_on = enable != 0;
+  return LJ_OK;
+}
+int lj_kernel_timing_read(lj_ctx* ctx, double* total_ms_out, int64_t* launches_out) {
+  LJ_ENTER(ctx);
+  if (!ctx) return LJ_ERR_BAD_ARG;
+  kt_fold_all(ctx);
+  if (total_ms_out) *total_ms_out = ctx->kt_ms;
+  if (launches_out) *launches_out = ctx->kt_launches;
+  return LJ_OK;
+}
 void* lj_ctx_stream(lj_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int lj_device_sm_count(lj_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 

@@ -140,6 +140,37 @@ def test_config_C_measure_is_the_bench_e2e_call(ctx, torch, sysC):
     assert np.abs(ph[:, :3] - s["p"]).max() / s["scale"] < TOL_FP64
 
 
+def test_config_C_kernel_timing_counts_the_dominant_kernel_alone(ctx, torch, sysC):
+    """lj_kernel_timing (the roofline leg of bench.py): one event pair per launch of lj_celltile_force, its
+    summed duration below the time of the whole loop (which also permutes the positions every step), nothing
+    recorded for per-row launches, under a stream capture or once switched off; results unchanged."""
+    s = sysC
+    qd = _aos4(torch, s["q"])
+    pl = ctx.makepair(qd, tiles=True)
+    pd = torch.zeros_like(qd)
+    ctx.force_loop(qd, pd, pl, loop=3, variant="celltile")            # warm
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream()
+    pd.zero_()
+    ctx.kernel_timing(True)
+    e0.record(st)
+    ctx.force_loop(qd, pd, pl, loop=100, variant="celltile")          # more launches than event pairs in the ring
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms, n = ctx.kernel_timing_read()
+    assert n == 100 and 0.0 < ms < e0.elapsed_time(e1)
+    assert ms / n > 0.05                                              # a 1M-atom force step is not microseconds
+    ctx.force_loop(qd, pd.clone(), pl, loop=2, variant="subwarp", group=8)      # not the dominant kernel
+    ctx.force_loop(qd, pd.clone(), pl, loop=4, variant="celltile", use_graph=True)  # captured launches are skipped
+    torch.cuda.synchronize()
+    assert ctx.kernel_timing_read()[1] == 100 + 1                     # (+ the graph path's warm launch outside the capture)
+    ctx.kernel_timing(False)
+    ctx.force_loop(qd, pd.clone(), pl, loop=2, variant="celltile")
+    assert ctx.kernel_timing_read()[1] == 101
+    assert np.abs(pd.cpu().numpy()[:, :3] - s["p"]).max() / s["scale"] < TOL_FP64
+
+
 # ------------------------------------------------------------------------ configs A and B through the cell-tile kernel
 @pytest.mark.parametrize("rho,gold", [(0.5, "density0.5.dat"), (1.0, "density1.dat")])
 @pytest.mark.parametrize("layout", ["aos4", "aos3", "soa"])
