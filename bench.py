@@ -19,7 +19,9 @@ per second = (list entries consumed per step) * steps / time.
               / mean launch duration measured live with CUDA events; peak from
              MEASURED_PEAKS.json.
   cpu_baseline  the REAL reference (cpu_ref/force_soa.cpp via oracle/_ref) on this box's host,
-             1 core (the reference is serial), on a bounded sample (rho=1.0, L=50).
+             1 core (the reference is serial), on a bounded sample (the workload's density, L=50).
+  config     the workload as a function of the command line alone (bench_config): `--impl reference`
+             prints the same `config` and states the bounded sample it timed in `sample`.
 
 With N > 1 (torchrun) the lattice is split into z-slabs, one per rank; ghost positions are
 exchanged every step over NVLink (see lj_gpu_b200/decomp.py) and value aggregates all ranks.
@@ -40,6 +42,35 @@ sys.path.insert(0, ROOT)
 REBUILD_EVERY = 20
 METRIC = "pair_interactions_per_s"
 UNIT = "pairs/s"
+CONFIG5_DENSITY = 0.8   # BASELINE config 5 (the N > 1 workload): FCC rho = 0.8, 320 cells per side
+
+
+def fcc_cells(density, L):
+    """init() of the reference driver (cuda/force_cuda.cu:47-94, lj_host.cpp): n = int(L / s) cells per
+    side with s = (rho / 4)^(-1/3), four atoms per cell."""
+    s = 1.0 / (density * 0.25) ** (1.0 / 3.0)
+    n = int(L / s)
+    return n, 4 * n ** 3
+
+
+def bench_config(args, n_gpus):
+    """`config` of the JSON line: the WORKLOAD, a function of the command line alone, so that both arms
+    (`--impl cuda` and `--impl reference`) name the same one.  What a run measured on it (pairs per step,
+    slab sizes, the kernel AUTO picked, the bounded sample the CPU arm ran) is stated outside `config`."""
+    if n_gpus <= 1:
+        n, pn = fcc_cells(args.density, args.L)
+        return {"workload": "synthetic FCC lattice N=%d (%d cells/side) rho=%.1f cutoff=3.0 search=3.3, full "
+                            "(directed) neighbour list, one force step per step, list rebuild every %d steps" % (
+                                pn, n, args.density, REBUILD_EVERY),
+                "l2": "inputs larger than L2 (the neighbour list alone, 4 B per directed pair, see l2_detail)",
+                "rebuild_every": REBUILD_EVERY}
+    cells5 = int(os.environ.get("LJ_BENCH_CELLS", "320"))     # 320 -> N = 131,072,000
+    return {"workload": "BASELINE config 5: synthetic FCC lattice N=%d (%d cells/side) rho=%.1f cutoff=3.0 "
+                        "search=3.3, full (directed) neighbour list, %d z-slabs, ghost positions exchanged every "
+                        "step, list rebuild every %d steps" % (4 * cells5 ** 3, cells5, CONFIG5_DENSITY, n_gpus,
+                                                               REBUILD_EVERY),
+            "parallelism": "z-slab x%d" % n_gpus, "l2": "inputs larger than L2",
+            "rebuild_every": REBUILD_EVERY}
 
 
 def measured_peak_gbs():
@@ -128,12 +159,13 @@ def roofline_traffic(prec):
 
 
 # ----------------------------------------------------------------------------- reference arm
-def cpu_reference_sample(steps_force=20, L=50.0):
+def cpu_reference_sample(steps_force=20, L=50.0, density=1.0):
     """The real reference on the host: one makepair()+sortpair() and `steps_force` x
-    force_sorted() at rho=1.0, L=50 (N=119,164): one rebuild period of the bench cadence."""
+    force_sorted() at the workload's density in the reference's own box, L=50 (N=119,164 at rho=1.0,
+    97,556 at rho=0.8; its static arrays end at N=400,000): one rebuild period of the bench cadence."""
     from oracle import ljoracle as lo
-    if lo.have_ref(1.0):
-        ref = lo.Ref(1.0, L)
+    if lo.have_ref(density):
+        ref = lo.Ref(density, L)
         t0 = time.perf_counter()
         nop, ptr, lst = ref.makepair()
         t_list = time.perf_counter() - t0
@@ -144,11 +176,11 @@ def cpu_reference_sample(steps_force=20, L=50.0):
         return dict(kind="reference", pn=ref.pn, pairs_half=len(lst), t_list=t_list, t_force=t_force,
                     steps=steps_force, cores=1,
                     what="cpu_ref/force_soa.cpp makepair()+sortpair() once + %d x force_sorted(), "
-                         "rho=1.0 L=50 N=%d, 1 thread (the reference is serial)" % (steps_force, ref.pn))
+                         "rho=%.1f L=50 N=%d, 1 thread (the reference is serial)" % (steps_force, density, ref.pn))
     # prebuilt reference missing: fall back to the C restatement of the same loops
     import numpy as np
     o = lo.Oracle()
-    q = o.init_fcc(1.0, L)
+    q = o.init_fcc(density, L)
     o.set_num_threads(1)
     t0 = time.perf_counter()
     nop, ptr, lst = o.makepair(q, full=False, brute=True)
@@ -159,8 +191,8 @@ def cpu_reference_sample(steps_force=20, L=50.0):
     t_force = time.perf_counter() - t0
     return dict(kind="port", pn=len(q), pairs_half=len(lst), t_list=t_list, t_force=t_force,
                 steps=steps_force, cores=1,
-                what="oracle/lj_oracle.c brute-force makepair once + %d x force_sorted, rho=1.0 L=50 "
-                     "N=%d, 1 thread" % (steps_force, len(q)))
+                what="oracle/lj_oracle.c brute-force makepair once + %d x force_sorted, rho=%.1f L=50 "
+                     "N=%d, 1 thread" % (steps_force, density, len(q)))
 
 
 def cpu_restatement_config_c(q, nop, ptr, lst):
@@ -236,7 +268,8 @@ def run_reference(args):
     # reference's O(N^2) makepair takes ~15 s on the sample, so it is timed ONCE and charged per
     # scheduled rebuild; the force loop is timed on min(K, 40) steps and scaled.
     k_force = max(1, min(args.steps, 40))
-    r = cpu_reference_sample(k_force)
+    density = args.density if args.gpus <= 1 else CONFIG5_DENSITY
+    r = cpu_reference_sample(k_force, density=density)
     per_step = r["t_force"] / r["steps"]
     builds = (args.steps + REBUILD_EVERY - 1) // REBUILD_EVERY
     total = per_step * args.steps + builds * r["t_list"]
@@ -245,11 +278,15 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": "FCC rho=1.0 cutoff=3.0 search=3.3 full-list-equivalent pairs, "
-                               "list rebuild every 20 steps; CPU sample L=50 N=%d" % r["pn"],
-                   "rebuild_every": REBUILD_EVERY},
+        "higher_is_better": True, "scaling": "weak" if args.gpus <= 1 else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "gpu_launches": 0,
+        # the other arm's workload; what was timed here is a bounded SAMPLE of it (same lattice, density, cutoff,
+        # search length and cadence in the reference's own L=50 box), stated in `sample` / cpu_baseline.sample
+        "config": bench_config(args, args.gpus),
+        "sample": "L=50 box of the same lattice: N=%d, %d directed pairs per step (full-list equivalent of the "
+                  "reference's half list); pairs/s of the sample stands for the workload (the reference's O(N^2) "
+                  "makepair would cost more per particle at the full size, so this favours the reference)" % (
+                      r["pn"], pairs_directed),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["what"] + "; force loop timed on %d steps (%.3f s), makepair timed "
                                    "once (%.2f s) and charged %d times" % (r["steps"], r["t_force"], r["t_list"], builds),
@@ -274,7 +311,7 @@ def run_cuda(args):
     if world > 1:
         from lj_gpu_b200 import decomp
         return decomp.bench_decomposed(args, METRIC, UNIT, REBUILD_EVERY, ClockSampler, measured_peak_gbs,
-                                       algorithmic_bytes, cpu_reference_sample)
+                                       algorithmic_bytes, cpu_reference_sample, bench_config)
     torch.cuda.set_device(local)
     ctx = LJContext(local)
     stream = torch.cuda.current_stream()
@@ -494,16 +531,21 @@ def run_cuda(args):
     achieved = bytes_force / (ms_roof * 1e-3) / 1e9
     traffic, traffic_src = roofline_traffic(args.prec)
 
+    cfg = bench_config(args, 1)
+    if fcc_cells(args.density, args.L)[1] != pn:   # cannot happen: lj_init_fcc is the same arithmetic
+        cfg["workload"] += " [generator returned N=%d]" % pn
+    if 4 * P <= 126e6:   # a small --L: the statement in `config` would be false
+        cfg["l2"] = "NOT larger than L2 (list %.0f MB) and no flush: not a valid bench size" % (4 * P / 1e6)
     out = {
         "metric": METRIC, "value": P * K / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.prec == "fp64" else "f32-mixed",
         "data": "synthetic",
-        "config": {"workload": "synthetic FCC lattice N=%d rho=%.1f cutoff=3.0 search=3.3, full list %d "
-                               "directed pairs, on-GPU list rebuild every %d steps" % (pn, args.density, P, REBUILD_EVERY),
-                   "layout": "aos_double4", "variant": args.variant, "group": args.group,
-                   "l2": "inputs larger than L2 (list %.0f MB per step vs 126 MB L2)" % (4 * P / 1e6),
-                   "rebuild_every": REBUILD_EVERY},
+        "config": cfg,
+        "pairs_per_step": int(P),
+        "l2_detail": "neighbour list %.0f MB per step vs 126 MB L2" % (4 * P / 1e6),
+        "kernel_selection": {"layout": "aos_double4", "variant": args.variant, "group": args.group,
+                             "list_build": "on the GPU (lj_build_list)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m.h2d_bytes / K,
@@ -536,7 +578,7 @@ def run_cuda(args):
     out["reference_gpu"] = ref_gpu
     out["config5_single_gpu"] = cfg5
     if not args.no_cpu:
-        r = cpu_reference_sample(20)
+        r = cpu_reference_sample(20, density=args.density if args.density in (0.5, 0.8, 1.0) else 1.0)
         t = r["t_force"] + r["t_list"]
         out["cpu_baseline"] = {
             "value": 2 * r["pairs_half"] * r["steps"] / t, "unit": UNIT, "cores": r["cores"],

@@ -395,7 +395,7 @@ def _measure_system(system, K, W, rebuild_every, fkw, ClockSampler=None):
 
 
 def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_peak_gbs, algorithmic_bytes,
-                     cpu_reference_sample=None):
+                     cpu_reference_sample=None, bench_config=None):
     """bench.py body for N > 1 (torchrun).  Main line: BASELINE config 5 -- FCC rho = 0.8, 320 cells per
     side, N = 131,072,000 -- split into N z-slabs: STRONG scaling (the total work is fixed).  Side
     block: the weak-scaling run of round 1 (~1.0e6 particles per GPU at the bench density)."""
@@ -469,12 +469,16 @@ def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_p
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.prec == "fp64" else "f32-mixed", "data": "synthetic",
-            "config": {"workload": "BASELINE config 5: synthetic FCC lattice N=%d (%d cells/side) rho=%.1f cutoff=3.0 "
-                                   "search=3.3, %d z-slabs of %d lattice layers, %d directed pairs, on-GPU list rebuild "
-                                   "every %d steps, ghost positions exchanged every step (%s)" % (
-                                       pn5, cells5, density5, world, slab_layers, P, rebuild_every, halo_used),
-                       "parallelism": "z-slab x%d" % world, "l2": "inputs larger than L2",
-                       "rebuild_every": rebuild_every, "setup_seconds_generator_and_first_build": setup_s},
+            # the workload as a function of the command line (bench.py: bench_config, shared with the reference
+            # arm); what this run measured on it is stated under "decomposition"
+            "config": bench_config(args, world) if bench_config else {
+                "workload": "BASELINE config 5: synthetic FCC lattice N=%d (%d cells/side) rho=%.1f cutoff=3.0 "
+                            "search=3.3" % (pn5, cells5, density5),
+                "parallelism": "z-slab x%d" % world, "l2": "inputs larger than L2", "rebuild_every": rebuild_every},
+            "pairs_per_step": int(P),
+            "decomposition": {"particles": int(pn5), "slabs": world, "lattice_layers_per_slab": int(slab_layers),
+                              "halo": halo_used, "list_build": "on the GPU (lj_build_list), per slab",
+                              "setup_seconds_generator_and_first_build": setup_s},
             "gpu_launches": r["launches"], "clocks": r["clocks"],
             "halo": {"mode": halo_used, "schedule": sched, "ms_step_overlap": r["ms_overlap"],
                      "ms_step_serial": r["ms_serial"], "ms_halo_alone": r["ms_halo"],
@@ -498,7 +502,7 @@ def bench_decomposed(args, metric, unit, rebuild_every, ClockSampler, measured_p
         }
         if cpu_reference_sample is not None and not getattr(args, "no_cpu", False):
             try:
-                c = cpu_reference_sample(20)
+                c = cpu_reference_sample(20, density=density5)
                 t = c["t_force"] + c["t_list"]
                 out["cpu_baseline"] = {"value": 2 * c["pairs_half"] * c["steps"] / t, "unit": unit, "cores": c["cores"],
                                        "kind": c["kind"], "sample": c["what"],

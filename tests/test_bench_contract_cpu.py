@@ -32,6 +32,39 @@ def test_reference_arm_prints_the_contract_line():
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and d["config"]["rebuild_every"] == 20
+    # both arms name the SAME workload: `config` is a function of the command line alone (bench_config), the
+    # bounded sample the CPU arm timed is stated beside it
+    assert d["config"] == _bench().bench_config(_Args(), 1)
+    assert "N=1000188 (63 cells/side) rho=1.0" in d["config"]["workload"]
+    assert "N=119164" in d["sample"] and d["scaling"] == "weak"
+
+
+class _Args:
+    density, L = 1.0, 100.1
+
+
+def _bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_bench_config_is_the_generator_arithmetic():
+    b = _bench()
+    assert b.fcc_cells(1.0, 100.1) == (63, 1000188)      # BASELINE config 3
+    assert b.fcc_cells(1.0, 50.0) == (31, 119164) and b.fcc_cells(0.5, 50.0) == (25, 62500)   # the reference's own boxes
+    c = b.bench_config(_Args(), 8)
+    assert "N=131072000 (320 cells/side) rho=0.8" in c["workload"] and c["parallelism"] == "z-slab x8"
+
+
+def test_reference_arm_at_n_gpus_names_config_5_and_samples_its_density():
+    lines = run_bench(["--gpus", "2", "--steps", "2", "--warmup", "1"], env={"RANK": "0", "WORLD_SIZE": "2"})
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["config"] == _bench().bench_config(_Args(), 2) and d["scaling"] == "strong" and d["n_gpus"] == 2
+    assert "rho=0.8" in d["cpu_baseline"]["sample"] and "N=97556" in d["sample"]
 
 
 def test_reference_arm_other_ranks_stay_silent():
